@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the authoring container (needs /root/reference):
+    python -m oracle.make_golden
+The reference modules are imported through oracle/ref_shim.py, loaded with the deterministic
+fixture weights of oracle/semivl_oracle.fixture_state_dict and run on seeded inputs; the script
+records inputs + reference outputs.  Weights are NOT stored (regenerated from the seed).
+The training-iteration fixture drives the reference's own model.forward / forward_maskclip /
+utils.train_utils functions in the order of semivl.py:224-323 (that loop lives under
+`if __name__ == '__main__'` and cannot be imported).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+from oracle import semivl_oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TEXT_DIR = os.path.join(ROOT, "semivl_b200", "configs", "_base_", "datasets", "text_embedding")
+
+
+def sample_idx(numel, k=64):
+    g = torch.Generator().manual_seed(numel % 65521 + 17)
+    return torch.randint(0, numel, (min(k, numel),), generator=g)
+
+
+def grad_summary(named_grads):
+    names, norms, samples = [], [], []
+    for n, g in named_grads:
+        names.append(n)
+        norms.append(g.double().norm().item())
+        s = g.flatten()[sample_idx(g.numel())].float().numpy()
+        samples.append(np.pad(s, (0, 64 - len(s))))
+    return dict(grad_names=np.array(names), grad_norms=np.array(norms), grad_samples=np.stack(samples))
+
+
+def synth_batch(b, crop, nclass, seed):
+    """Synthetic SemiVL batch: randn images, labels with a 255 block, pad-strip ignore masks, cutmix boxes."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda: torch.randn(b, 3, crop, crop, generator=g)
+    batch = dict(img_x=r(), img_w=r(), img_s1=r(), img_s2=r(), img_w_other=r(), img_s1_other=r(), img_s2_other=r())
+    mask_x = torch.randint(0, nclass, (b, crop, crop), generator=g)
+    mask_x[:, : crop // 8, : crop // 3] = 255
+    ign = torch.zeros(b, crop, crop, dtype=torch.long)
+    ign[:, -crop // 10:, :] = 255
+    ign_o = torch.zeros(b, crop, crop, dtype=torch.long)
+    ign_o[:, :, -crop // 12:] = 255
+    def box(frac):
+        m = torch.zeros(b, crop, crop)
+        h = int(crop * frac)
+        m[:, crop // 5: crop // 5 + h, crop // 4: crop // 4 + h] = 1
+        return m
+    batch.update(mask_x=mask_x, ignore_mask=ign, ignore_mask_other=ign_o, mix1=box(0.5), mix2=box(0.3))
+    return batch
+
+
+def build(crop, nclass=21, dataset="pascal", text="single", mcc_text=None):
+    cfg = ref_shim.default_cfg(dataset=dataset, nclass=nclass, crop_size=crop, text=text, mcc_text=mcc_text)
+    m = ref_shim.build_reference_model(cfg)
+    mc = O.ModelCfg(img_size=crop, num_classes=nclass)
+    sd = O.fixture_state_dict(O.param_shapes(mc), seed=0)
+    m.load_state_dict(sd)
+    return m, mc, sd
+
+
+def forward_fixture(name, crop, b, seed, nclass=21):
+    m, mc, sd = build(crop, nclass)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(b, 3, crop, crop, generator=g)
+    lab = torch.randint(0, nclass, (b, crop, crop), generator=g)
+    lab[:, : crop // 7, : crop // 2] = 255
+    with ref_shim.in_reference_cwd():
+        m.train()
+        feats_all = m.extract_feat(img)
+        feats, glob = feats_all[0]
+        low = m.decode_head.forward(feats_all)
+        y = m(img)
+        loss = F.cross_entropy(y, lab, ignore_index=255)
+        loss.backward()
+        mcl = m.forward_maskclip(img, 0.9)
+        # maskclip confidences are degenerate (all 255) at fixture scale: also record at a low threshold
+        mcl_lo = m.forward_maskclip(img, 1.0 / nclass + 1e-3)
+    out = dict(img=img.numpy(), label=lab.numpy().astype(np.int16), crop=crop, nclass=nclass, seed=seed,
+               logits_lowres=low.detach().numpy(), emb=feats[-1].detach().numpy(),
+               feat0_sample=feats[0].detach().flatten()[sample_idx(feats[0].numel(), 4096)].numpy(),
+               feat1_sample=feats[1].detach().flatten()[sample_idx(feats[1].numel(), 4096)].numpy(),
+               global_emb=glob.detach().numpy(), loss=np.float64(loss.item()),
+               argmax=y.argmax(1).numpy().astype(np.uint8),
+               logits_sample=y.detach().flatten()[sample_idx(y.numel(), 8192)].numpy(),
+               logits_absmax=np.float64(y.abs().max().item()),
+               maskclip=mcl.numpy().astype(np.uint8), maskclip_lo=mcl_lo.numpy().astype(np.uint8),
+               maskclip_lo_thresh=np.float64(1.0 / nclass + 1e-3))
+    out.update(grad_summary([(n, q.grad) for n, q in m.named_parameters() if q.grad is not None]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "loss", loss.item(), "ngrads", len(out["grad_names"]))
+
+
+def step_fixture(name, crop, b, seed, nclass=21):
+    """semivl.py:224-323 driven on the reference model with injected dropout2d masks."""
+    m, mc, sd = build(crop, nclass)
+    import model.builder as ref_builder
+    from utils.train_utils import confidence_weighted_loss, cutmix_img_, cutmix_mask
+    batch = synth_batch(b, crop, nclass, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    drop_masks = [(torch.rand(2 * b, c, 1, 1, generator=g) >= 0.5).float() for c in (768, 768, 512)]
+    hp = dict(conf_thresh=1.0 / nclass + 2e-3, conf_mode="pixelwise", mcc_conf_thresh=1.0 / nclass + 1e-3,
+              mcc_loss_reduce="mean_all", mcc_lambda=0.07)
+    cfgd = dict(conf_mode=hp["conf_mode"], conf_thresh=hp["conf_thresh"])
+
+    calls = {"i": 0}
+    real_dropout2d = F.dropout2d
+
+    def fake_dropout2d(f, p=0.5, training=True, inplace=False):
+        mk = drop_masks[calls["i"] % 3]
+        calls["i"] += 1
+        return f * mk / (1 - p)
+    ref_builder.F.dropout2d = fake_dropout2d
+    try:
+        with ref_shim.in_reference_cwd():
+            bt = {k: v.clone() for k, v in batch.items()}
+            cutmix_img_(bt["img_s1"], bt["img_s1_other"], bt["mix1"])
+            cutmix_img_(bt["img_s2"], bt["img_s2_other"], bt["mix2"])
+            with torch.no_grad():
+                m.eval()
+                pred_w_other = m(bt["img_w_other"]).detach()
+                conf_w_other, mask_w_other = pred_w_other.softmax(dim=1).max(dim=1)
+                mclip = m.forward_maskclip(torch.cat((bt["img_w"], bt["img_w_other"])), conf_tresh=hp["mcc_conf_thresh"])
+                mclip, mclip_other = mclip.split([b, b])
+                mclip[bt["ignore_mask"] == 255] = 255
+                mclip_other[bt["ignore_mask_other"] == 255] = 255
+            m.train()
+            preds, preds_fp = m(torch.cat((bt["img_x"], bt["img_w"])), need_fp=True)
+            pred_x, pred_w = preds.chunk(2)
+            _, pred_w_fp = preds_fp.chunk(2)
+            pred_s1, pred_s2 = m(torch.cat((bt["img_s1"], bt["img_s2"]))).chunk(2)
+            pred_w = pred_w.detach()
+            conf_w, mask_w = pred_w.softmax(dim=1).max(dim=1)
+            mix1, mix2 = bt["mix1"], bt["mix2"]
+            mm1, mm2 = cutmix_mask(mask_w, mask_w_other, mix1), cutmix_mask(mask_w, mask_w_other, mix2)
+            cm1, cm2 = cutmix_mask(conf_w, conf_w_other, mix1), cutmix_mask(conf_w, conf_w_other, mix2)
+            im1 = cutmix_mask(bt["ignore_mask"], bt["ignore_mask_other"], mix1)
+            im2 = cutmix_mask(bt["ignore_mask"], bt["ignore_mask_other"], mix2)
+            mc1, mc2 = cutmix_mask(mclip, mclip_other, mix1), cutmix_mask(mclip, mclip_other, mix2)
+            cu = torch.nn.CrossEntropyLoss(reduction="none")
+            cmc = torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none")
+            loss_x = F.cross_entropy(pred_x, bt["mask_x"], ignore_index=255)
+            loss_s1 = confidence_weighted_loss(cu(pred_s1, mm1), cm1, im1, cfgd)
+            loss_s2 = confidence_weighted_loss(cu(pred_s2, mm2), cm2, im2, cfgd)
+            loss_fp = confidence_weighted_loss(cu(pred_w_fp, mask_w), conf_w, bt["ignore_mask"], cfgd)
+            l_mc1 = cmc(pred_s1, mc1).sum() / im1.numel()
+            l_mc2 = cmc(pred_s2, mc2).sum() / im2.numel()
+            l_mcf = cmc(pred_w_fp, mclip).sum() / bt["ignore_mask"].numel()
+            lam = hp["mcc_lambda"]
+            loss = (loss_x + loss_s1 * 0.25 + loss_s2 * 0.25 + loss_fp * 0.5) / 2.0
+            loss = loss + l_mc1 * 0.25 * lam + l_mc2 * 0.25 * lam + l_mcf * 0.5 * lam
+            loss.backward()
+    finally:
+        ref_builder.F.dropout2d = real_dropout2d
+    out = {k: (v.numpy().astype(np.int16) if v.dtype == torch.long else v.numpy()) for k, v in batch.items()}
+    out.update({f"drop_mask{i}": d.numpy() for i, d in enumerate(drop_masks)})
+    out.update({f"hp_{k}": np.array(v) for k, v in hp.items()})
+    out.update(crop=crop, nclass=nclass, seed=seed, b=b, loss=np.float64(loss.item()),
+               terms=np.array([t.item() for t in (loss_x, loss_s1, loss_s2, loss_fp, l_mc1, l_mc2, l_mcf)], dtype=np.float64),
+               conf_frac=np.float64((conf_w >= hp["conf_thresh"]).float().mean().item()),
+               mclip_valid_frac=np.float64((mclip != 255).float().mean().item()),
+               mask_w=mask_w.numpy().astype(np.uint8), mclip=mclip.numpy().astype(np.uint8))
+    out.update(grad_summary([(n, q.grad) for n, q in m.named_parameters() if q.grad is not None]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "loss", loss.item(), "terms", out["terms"], "conf_frac", out["conf_frac"], "mclip_valid", out["mclip_valid_frac"])
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    forward_fixture("fwd_c64_b2", 64, 2, seed=11)          # tiny: every op, multiple of 16
+    forward_fixture("fwd_c72_b1", 72, 1, seed=12)          # corner pad + bicubic pos-embed resize (maskclip_vit.py:448-459)
+    forward_fixture("fwd_c224_b1", 224, 1, seed=13)        # BASELINE config 1
+    step_fixture("step_c64_b1", 64, 1, seed=21)            # full SemiVL iteration (semivl.py:224-323)
+    step_fixture("step_c96_b2", 96, 2, seed=22)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+/* semivl_b200 -- C ABI of the B200-native SemiVL hot path.
+ *
+ * Drop-in boundary.  The reference (google-research/semivl) is pure Python/PyTorch and has no FFI of
+ * its own; every entry point below replaces the stock ATen/cuDNN/cuBLAS dispatch that
+ * the reference makes at the cited file:line.  Conventions (last row):
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless stated;
+ *   - the caller owns every buffer; kernels are asynchronous on the passed cudaStream_t (as void*);
+ *   - return 0 on success, negative svl_status on failure; svl_last_error() gives the message;
+ *   - no internal allocation, no global state beyond the resolved driver entry point.
+ * Built for sm_100a only (tcgen05 / TMEM / TMA); there is no fallback path.
+ */
+#ifndef SEMIVL_B200_H_
+#define SEMIVL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SVL_OK = 0,
+  SVL_ERR_INVALID = -1,  /* bad argument / unsupported shape */
+  SVL_ERR_CUDA = -2,     /* CUDA runtime / driver error */
+  SVL_ERR_ARCH = -3      /* not running on sm_100 */
+} svl_status;
+
+/* Storage types of activation tensors.
+ * SVL_BF16X2 is the precise-mode operand format: value = hi + lo (two bf16), hi at [row*ld + col] and lo at
+ * [row*ld + ld/2 + col]; ld is therefore twice the logical row width.  A contraction over split operands is
+ * issued as three tensor-core taps (hi*hi + hi*lo + lo*hi) and reproduces an fp32 contraction to ~2^-17. */
+typedef enum { SVL_F32 = 0, SVL_BF16 = 1, SVL_BF16X2 = 2 } svl_dtype;
+
+const char* svl_last_error(void);
+int svl_version(void);
+/* 0 if the current device is sm_100 and the TMA driver entry point resolved. */
+int svl_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core contraction engine (tcgen05.mma, TMEM accumulators, TMA-staged SWIZZLE_128B tiles).
+ *
+ *   D[m, n] = epilogue( sum_{t < num_taps} sum_{k < k_per_tap} A_t[m, k] * B_t[n, k] )
+ *
+ * One engine covers: every nn.Linear of the ViT / class-attention blocks (maskclip_vit.py:110-144 via
+ * mmcv MultiheadAttention/FFN), the patch-embedding conv as an im2col GEMM (maskclip_vit.py:495), the
+ * CLIP projection (maskclip_vit.py:552), the text-similarity einsum (vlg_head.py:217), all 1x1 / 3x3 /
+ * dilated convs and the 2x2 transposed convs of the VLG head as implicit GEMMs with one tap per filter
+ * position (vlg_head.py:84-137,169,181-190) and their data gradients (same engine, mirrored taps,
+ * transposed weights).  A tap selects a pixel shift of A (conv), a column offset into A and a
+ * (row, column) offset into B; precise mode (BF16X2 operands) triples the taps.
+ * ---------------------------------------------------------------------------------------------- */
+#define SVL_MAX_TAPS 32
+
+typedef enum { SVL_ACT_NONE = 0, SVL_ACT_GELU = 1, SVL_ACT_RELU = 2 } svl_act;
+typedef enum { SVL_OUT_LINEAR = 0, SVL_OUT_CONVT2X2 = 1 } svl_out_mode;
+
+typedef struct {
+  /* ---- A operand: activations, bf16, K-major (channels / features contiguous) ---- */
+  const void* a;
+  int a_conv;           /* 0: 2-D [m, lda] row-major.  1: NHWC image batch [nb, h, w, lda] (m = nb*h*w) */
+  int64_t m;            /* output rows */
+  int64_t lda;          /* elements per row / pixel */
+  int64_t a_cols;       /* valid columns from `a` (TMA inner extent); 0 = lda */
+  int nb, h, w;         /* a_conv geometry */
+  /* ---- B operand: weights, bf16, [b_rows, ldb], K contiguous ---- */
+  const void* b;
+  int64_t b_rows;
+  int64_t ldb;
+  /* ---- contraction ---- */
+  int n;                /* output columns */
+  int k_per_tap;        /* contraction length per tap, multiple of 16 */
+  int num_taps;
+  int tap_dy[SVL_MAX_TAPS], tap_dx[SVL_MAX_TAPS];   /* a_conv: input pixel offset per tap (zero padding outside the image) */
+  int tap_a_koff[SVL_MAX_TAPS];                     /* column offset into A per tap */
+  int tap_b_row[SVL_MAX_TAPS];                      /* row offset into B per tap (added to the output column) */
+  int tap_b_col[SVL_MAX_TAPS];                      /* column offset into B per tap (added to k) */
+  /* ---- epilogue:  v = alpha*acc + bias[col] + row_bias[(row / row_bias_div) * row_bias_ld + col]
+   *                 preact_out <- v ; v = act(v) ; v *= act'(dact_src) ; v += residual ; (v += out) ; out <- v ---- */
+  void* out;            /* [m, ldc] */
+  int out_dtype;        /* svl_dtype */
+  int64_t ldc;
+  int out_mode;         /* svl_out_mode; CONVT2X2: row = (img, y, x) of an [*, out_h, out_w] grid, column block q = col / (n/4)
+                           scatters to pixel (2y + q/2, 2x + q%2) of an NHWC [*, 2*out_h, 2*out_w, ldc] tensor, channel col % (n/4) */
+  int out_h, out_w;
+  float alpha;          /* 0 is treated as 1 */
+  const float* bias;    /* [n] or NULL */
+  const float* row_bias; int64_t row_bias_div; int64_t row_bias_ld;
+  int act;              /* svl_act */
+  void* preact_out; int preact_dtype; int64_t ld_preact;   /* F32 or BF16, or NULL */
+  const void* dact_src; int dact_dtype; int dact_kind; int64_t ld_dact;
+                        /* multiply by act'(src): GELU -> src is the saved pre-activation; RELU -> src is the saved OUTPUT, factor (src > 0) */
+  const void* residual; int res_dtype; int64_t ldres;      /* F32 or BF16, or NULL */
+  int accumulate;       /* 1: out += result (F32 out only) */
+  /* ---- tuning ---- */
+  int block_n;          /* 0 = auto */
+} svl_gemm_desc;
+
+int svl_gemm(const svl_gemm_desc* d, void* stream);
+
+/* Weight gradient on the same tensor cores, operands read MN-major straight from their forward layouts:
+ *   dw[slot*slot_stride + i*ld_dw + j] += alpha * sum_{taps t of slot} sum_rows DY[row, dy_koff_t + i] * X[shift_t(row), x_koff_t + j]
+ * Split-K over row blocks, partial tiles reduced with red.global.add.f32 (caller zero-fills dw or accumulates across calls).
+ * replaces: autograd wgrad of nn.Linear / nn.Conv2d / nn.ConvTranspose2d on the hot path (semivl.py:327). */
+typedef struct {
+  const void* dy; int64_t ld_dy; int64_t dy_cols;   /* bf16 [rows, ld_dy]; dy_cols = valid columns from `dy` (0 = ld_dy) */
+  const void* x;  int64_t ld_x;  int64_t x_cols;    /* bf16 [rows, ld_x] or NHWC [nb,h,w,ld_x] */
+  int conv;                                         /* 1: both operands are NHWC images and taps shift x */
+  int64_t rows; int nb, h, w;
+  int m;                                            /* output rows  (dy channels) */
+  int n;                                            /* output columns per slot (x channels) */
+  int num_taps;
+  int tap_dy[SVL_MAX_TAPS], tap_dx[SVL_MAX_TAPS];   /* x is read at pixel + (dy, dx), zero outside the image */
+  int tap_dy_koff[SVL_MAX_TAPS], tap_x_koff[SVL_MAX_TAPS];
+  int tap_slot[SVL_MAX_TAPS];                       /* output slot per tap; ascending, taps of one slot contiguous */
+  float* dw; int64_t ld_dw; int64_t slot_stride;
+  float alpha;                                      /* 0 is treated as 1 */
+  int splits;                                       /* 0 = auto */
+} svl_wgrad_desc;
+
+int svl_wgrad(const svl_wgrad_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMIVL_B200_H_ */

@@ -1,0 +1,366 @@
+// Tensor-core contraction engine: persistent, warp-specialised tcgen05 GEMM with tap-based implicit convolution.
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
+//   warps 2..5  : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global)
+//
+// Accumulators are double-buffered in TMEM (2 x block_n columns) so the epilogue of tile i overlaps the main
+// loop of tile i+1.  Tile = 128 output rows x block_n columns, K step 64 (one 128-byte swizzle row).
+// In conv mode the 128 rows of a tile are a (bn images x bh rows x bw columns) box of an NHWC tensor, fetched with a
+// 4-D tensor map; a filter tap only shifts the box coordinates and TMA's out-of-bounds zero fill is the padding.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace svl {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+  // geometry
+  int a_conv;
+  int64_t m;
+  int nb, h, w;
+  int bw, bh, bn;                  // conv tile box
+  int tiles_x, tiles_y;            // conv tiles per image row / column-of-tiles
+  int num_m_tiles, num_n_tiles;
+  int n, block_n, k_per_tap, num_taps;
+  int stages, tmem_cols;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes;
+  int tap_dy[SVL_MAX_TAPS], tap_dx[SVL_MAX_TAPS], tap_a_koff[SVL_MAX_TAPS], tap_b_row[SVL_MAX_TAPS], tap_b_col[SVL_MAX_TAPS];
+  // epilogue
+  void* out; int out_dtype; int64_t ldc; int out_mode; int out_h, out_w;
+  float alpha; const float* bias; const float* row_bias; int64_t row_bias_div, row_bias_ld;
+  int act; void* preact_out; int preact_dtype; int64_t ld_preact;
+  const void* dact_src; int dact_dtype; int dact_kind; int64_t ld_dact;
+  const void* residual; int res_dtype; int64_t ldres;
+  int accumulate;
+};
+
+// global row index of tile row r, or -1 when the row is padding
+__device__ __forceinline__ int64_t tile_row_to_global(const GemmParams& p, int m_tile, int r) {
+  if (!p.a_conv) {
+    int64_t g = (int64_t)m_tile * BM + r;
+    return g < p.m ? g : -1;
+  }
+  int tx = m_tile % p.tiles_x;
+  int ty = (m_tile / p.tiles_x) % p.tiles_y;
+  int tn = m_tile / (p.tiles_x * p.tiles_y);
+  int ix = r % p.bw, iy = (r / p.bw) % p.bh, in = r / (p.bw * p.bh);
+  int x = tx * p.bw + ix, y = ty * p.bh + iy, img = tn * p.bn + in;
+  if (in >= p.bn || x >= p.w || y >= p.h || img >= p.nb) return -1;
+  return ((int64_t)img * p.h + y) * p.w + x;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x A][stages x B][barriers][tmem ptr]
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + p.stages * p.a_stage_bytes;
+  const uint32_t bar_base = smem_b + p.stages * p.b_stage_bytes;          // 8-byte aligned (stage sizes are multiples of 1024)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 4);
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks_per_tap = (p.k_per_tap + BK - 1) / BK;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+        const int n0 = n_tile * p.block_n;
+        int cx = 0, cy = 0, cn = 0;
+        if (p.a_conv) {
+          cx = (m_tile % p.tiles_x) * p.bw;
+          cy = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+          cn = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn;
+        }
+        for (int t = 0; t < p.num_taps; ++t) {
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_tx_bytes + p.b_stage_bytes);
+            const uint32_t sa = smem_a + stage * p.a_stage_bytes, sb = smem_b + stage * p.b_stage_bytes;
+            if (p.a_conv)
+              ptx::tma_load_4d(sa, &tmA, full_bar(stage), p.tap_a_koff[t] + kb * BK, cx + p.tap_dx[t], cy + p.tap_dy[t], cn);
+            else
+              ptx::tma_load_2d(sa, &tmA, full_bar(stage), p.tap_a_koff[t] + kb * BK, m_tile * BM);
+            ptx::tma_load_2d(sb, &tmB, full_bar(stage), p.tap_b_col[t] + kb * BK, p.tap_b_row[t] + n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+        uint32_t accum = 0;
+        for (int t = 0; t < p.num_taps; ++t) {
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = smem_a + stage * p.a_stage_bytes, sb = smem_b + stage * p.b_stage_bytes;
+            const uint64_t adesc = ptx::make_smem_desc(sa, 16, 1024), bdesc = ptx::make_smem_desc(sb, 16, 1024);
+            const int nk = min(BK, p.k_per_tap - kb * BK) / 16;
+            for (int kk = 0; kk < nk; ++kk) {
+              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, accum);
+              accum = 1;
+            }
+            ptx::umma_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        ptx::umma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // tile row of this thread
+    const float alpha = p.alpha == 0.f ? 1.f : p.alpha;
+    const int cq = p.out_mode == SVL_OUT_CONVT2X2 ? p.n / 4 : 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      const int n0 = n_tile * p.block_n;
+      const int64_t grow = tile_row_to_global(p, m_tile, r);
+      int64_t ct_base = 0;                  // CONVT2X2: element offset of output pixel (2y, 2x), channel 0
+      if (cq && grow >= 0) {
+        int64_t hw = (int64_t)p.out_h * p.out_w;
+        int64_t img = grow / hw;
+        int y = (int)((grow % hw) / p.out_w), x = (int)(grow % p.out_w);
+        ct_base = ((img * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.ldc;
+      }
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        if (n0 + c0 >= p.n) break;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
+        ptx::tmem_ld_wait();
+        if (grow < 0) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = n0 + c0 + g * 8;
+          const int cnt = min(8, p.n - col);
+          if (cnt <= 0) break;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * alpha;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(p.bias + col + i);
+          }
+          if (p.row_bias) {
+            const float* rb = p.row_bias + (grow / p.row_bias_div) * p.row_bias_ld + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(rb + i);
+          }
+          if (p.preact_out) st8(p.preact_out, p.preact_dtype, grow * p.ld_preact + col, 0, cnt, f);
+          if (p.act == SVL_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = gelu_exact(f[i]);
+          } else if (p.act == SVL_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.dact_src) {
+            float s[8];
+            ld8(p.dact_src, p.dact_dtype, grow * p.ld_dact + col, p.ld_dact / 2, cnt, s);
+            if (p.dact_kind == SVL_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] *= gelu_grad(s[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = s[i] > 0.f ? f[i] : 0.f;
+            }
+          }
+          if (p.residual) {
+            float s[8];
+            ld8(p.residual, p.res_dtype, grow * p.ldres + col, 0, cnt, s);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += s[i];
+          }
+          int64_t off;
+          if (cq) {
+            const int qq = col / cq, cc = col % cq;       // cq % 8 == 0: an 8-group never straddles a quadrant
+            off = ct_base + ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
+          } else {
+            off = grow * p.ldc + col;
+          }
+          if (p.accumulate) {
+            float s[8];
+            ld8(p.out, SVL_F32, off, 0, cnt, s);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += s[i];
+          }
+          st8(p.out, p.out_dtype, off, p.ldc / 2, cnt, f);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int auto_block_n(int n) {
+  if (n <= 256) return (n + 15) / 16 * 16;
+  int best = 256, best_pad = 1 << 30;
+  for (int bn : {256, 192, 128}) {
+    int pad = (n + bn - 1) / bn * bn - n;
+    if (pad < best_pad) { best = bn; best_pad = pad; }
+  }
+  return best;
+}
+
+}  // namespace
+}  // namespace svl
+
+using namespace svl;
+
+extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
+  SVL_CHECK_ARG(d && d->a && d->b && d->out, "svl_gemm: null operand");
+  SVL_CHECK_ARG(d->m > 0 && d->n > 0, "svl_gemm: empty problem m=%lld n=%d", (long long)d->m, d->n);
+  SVL_CHECK_ARG(d->k_per_tap > 0 && d->k_per_tap % 16 == 0, "svl_gemm: k_per_tap=%d must be a positive multiple of 16", d->k_per_tap);
+  SVL_CHECK_ARG(d->num_taps >= 1 && d->num_taps <= SVL_MAX_TAPS, "svl_gemm: num_taps=%d out of range", d->num_taps);
+  SVL_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "svl_gemm: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
+  SVL_CHECK_ARG(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->b & 15) == 0, "svl_gemm: operands must be 16-byte aligned");
+  SVL_CHECK_ARG(d->out_dtype == SVL_F32 || d->out_dtype == SVL_BF16 || d->out_dtype == SVL_BF16X2, "svl_gemm: bad out_dtype");
+  SVL_CHECK_ARG(!d->accumulate || d->out_dtype == SVL_F32, "svl_gemm: accumulate needs an F32 output");
+  if (d->out_mode == SVL_OUT_CONVT2X2)
+    SVL_CHECK_ARG(d->n % 32 == 0 && d->out_h > 0 && d->out_w > 0 && d->m % ((int64_t)d->out_h * d->out_w) == 0,
+                  "svl_gemm: CONVT2X2 needs n %% 32 == 0 and m a multiple of out_h*out_w");
+  if (int rc = svl_check_device()) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_conv = d->a_conv;
+  p.m = d->m;
+  p.n = d->n;
+  p.k_per_tap = d->k_per_tap;
+  p.num_taps = d->num_taps;
+  for (int t = 0; t < d->num_taps; ++t) {
+    p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_a_koff[t] = d->tap_a_koff[t];
+    p.tap_b_row[t] = d->tap_b_row[t]; p.tap_b_col[t] = d->tap_b_col[t];
+  }
+  p.block_n = d->block_n > 0 ? d->block_n : auto_block_n(d->n);
+  SVL_CHECK_ARG(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "svl_gemm: block_n=%d invalid", p.block_n);
+  p.num_n_tiles = (d->n + p.block_n - 1) / p.block_n;
+  const int64_t a_cols = d->a_cols > 0 ? d->a_cols : d->lda;
+
+  CUtensorMap tmA, tmB;
+  if (d->a_conv) {
+    SVL_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0 && (int64_t)d->nb * d->h * d->w == d->m, "svl_gemm: conv geometry does not match m");
+    p.nb = d->nb; p.h = d->h; p.w = d->w;
+    p.bw = d->w < BM ? d->w : BM;
+    p.bh = d->h < BM / p.bw ? d->h : BM / p.bw;
+    p.bn = d->nb < BM / (p.bw * p.bh) ? d->nb : BM / (p.bw * p.bh);
+    p.tiles_x = (d->w + p.bw - 1) / p.bw;
+    p.tiles_y = (d->h + p.bh - 1) / p.bh;
+    int tiles_n = (d->nb + p.bn - 1) / p.bn;
+    int64_t mt = (int64_t)p.tiles_x * p.tiles_y * tiles_n;
+    SVL_CHECK_ARG(mt < (1ll << 30), "svl_gemm: too many tiles");
+    p.num_m_tiles = (int)mt;
+    p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
+    uint64_t dims[4] = {(uint64_t)a_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->w, (uint64_t)d->lda * 2 * d->w * d->h};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (int rc = tma_encode_bf16(&tmA, d->a, 4, dims, strides, box)) return rc;
+  } else {
+    int64_t mt = (d->m + BM - 1) / BM;
+    SVL_CHECK_ARG(mt < (1ll << 30), "svl_gemm: too many tiles");
+    p.num_m_tiles = (int)mt;
+    p.a_tx_bytes = BM * 128u;
+    uint64_t dims[2] = {(uint64_t)a_cols, (uint64_t)d->m};
+    uint64_t strides[1] = {(uint64_t)d->lda * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    if (int rc = tma_encode_bf16(&tmA, d->a, 2, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d->ldb, (uint64_t)d->b_rows};
+    uint64_t strides[1] = {(uint64_t)d->ldb * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)p.block_n};
+    if (int rc = tma_encode_bf16(&tmB, d->b, 2, dims, strides, box)) return rc;
+  }
+  p.a_stage_bytes = BM * 128u;
+  p.b_stage_bytes = (uint32_t)p.block_n * 128u;      // block_n % 16 == 0 -> multiple of 2048, keeps every stage 1024-aligned
+  p.stages = (int)(kSmemBudget / (p.a_stage_bytes + p.b_stage_bytes));
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.tmem_cols = pow2ceil(2 * p.block_n < 32 ? 32 : 2 * p.block_n);
+
+  p.out = d->out; p.out_dtype = d->out_dtype; p.ldc = d->ldc; p.out_mode = d->out_mode; p.out_h = d->out_h; p.out_w = d->out_w;
+  p.alpha = d->alpha; p.bias = d->bias; p.row_bias = d->row_bias; p.row_bias_div = d->row_bias_div > 0 ? d->row_bias_div : 1;
+  p.row_bias_ld = d->row_bias_ld;
+  p.act = d->act; p.preact_out = d->preact_out; p.preact_dtype = d->preact_dtype; p.ld_preact = d->ld_preact;
+  p.dact_src = d->dact_src; p.dact_dtype = d->dact_dtype; p.dact_kind = d->dact_kind; p.ld_dact = d->ld_dact;
+  p.residual = d->residual; p.res_dtype = d->res_dtype; p.ldres = d->ldres;
+  p.accumulate = d->accumulate;
+
+  const size_t smem = 1024 + (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 8 * (2 * kMaxStages + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVL_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}

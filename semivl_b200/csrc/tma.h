@@ -1,0 +1,12 @@
+// Host-side helpers shared by the kernels' launchers.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace svl {
+// Encode a tiled bf16 tensor map with SWIZZLE_128B and zero out-of-bounds fill.
+// dims[0] is the contiguous dimension; strides_bytes has rank-1 entries (dimension 1..rank-1).
+int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+int num_sms();
+}  // namespace svl

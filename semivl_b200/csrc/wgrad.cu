@@ -1,0 +1,293 @@
+// Weight-gradient contraction on tcgen05 with MN-major operands:
+//
+//   DW[slot][i][j] += alpha * sum_{taps t of slot} sum_{rows r} DY[r, dy_koff_t + i] * X[shift_t(r), x_koff_t + j]
+//
+// Both operands are read straight from their forward (row = pixel/token, channels contiguous) layouts: a TMA box of
+// 64 rows x 64 channels lands in shared memory as 64 K-rows of 128 bytes, which is exactly the canonical MN-major
+// SWIZZLE_128B operand tile (8 K-rows per 1024-byte group, 64-channel chunks one box apart).  The contraction runs over
+// rows; it is split across CTAs (split-K) and the partial tiles are reduced with red.global.add.f32.
+// replaces: autograd's wgrad of nn.Linear / nn.Conv2d / nn.ConvTranspose2d on the hot path (semivl.py:327).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace svl {
+namespace {
+
+constexpr int BM = 128;       // dy channels per tile
+constexpr int KB = 64;        // rows per K block
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+constexpr uint32_t kBoxBytes = 64 * 128;
+
+struct WgradParams {
+  int conv;
+  int64_t rows;
+  int nb, h, w, bw, bh, bn, tiles_x, tiles_y;
+  int64_t num_kblocks;            // K blocks over all rows
+  int m, n, block_n, num_m_tiles, num_n_tiles, num_slots, splits;
+  int num_taps;
+  int tap_dy[SVL_MAX_TAPS], tap_dx[SVL_MAX_TAPS], tap_dy_koff[SVL_MAX_TAPS], tap_x_koff[SVL_MAX_TAPS];
+  int slot_tap0[SVL_MAX_TAPS + 1];   // taps of slot s are [slot_tap0[s], slot_tap0[s+1])
+  uint32_t k_tx_bytes;            // bytes one 64-channel box transfers (rows in the box * 128)
+  int stages, tmem_cols;
+  float* dw; int64_t ld_dw, slot_stride;
+  float alpha;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  const uint32_t a_stage = 2 * kBoxBytes, b_stage = (uint32_t)(p.block_n / 64) * kBoxBytes;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + p.stages * a_stage;
+  const uint32_t bar_base = smem_b + p.stages * b_stage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 1);
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work decomposition
+  int bid = blockIdx.x;
+  const int split = bid % p.splits; bid /= p.splits;
+  const int m_tile = bid % p.num_m_tiles; bid /= p.num_m_tiles;
+  const int n_tile = bid % p.num_n_tiles; bid /= p.num_n_tiles;
+  const int slot = bid;
+  const int64_t kb_per = (p.num_kblocks + p.splits - 1) / p.splits;
+  const int64_t kb0 = split * kb_per;
+  const int64_t kb1 = kb0 + kb_per < p.num_kblocks ? kb0 + kb_per : p.num_kblocks;
+  const int tap0 = p.slot_tap0[slot], tap1 = p.slot_tap0[slot + 1];
+  const bool has_work = kb1 > kb0 && tap1 > tap0;
+
+  // partial boxes (tiny images) leave K-rows of a stage untouched: they must read as zero
+  if (p.k_tx_bytes < kBoxBytes) {
+    uint4* z = (uint4*)(smem_raw + (smem_base - raw));
+    const int n16 = (int)((p.stages * (a_stage + b_stage)) / 16);
+    for (int i = threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDY);
+    ptx::prefetch_tmap(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tfull_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const int nchunks_b = p.block_n / 64;
+
+  if (has_work) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = tap0; t < tap1; ++t) {
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.k_tx_bytes * (2 + nchunks_b));
+            const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
+            const int ca = p.tap_dy_koff[t] + m_tile * BM, cb = p.tap_x_koff[t] + n_tile * p.block_n;
+            if (p.conv) {
+              const int cx = (int)(kb % p.tiles_x) * p.bw;
+              const int cy = (int)((kb / p.tiles_x) % p.tiles_y) * p.bh;
+              const int cn = (int)(kb / ((int64_t)p.tiles_x * p.tiles_y)) * p.bn;
+              for (int c = 0; c < 2; ++c) ptx::tma_load_4d(sa + c * kBoxBytes, &tmDY, full_bar(stage), ca + c * 64, cx, cy, cn);
+              for (int c = 0; c < nchunks_b; ++c)
+                ptx::tma_load_4d(sb + c * kBoxBytes, &tmX, full_bar(stage), cb + c * 64, cx + p.tap_dx[t], cy + p.tap_dy[t], cn);
+            } else {
+              const int r0 = (int)(kb * KB);
+              for (int c = 0; c < 2; ++c) ptx::tma_load_2d(sa + c * kBoxBytes, &tmDY, full_bar(stage), ca + c * 64, r0);
+              for (int c = 0; c < nchunks_b; ++c) ptx::tma_load_2d(sb + c * kBoxBytes, &tmX, full_bar(stage), cb + c * 64, r0);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t accum = 0;
+        for (int t = tap0; t < tap1; ++t) {
+          for (int64_t kb = kb0; kb < kb1; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
+            const uint64_t adesc = ptx::make_smem_desc(sa, kBoxBytes, 1024), bdesc = ptx::make_smem_desc(sb, kBoxBytes, 1024);
+#pragma unroll
+            for (int kk = 0; kk < KB / 16; ++kk) {
+              // 16 K-rows = 2048 bytes further into every chunk
+              ptx::umma_bf16(tmem_base, adesc + (uint64_t)(kk * 128), bdesc + (uint64_t)(kk * 128), idesc, accum);
+              accum = 1;
+            }
+            ptx::umma_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        ptx::umma_commit(tfull_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int i = m_tile * BM + q * 32 + lane;       // output row (dy channel)
+      ptx::mbar_wait(tfull_bar, 0);
+      ptx::tc_fence_after();
+      float* row = p.dw + (int64_t)slot * p.slot_stride + (int64_t)i * p.ld_dw;
+      const int n0 = n_tile * p.block_n;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        if (n0 + c0 >= p.n) break;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        if (i >= p.m) continue;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int col = n0 + c0 + g * 4;
+          float* dst = row + col;
+          float f0 = __uint_as_float(v[g * 4]) * p.alpha, f1 = __uint_as_float(v[g * 4 + 1]) * p.alpha,
+                f2 = __uint_as_float(v[g * 4 + 2]) * p.alpha, f3 = __uint_as_float(v[g * 4 + 3]) * p.alpha;
+          if (col + 4 <= p.n && ((uintptr_t)dst & 15) == 0) {
+            red_add_v4(dst, f0, f1, f2, f3);
+          } else {
+            if (col < p.n) atomicAdd(dst, f0);
+            if (col + 1 < p.n) atomicAdd(dst + 1, f1);
+            if (col + 2 < p.n) atomicAdd(dst + 2, f2);
+            if (col + 3 < p.n) atomicAdd(dst + 3, f3);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace
+}  // namespace svl
+
+using namespace svl;
+
+extern "C" int svl_wgrad(const svl_wgrad_desc* d, void* stream) {
+  SVL_CHECK_ARG(d && d->dy && d->x && d->dw, "svl_wgrad: null operand");
+  SVL_CHECK_ARG(d->rows > 0 && d->m > 0 && d->n > 0, "svl_wgrad: empty problem");
+  SVL_CHECK_ARG(d->num_taps >= 1 && d->num_taps <= SVL_MAX_TAPS, "svl_wgrad: num_taps=%d out of range", d->num_taps);
+  SVL_CHECK_ARG(d->ld_dy % 8 == 0 && d->ld_x % 8 == 0, "svl_wgrad: leading dimensions must be multiples of 8 elements");
+  SVL_CHECK_ARG(((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->x & 15) == 0, "svl_wgrad: operands must be 16-byte aligned");
+  if (int rc = svl_check_device()) return rc;
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.conv = d->conv;
+  p.rows = d->rows;
+  p.m = d->m;
+  p.n = d->n;
+  p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  p.num_taps = d->num_taps;
+  int nslots = 0;
+  for (int t = 0; t < d->num_taps; ++t) {
+    p.tap_dy[t] = d->tap_dy[t]; p.tap_dx[t] = d->tap_dx[t];
+    p.tap_dy_koff[t] = d->tap_dy_koff[t]; p.tap_x_koff[t] = d->tap_x_koff[t];
+    int s = d->tap_slot[t];
+    SVL_CHECK_ARG(s == nslots || s == nslots - 1, "svl_wgrad: tap slots must be contiguous and ascending (tap %d slot %d)", t, s);
+    if (s == nslots) { p.slot_tap0[nslots] = t; ++nslots; }
+  }
+  p.slot_tap0[nslots] = d->num_taps;
+  p.num_slots = nslots;
+  p.block_n = d->n >= 256 ? 256 : (d->n + 63) / 64 * 64;
+  if (d->n > 256) {
+    int best = 256, best_pad = 1 << 30;
+    for (int bn : {256, 192, 128}) {
+      int pad = (d->n + bn - 1) / bn * bn - d->n;
+      if (pad < best_pad) { best = bn; best_pad = pad; }
+    }
+    p.block_n = best;
+  }
+  p.num_m_tiles = (d->m + BM - 1) / BM;
+  p.num_n_tiles = (d->n + p.block_n - 1) / p.block_n;
+  const int64_t dy_cols = d->dy_cols > 0 ? d->dy_cols : d->ld_dy;
+  const int64_t x_cols = d->x_cols > 0 ? d->x_cols : d->ld_x;
+
+  CUtensorMap tmDY, tmX;
+  if (d->conv) {
+    SVL_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0 && (int64_t)d->nb * d->h * d->w == d->rows, "svl_wgrad: conv geometry does not match rows");
+    p.nb = d->nb; p.h = d->h; p.w = d->w;
+    p.bw = d->w < KB ? d->w : KB;
+    p.bh = d->h < KB / p.bw ? d->h : KB / p.bw;
+    p.bn = d->nb < KB / (p.bw * p.bh) ? d->nb : KB / (p.bw * p.bh);
+    p.tiles_x = (d->w + p.bw - 1) / p.bw;
+    p.tiles_y = (d->h + p.bh - 1) / p.bh;
+    p.num_kblocks = (int64_t)p.tiles_x * p.tiles_y * ((d->nb + p.bn - 1) / p.bn);
+    p.k_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
+    uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    uint64_t dims[4] = {(uint64_t)dy_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t st[3] = {(uint64_t)d->ld_dy * 2, (uint64_t)d->ld_dy * 2 * d->w, (uint64_t)d->ld_dy * 2 * d->w * d->h};
+    if (int rc = tma_encode_bf16(&tmDY, d->dy, 4, dims, st, box)) return rc;
+    uint64_t dimsx[4] = {(uint64_t)x_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t stx[3] = {(uint64_t)d->ld_x * 2, (uint64_t)d->ld_x * 2 * d->w, (uint64_t)d->ld_x * 2 * d->w * d->h};
+    if (int rc = tma_encode_bf16(&tmX, d->x, 4, dimsx, stx, box)) return rc;
+  } else {
+    p.num_kblocks = (d->rows + KB - 1) / KB;
+    p.k_tx_bytes = kBoxBytes;
+    uint32_t box[2] = {64u, (uint32_t)KB};
+    uint64_t dims[2] = {(uint64_t)dy_cols, (uint64_t)d->rows};
+    uint64_t st[1] = {(uint64_t)d->ld_dy * 2};
+    if (int rc = tma_encode_bf16(&tmDY, d->dy, 2, dims, st, box)) return rc;
+    uint64_t dimsx[2] = {(uint64_t)x_cols, (uint64_t)d->rows};
+    uint64_t stx[1] = {(uint64_t)d->ld_x * 2};
+    if (int rc = tma_encode_bf16(&tmX, d->x, 2, dimsx, stx, box)) return rc;
+  }
+  const uint32_t stage_bytes = 2 * kBoxBytes + (uint32_t)(p.block_n / 64) * kBoxBytes;
+  p.stages = (int)(kSmemBudget / stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.tmem_cols = pow2ceil(p.block_n < 32 ? 32 : p.block_n);
+  p.dw = d->dw; p.ld_dw = d->ld_dw; p.slot_stride = d->slot_stride;
+
+  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * p.num_slots;
+  int splits = d->splits;
+  if (splits <= 0) {
+    // fill ~2 waves of the machine, but keep at least 8 K blocks per CTA
+    int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles;
+    int64_t cap = p.num_kblocks / 8 > 0 ? p.num_kblocks / 8 : 1;
+    splits = (int)(want < cap ? want : cap);
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.num_kblocks) splits = (int)p.num_kblocks;
+  p.splits = splits;
+
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 8 * (2 * kMaxStages + 2) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVL_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t grid = tiles * splits;
+  SVL_CHECK_ARG(grid < (1ll << 31), "svl_wgrad: grid too large");
+  wgrad_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}

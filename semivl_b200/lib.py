@@ -1,0 +1,115 @@
+"""ctypes binding of the C-ABI CUDA library (include/semivl_b200.h).
+
+There is no fallback: importing this module raises if the library has not been built
+(`python -m semivl_b200.build`), and every call raises SvlError on a non-zero status.
+Tensors are passed as raw device pointers; torch only owns memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libsemivl_b200.so")
+
+F32, BF16, BF16X2 = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+OUT_LINEAR, OUT_CONVT2X2 = 0, 1
+MAX_TAPS = 32
+
+
+class SvlError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: build the CUDA extension first (python -m semivl_b200.build); "
+                      "semivl_b200 has no CPU / PyTorch fallback path")
+_lib = C.CDLL(LIB_PATH)
+
+_TapArr = C.c_int * MAX_TAPS
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_conv", C.c_int), ("m", C.c_int64), ("lda", C.c_int64), ("a_cols", C.c_int64),
+        ("nb", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("b", C.c_void_p), ("b_rows", C.c_int64), ("ldb", C.c_int64),
+        ("n", C.c_int), ("k_per_tap", C.c_int), ("num_taps", C.c_int),
+        ("tap_dy", _TapArr), ("tap_dx", _TapArr), ("tap_a_koff", _TapArr), ("tap_b_row", _TapArr), ("tap_b_col", _TapArr),
+        ("out", C.c_void_p), ("out_dtype", C.c_int), ("ldc", C.c_int64), ("out_mode", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
+        ("alpha", C.c_float), ("bias", C.c_void_p), ("row_bias", C.c_void_p), ("row_bias_div", C.c_int64), ("row_bias_ld", C.c_int64),
+        ("act", C.c_int), ("preact_out", C.c_void_p), ("preact_dtype", C.c_int), ("ld_preact", C.c_int64),
+        ("dact_src", C.c_void_p), ("dact_dtype", C.c_int), ("dact_kind", C.c_int), ("ld_dact", C.c_int64),
+        ("residual", C.c_void_p), ("res_dtype", C.c_int), ("ldres", C.c_int64),
+        ("accumulate", C.c_int), ("block_n", C.c_int),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("ld_dy", C.c_int64), ("dy_cols", C.c_int64),
+        ("x", C.c_void_p), ("ld_x", C.c_int64), ("x_cols", C.c_int64),
+        ("conv", C.c_int), ("rows", C.c_int64), ("nb", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("m", C.c_int), ("n", C.c_int), ("num_taps", C.c_int),
+        ("tap_dy", _TapArr), ("tap_dx", _TapArr), ("tap_dy_koff", _TapArr), ("tap_x_koff", _TapArr), ("tap_slot", _TapArr),
+        ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("slot_stride", C.c_int64),
+        ("alpha", C.c_float), ("splits", C.c_int),
+    ]
+
+
+_lib.svl_last_error.restype = C.c_char_p
+_lib.svl_version.restype = C.c_int
+_lib.svl_check_device.restype = C.c_int
+_lib.svl_gemm.restype = C.c_int
+_lib.svl_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+
+_lib.svl_wgrad.restype = C.c_int
+_lib.svl_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
+
+launches = 0     # number of kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise SvlError(f"{what}: status {rc}: {_lib.svl_last_error().decode()}")
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def version():
+    return _lib.svl_version()
+
+
+def check_device():
+    check(_lib.svl_check_device(), "svl_check_device")
+
+
+def dtype_of(t, split=False):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16X2 if split else BF16
+    raise SvlError(f"unsupported dtype {t.dtype}")
+
+
+def raw_gemm(desc):
+    global launches
+    check(_lib.svl_gemm(C.byref(desc), stream()), "svl_gemm")
+    launches += 1
+
+
+def raw_wgrad(desc):
+    global launches
+    check(_lib.svl_wgrad(C.byref(desc), stream()), "svl_wgrad")
+    launches += 1
+
+
+def lib():
+    return _lib

@@ -1,0 +1,198 @@
+"""GPU parity of the tcgen05 contraction engine (svl_gemm) against plain PyTorch fp32 on the same operands.
+
+fast mode   : operands rounded to bf16, fp32 accumulate -> compared with an fp32 matmul of the rounded operands (tol 2e-3 of scale)
+precise mode: split bf16 pairs, 3 taps                  -> compared with an fp32 matmul of the ORIGINAL operands (tol 3e-5 of scale)
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # the fp32 references must be fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from semivl_b200 import lib, ops
+    lib.check_device()
+    return ops
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 200, 192), (1000, 768, 768), (4100, 2304, 768), (77, 21, 512), (513, 3072, 768)])
+def test_plain_gemm(ops, m, n, k):
+    from semivl_b200 import lib as L
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    bias = torch.randn(n, device="cuda", generator=g)
+    out = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(_bf(a), _bf(w), out, n=n, k=k, bias=bias)
+    ref = _bf(a).float() @ _bf(w).float().t() + bias
+    assert _rel(out, ref) < 1e-4
+    # bf16 output
+    out16 = torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(_bf(a), _bf(w), out16, n=n, k=k, bias=bias)
+    assert _rel(out16, ref) < 6e-3
+    # precise mode (split operands)
+    outp = torch.zeros(m, n, device="cuda")
+    ops.gemm(ops.split_bf16(a), ops.split_bf16(w), outp, n=n, k=k, bias=bias, precise=True)
+    refp = a @ w.t() + bias
+    assert _rel(outp, refp) < 3e-5
+    # split output of precise mode
+    outs = torch.zeros(m, 2 * n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ops.split_bf16(a), ops.split_bf16(w), outs, n=n, k=k, bias=bias, precise=True, out_dtype=L.BF16X2)
+    assert _rel(outs[:, :n].float() + outs[:, n:].float(), refp) < 3e-5
+
+
+def test_epilogue_gelu_residual_preact(ops):
+    from semivl_b200 import lib as L
+    m, n, k = 700, 320, 256
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    bias = torch.randn(n, device="cuda", generator=g)
+    res = torch.randn(m, n, device="cuda", generator=g)
+    out = torch.zeros(m, n, device="cuda")
+    pre = torch.zeros(m, n, device="cuda")
+    ops.gemm(_bf(a), _bf(w), out, n=n, k=k, bias=bias, act=L.ACT_GELU, residual=res, preact_out=pre, alpha=0.5)
+    z = 0.5 * (_bf(a).float() @ _bf(w).float().t()) + bias
+    assert _rel(pre, z) < 1e-4
+    assert _rel(out, F.gelu(z) + res) < 1e-4
+    # act' multiply (GELU backward) + accumulate
+    src = torch.randn(m, n, device="cuda", generator=g)
+    acc = torch.randn(m, n, device="cuda", generator=g)
+    acc0 = acc.clone()
+    ops.gemm(_bf(a), _bf(w), acc, n=n, k=k, dact_src=src, dact_kind=L.ACT_GELU, accumulate=True)
+    s = src.clone().requires_grad_(True)
+    F.gelu(s).sum().backward()
+    ref = acc0 + (_bf(a).float() @ _bf(w).float().t()) * s.grad
+    assert _rel(acc, ref) < 1e-4
+    # relu' from saved output + row bias
+    y = torch.randn(m, n, device="cuda", generator=g)
+    rb = torch.randn(7, n, device="cuda", generator=g)
+    o2 = torch.zeros(m, n, device="cuda")
+    ops.gemm(_bf(a), _bf(w), o2, n=n, k=k, dact_src=_bf(y), dact_kind=L.ACT_RELU, row_bias=rb, row_bias_div=100)
+    zz = _bf(a).float() @ _bf(w).float().t() + rb[torch.arange(m, device="cuda") // 100]
+    assert _rel(o2, zz * (_bf(y).float() > 0)) < 1e-4
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,ks,dil", [(5, 12, 12, 64, 48, 3, 2), (7, 32, 32, 128, 128, 3, 6), (3, 64, 64, 128, 64, 3, 1),
+                                                     (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
+                                                     (2, 128, 128, 32, 1, 3, 1), (4, 8, 8, 256, 64, 1, 1)])
+@pytest.mark.parametrize("precise", [False, True])
+def test_implicit_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
+    g = torch.Generator(device="cuda").manual_seed(nb * h + cin + cout)
+    x = torch.randn(nb, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, ks, ks, device="cuda", generator=g) / (cin * ks * ks) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    if not precise:
+        x, wt = _bf(x).float(), _bf(wt).float()
+    ref = F.conv2d(x, wt, bias, padding=dil * (ks // 2), dilation=dil).permute(0, 2, 3, 1)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    a = ops.split_bf16(x_nhwc) if precise else _bf(x_nhwc)
+    wk = wt.permute(2, 3, 0, 1).reshape(ks * ks * cout, cin)          # [tap*cout, cin]
+    b = ops.prep_weight(wk, precise)
+    filt = [((i - ks // 2) * dil, (j - ks // 2) * dil) for i in range(ks) for j in range(ks)]
+    out = torch.full((nb, h, w, cout), float("nan"), device="cuda")
+    ops.gemm(a, b, out, n=cout, k=cin, precise=precise, conv=(nb, h, w), filt=filt, b_row_stride=cout, bias=bias)
+    assert _rel(out, ref) < (3e-5 if precise else 1e-4)
+
+
+def test_convtranspose_scatter(ops):
+    from semivl_b200 import lib as L
+    nb, h, w, cin, cout = 3, 16, 16, 128, 96
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = _bf(torch.randn(nb, cin, h, w, device="cuda", generator=g)).float()
+    wt = _bf(torch.randn(cin, cout, 2, 2, device="cuda", generator=g) / cin ** 0.5).float()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    ref = F.conv_transpose2d(x, wt, bias, stride=2).permute(0, 2, 3, 1)
+    a = _bf(x.permute(0, 2, 3, 1).contiguous()).reshape(nb * h * w, cin)
+    b = _bf(wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous())          # rows (qy, qx, co)
+    ldc = 128
+    out = torch.zeros(nb, 2 * h, 2 * w, ldc, device="cuda")
+    ops.gemm(a, b, out, n=4 * cout, k=cin, bias=bias.repeat(4), out_mode=L.OUT_CONVT2X2, out_hw=(h, w), ldc=ldc)
+    assert _rel(out[..., :cout], ref) < 1e-4
+    assert out[..., cout:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("rows,m,n", [(64, 128, 64), (1000, 200, 100), (4100, 2304, 768), (16400, 768, 768), (333, 21, 512)])
+@pytest.mark.parametrize("precise", [False, True])
+def test_wgrad_linear(ops, rows, m, n, precise):
+    g = torch.Generator(device="cuda").manual_seed(rows + m)
+    dy = torch.randn(rows, m, device="cuda", generator=g)
+    x = torch.randn(rows, n, device="cuda", generator=g)
+    if not precise:
+        dy, x = _bf(dy).float(), _bf(x).float()
+    mp, np_ = (m + 7) // 8 * 8, (n + 7) // 8 * 8           # TMA needs 16-byte row strides
+    dyp = torch.zeros(rows, mp, device="cuda"); dyp[:, :m] = dy
+    xp = torch.zeros(rows, np_, device="cuda"); xp[:, :n] = x
+    a = ops.split_bf16(dyp) if precise else _bf(dyp)
+    b = ops.split_bf16(xp) if precise else _bf(xp)
+    dw = torch.ones(m, n, device="cuda")
+    ops.wgrad(a, b, dw, m=m, n=n, precise=precise, alpha=0.5)
+    ref = 1.0 + 0.5 * (dy.double().t() @ x.double()).float()
+    assert _rel(dw, ref) < (3e-5 if precise else 1e-4)
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,ks,dil", [(5, 12, 12, 64, 48, 3, 2), (7, 32, 32, 128, 128, 3, 6), (3, 64, 64, 128, 64, 3, 1),
+                                                     (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
+                                                     (4, 8, 8, 256, 64, 1, 1)])
+@pytest.mark.parametrize("precise", [False, True])
+def test_wgrad_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
+    g = torch.Generator(device="cuda").manual_seed(nb * h + cin + cout)
+    x = torch.randn(nb, cin, h, w, device="cuda", generator=g)
+    dy = torch.randn(nb, cout, h, w, device="cuda", generator=g)
+    if not precise:
+        x, dy = _bf(x).float(), _bf(dy).float()
+    wt = torch.zeros(cout, cin, ks, ks, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wt, None, padding=dil * (ks // 2), dilation=dil).backward(dy.double())
+    ref = wt.grad.permute(2, 3, 0, 1).reshape(ks * ks, cout, cin).float()
+    xa = x.permute(0, 2, 3, 1).contiguous()
+    dya = dy.permute(0, 2, 3, 1).contiguous()
+    a = ops.split_bf16(dya) if precise else _bf(dya)
+    b = ops.split_bf16(xa) if precise else _bf(xa)
+    filt = [((i - ks // 2) * dil, (j - ks // 2) * dil) for i in range(ks) for j in range(ks)]
+    dw = torch.zeros(ks * ks, cout, cin, device="cuda")
+    ops.wgrad(a, b, dw, m=cout, n=cin, precise=precise, conv=(nb, h, w), filt=filt)
+    assert _rel(dw, ref) < (3e-5 if precise else 1e-4)
+
+
+def test_throughput_report(ops):
+    """Not an assertion on speed: prints achieved TFLOP/s for the ViT-block shapes (used when reading gpurun logs)."""
+    for (m, n, k) in [(16400, 2304, 768), (16400, 768, 768), (16400, 3072, 768), (16400, 768, 3072)]:
+        a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
+        w = torch.randn(n, k, device="cuda").to(torch.bfloat16)
+        out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.gemm(a, w, out, n=n, k=k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.gemm(a, w, out, n=n, k=k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"gemm {m}x{n}x{k}: {ms * 1e3:.1f} us  {2 * m * n * k / ms / 1e9:.1f} TFLOP/s")
+    for (rows, m, n) in [(16400, 2304, 768), (16400, 768, 768)]:
+        dy = torch.randn(rows, m, device="cuda").to(torch.bfloat16)
+        x = torch.randn(rows, n, device="cuda").to(torch.bfloat16)
+        dw = torch.zeros(m, n, device="cuda")
+        for _ in range(3):
+            ops.wgrad(dy, x, dw, m=m, n=n)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.wgrad(dy, x, dw, m=m, n=n)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"wgrad {rows}x{m}x{n}: {ms * 1e3:.1f} us  {2 * m * n * rows / ms / 1e9:.1f} TFLOP/s")

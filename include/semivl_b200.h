@@ -120,6 +120,49 @@ typedef struct {
 
 int svl_wgrad(const svl_wgrad_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Token / normalisation kernels (HBM-bound).  `*_dtype` arguments are svl_dtype; `ld*` are row strides in elements.
+ * ---------------------------------------------------------------------------------------------- */
+/* im2col of non-overlapping p x p patches with bottom/right zero pad (mmseg PatchEmbed 'corner'),
+ * img f32 NCHW [b,3,H,W] -> out [b*hp*wp, 3*p*p] (BF16 or BF16X2), column order (c, py, px) = conv weight order.
+ * replaces the input side of the PatchEmbed conv, maskclip_vit.py:495. */
+int svl_patchify(const float* img, void* out, int out_dtype, int b, int H, int W, int p, int hp, int wp, void* stream);
+/* x[b,0,:] = cls + pos[0]; x[b,1+i,:] = patches[b*hw+i,:] + pos[1+i]   (maskclip_vit.py:498-500) */
+int svl_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int b, int hw, int c, void* stream);
+/* LayerNorm over the last dim (maskclip_vit.py:111,132,141-142,507,539-541).  mean/rstd [rows] saved when non-NULL. */
+int svl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int y_dtype, int64_t ldy,
+                      float* mean, float* rstd, int64_t rows, int c, float eps, void* stream);
+/* dx = dres1 + dres2 + LN'(dy) (f32, contiguous rows; dres may be NULL); dx_act = optional copy in an operand format;
+ * dgamma/dbeta (+=, atomics) when non-NULL. */
+int svl_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                      const float* mean, const float* rstd, const float* dres1, const float* dres2, float* dx, void* dx_act,
+                      int act_dtype, int64_t ld_act, float* dgamma, float* dbeta, int64_t rows, int c, void* stream);
+/* y[r,:] = x[r,:] / max(||x[r,:]||_2, eps)   (maskclip_vit.py:555,589; F.normalize vlg_head.py:215-216) */
+int svl_l2norm_fwd(const float* x, int64_t ldx, float* y, void* y_act, int act_dtype, int64_t ld_act, float* inv_norm, int64_t rows,
+                   int c, float eps, void* stream);
+int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* y, const float* inv_norm, float* dx, int64_t lddx,
+                   int accumulate, int64_t rows, int c, void* stream);
+/* dst = scale * src with a storage-type change (scale 0 is treated as 1) */
+int svl_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows, int cols,
+             float scale, void* stream);
+/* out[col] += sum_rows x[row, col]  (bias gradients) */
+int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
+/* out[i] (+)= sum_b x[b, i]  (pos_embed gradient, maskclip_vit.py:500) */
+int svl_batch_sum(const float* x, float* out, int b, int64_t inner, int accumulate, void* stream);
+int svl_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-head self-attention, head_dim 64 (nn.MultiheadAttention core, maskclip_vit.py:77-84,141; also the
+ * class-attention of SemanticTransformer, vlg_head.py:39-67).  qkv packed [b, L, 3E] bf16 (q | k | v, heads contiguous
+ * inside each third; split != 0: BF16X2 rows of 6E), out [b, L, E] (2E when split), lse [b, heads, L]; never materialises LxL.
+ * Backward: delta_ws is a caller-provided [b, heads, L] f32 scratch; dv_add (optional, [b*L, E]) is added to dV before it is
+ * stored (the MaskCLIP v-path gradient, maskclip_vit.py:110-118); dqkv has the layout of qkv.
+ * ---------------------------------------------------------------------------------------------- */
+int svl_attention_fwd(const void* qkv, int split, void* out, float* lse, int b, int L, int heads, float scale, void* stream);
+int svl_attention_bwd(const void* qkv, const void* out, const void* dout, int split, const float* lse, float* delta_ws,
+                      const void* dv_add, int dv_add_dtype, int64_t ld_dv_add, void* dqkv, int b, int L, int heads, float scale,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,408 @@
+// HBM-bound token / normalisation kernels of the ViT path: patchify, token assembly, LayerNorm fwd/bwd,
+// L2 normalisation fwd/bwd and small utilities (cast, column sums, batch sums).  One warp per row, 128-bit loads,
+// warp-shuffle reductions, fp32 statistics.
+#include "common.cuh"
+
+namespace svl {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kMaxVec = 8;   // up to 8 float4 per lane -> rows up to 1024 wide
+
+inline int grid_for_rows(int64_t rows) {
+  int64_t b = cdiv(rows, kWarpsPerBlock);
+  int64_t cap = 148 * 16;
+  return (int)(b < cap ? b : cap);
+}
+
+// ---------------------------------------------------------------------------------------------- patchify
+// one thread per 8 output columns (8 consecutive px of one (c, py) row): 2 float4 loads, one 16-byte store
+__global__ void patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int out_dtype, int b, int H, int W, int p,
+                                int hp, int wp) {
+  const int K = 3 * p * p;
+  const int groups = K / 8;
+  const int64_t total = (int64_t)b * hp * wp * groups;
+  const int64_t ld = out_dtype == SVL_BF16X2 ? 2 * K : K;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const int64_t row = idx / groups;
+    const int col = g * 8;
+    const int c = col / (p * p), py = (col / p) % p, px = col % p;
+    const int pw = (int)(row % wp), ph = (int)((row / wp) % hp), bi = (int)(row / ((int64_t)wp * hp));
+    const int y = ph * p + py, x0 = pw * p + px;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int x = x0 + i;
+      f[i] = (y < H && x < W) ? __ldg(img + (((int64_t)bi * 3 + c) * H + y) * W + x) : 0.f;
+    }
+    st8(out, out_dtype, row * ld + col, ld / 2, 8, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- token assembly
+__global__ void assemble_tokens_kernel(const float* __restrict__ patches, const float* __restrict__ cls, const float* __restrict__ pos,
+                                       float* __restrict__ x, int b, int hw, int c) {
+  const int L = hw + 1;
+  const int c4 = c / 4;
+  const int64_t total = (int64_t)b * L * c4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % c4);
+    const int64_t t = idx / c4;
+    const int l = (int)(t % L), bi = (int)(t / L);
+    float4 pe = __ldg((const float4*)(pos + (int64_t)l * c) + j);
+    float4 v = l == 0 ? __ldg((const float4*)cls + j) : __ldg((const float4*)(patches + ((int64_t)bi * hw + l - 1) * c) + j);
+    v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+    ((float4*)(x + t * c))[j] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     void* __restrict__ y, int y_dtype, int64_t ldy, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int c,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = c / 128;                      // float4 per lane
+  for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float4* xr = (const float4*)(x + row * ldx);
+    float4 v[kMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        v[i] = xr[i * 32 + lane];
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
+    const float mu = warp_sum(s) / c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        float a = v[i].x - mu, b = v[i].y - mu, cc = v[i].z - mu, d = v[i].w - mu;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    const float rs = rsqrtf(warp_sum(q) / c + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        float4 g = __ldg((const float4*)gamma + i * 32 + lane), bt = __ldg((const float4*)beta + i * 32 + lane);
+        float o0 = (v[i].x - mu) * rs * g.x + bt.x, o1 = (v[i].y - mu) * rs * g.y + bt.y, o2 = (v[i].z - mu) * rs * g.z + bt.z,
+              o3 = (v[i].w - mu) * rs * g.w + bt.w;
+        if (y_dtype == SVL_F32) {
+          ((float4*)((float*)y + row * ldy))[i * 32 + lane] = make_float4(o0, o1, o2, o3);
+        } else {
+          __nv_bfloat16* yr = (__nv_bfloat16*)y + row * ldy + col;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+          uint2 u;
+          u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1;
+          *(uint2*)yr = u;
+          if (y_dtype == SVL_BF16X2) {
+            float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            __nv_bfloat162 l0 = __floats2bfloat162_rn(o0 - f0.x, o1 - f0.y), l1 = __floats2bfloat162_rn(o2 - f1.x, o3 - f1.y);
+            u.x = *(uint32_t*)&l0; u.y = *(uint32_t*)&l1;
+            *(uint2*)(yr + ldy / 2) = u;
+          }
+        }
+      }
+  }
+}
+
+// dx = dres1 + dres2 + LN'(dy); optional activation-format copy of dx; optional dgamma/dbeta accumulation
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const float* __restrict__ x, int64_t ldx,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ dres1, const float* __restrict__ dres2, float* __restrict__ dx, void* __restrict__ dx_act,
+                     int act_dtype, int64_t ld_act, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int c) {
+  __shared__ float sg[1024], sb[1024];
+  const int lane = threadIdx.x & 31;
+  const int nv = c / 128;
+  const bool want_wg = dgamma != nullptr;
+  float ag[kMaxVec * 4], ab[kMaxVec * 4];
+  if (want_wg) {
+#pragma unroll
+    for (int i = 0; i < kMaxVec * 4; ++i) ag[i] = ab[i] = 0.f;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) sg[i] = sb[i] = 0.f;
+    __syncthreads();
+  }
+  for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kMaxVec * 4], g[kMaxVec * 4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        float4 xv = *(const float4*)(x + row * ldx + col);
+        float4 gm = __ldg((const float4*)(gamma + col));
+        float d[4];
+        if (dy_dtype == SVL_F32) {
+          float4 t = *(const float4*)((const float*)dy + row * lddy + col);
+          d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+        } else {
+          const __nv_bfloat16* p = (const __nv_bfloat16*)dy + row * lddy + col;
+          uint2 u = *(const uint2*)p;
+          float2 a = __bfloat1622float2(*(__nv_bfloat162*)&u.x), b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
+          d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+          if (dy_dtype == SVL_BF16X2) {
+            u = *(const uint2*)(p + lddy / 2);
+            a = __bfloat1622float2(*(__nv_bfloat162*)&u.x); b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
+            d[0] += a.x; d[1] += a.y; d[2] += b.x; d[3] += b.y;
+          }
+        }
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gm.x, gm.y, gm.z, gm.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float h = (xs[j] - mu) * rs;
+          xh[i * 4 + j] = h;
+          if (want_wg) { ag[i * 4 + j] += d[j] * h; ab[i * 4 + j] += d[j]; }
+          const float gg = d[j] * gs[j];
+          g[i * 4 + j] = gg;
+          s1 += gg;
+          s2 += gg * h;
+        }
+      }
+    s1 = warp_sum(s1) / c;
+    s2 = warp_sum(s2) / c;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rs * (g[i * 4 + j] - s1 - xh[i * 4 + j] * s2);
+        if (dres1) {
+          float4 t = *(const float4*)(dres1 + row * (int64_t)c + col);
+          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+        }
+        if (dres2) {
+          float4 t = *(const float4*)(dres2 + row * (int64_t)c + col);
+          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+        }
+        if (dx) *(float4*)(dx + row * (int64_t)c + col) = make_float4(o[0], o[1], o[2], o[3]);
+        if (dx_act) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) store_from_f32(dx_act, act_dtype, row * ld_act + col + j, o[j], ld_act / 2);
+        }
+      }
+  }
+  if (want_wg) {
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          atomicAdd(&sg[col + j], ag[i * 4 + j]);
+          atomicAdd(&sb[col + j], ab[i * 4 + j]);
+        }
+      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      atomicAdd(dgamma + i, sg[i]);
+      atomicAdd(dbeta + i, sb[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- L2 normalisation
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_fwd_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, void* __restrict__ y_act, int act_dtype, int64_t ld_act,
+                  float* __restrict__ inv_norm, int64_t rows, int c, float eps) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float* xr = x + row * ldx;
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s += xr[i] * xr[i];
+    const float nrm = sqrtf(warp_sum(s));
+    const float inv = 1.f / fmaxf(nrm, eps);
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+    for (int i = lane; i < c; i += 32) {
+      const float v = xr[i] * inv;
+      if (y) y[row * (int64_t)c + i] = v;
+      if (y_act) store_from_f32(y_act, act_dtype, row * ld_act + i, v, ld_act / 2);
+    }
+  }
+}
+
+// y = x * inv  ->  dx = inv * (dy - y * <dy, y>)      (rows whose norm was clamped by eps are treated the same way; never hit in practice)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+l2norm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const float* __restrict__ y, const float* __restrict__ inv_norm,
+                  float* __restrict__ dx, int64_t lddx, int accumulate, int64_t rows, int c) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s += load_as_f32(dy, dy_dtype, row * lddy + i, lddy / 2) * y[row * (int64_t)c + i];
+    s = warp_sum(s);
+    const float inv = inv_norm[row];
+    for (int i = lane; i < c; i += 32) {
+      float v = inv * (load_as_f32(dy, dy_dtype, row * lddy + i, lddy / 2) - y[row * (int64_t)c + i] * s);
+      if (accumulate) v += dx[row * lddx + i];
+      dx[row * lddx + i] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- utilities
+__global__ void cast_kernel(const void* __restrict__ src, int src_dtype, int64_t ld_src, void* __restrict__ dst, int dst_dtype, int64_t ld_dst,
+                            int64_t rows, int cols, float scale) {
+  const int groups = (cols + 7) / 8;
+  const int64_t total = rows * groups;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const int64_t row = idx / groups;
+    const int cnt = min(8, cols - g * 8);
+    float f[8];
+    ld8(src, src_dtype, row * ld_src + g * 8, ld_src / 2, cnt, f);
+    if (scale != 1.f) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] *= scale;
+    }
+    st8(dst, dst_dtype, row * ld_dst + g * 8, ld_dst / 2, cnt, f);
+  }
+}
+
+// out[col] (+)= sum_rows x[row, col]; grid (col tiles of 32, row splits); block 32 x 8
+__global__ void colsum_kernel(const void* __restrict__ x, int x_dtype, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (col < cols)
+    for (int64_t r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) s += load_as_f32(x, x_dtype, r * ld + col, ld / 2);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
+
+// out[i] (+)= sum_b x[b, i]
+__global__ void batch_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int b, int64_t inner, int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < inner; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = accumulate ? out[i] : 0.f;
+    for (int j = 0; j < b; ++j) s += x[j * inner + i];
+    out[i] = s;
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, float alpha, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] += alpha * src[i];
+}
+
+inline int ew_grid(int64_t total, int block = 256) {
+  int64_t b = cdiv(total, block);
+  int64_t cap = 148 * 32;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+}  // namespace svl
+
+using namespace svl;
+
+extern "C" int svl_patchify(const float* img, void* out, int out_dtype, int b, int H, int W, int p, int hp, int wp, void* stream) {
+  SVL_CHECK_ARG(img && out && b > 0 && p % 8 == 0, "svl_patchify: bad arguments");
+  SVL_CHECK_ARG(hp * p >= H && wp * p >= W, "svl_patchify: patch grid does not cover the image");
+  const int64_t total = (int64_t)b * hp * wp * (3 * p * p / 8);
+  patchify_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(img, out, out_dtype, b, H, W, p, hp, wp);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int b, int hw, int c, void* stream) {
+  SVL_CHECK_ARG(patches && cls && pos && x && c % 4 == 0, "svl_assemble_tokens: bad arguments");
+  const int64_t total = (int64_t)b * (hw + 1) * (c / 4);
+  assemble_tokens_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(patches, cls, pos, x, b, hw, c);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int y_dtype, int64_t ldy,
+                                 float* mean, float* rstd, int64_t rows, int c, float eps, void* stream) {
+  SVL_CHECK_ARG(x && gamma && beta && y, "svl_layernorm_fwd: null pointer");
+  SVL_CHECK_ARG(c % 128 == 0 && c <= 128 * kMaxVec, "svl_layernorm_fwd: c=%d must be a multiple of 128 and <= %d", c, 128 * kMaxVec);
+  SVL_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0, "svl_layernorm_fwd: strides must be multiples of 4");
+  if (rows == 0) return SVL_OK;
+  layernorm_fwd_kernel<<<grid_for_rows(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, y, y_dtype, ldy, mean, rstd,
+                                                                                           rows, c, eps);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                                 const float* mean, const float* rstd, const float* dres1, const float* dres2, float* dx, void* dx_act,
+                                 int act_dtype, int64_t ld_act, float* dgamma, float* dbeta, int64_t rows, int c, void* stream) {
+  SVL_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_act), "svl_layernorm_bwd: null pointer");
+  SVL_CHECK_ARG(c % 128 == 0 && c <= 128 * kMaxVec, "svl_layernorm_bwd: c=%d must be a multiple of 128 and <= %d", c, 128 * kMaxVec);
+  if (rows == 0) return SVL_OK;
+  int grid = grid_for_rows(rows);
+  if (dgamma && grid > 296) grid = 296;     // fewer, longer-lived blocks: cheaper dgamma/dbeta reduction
+  layernorm_bwd_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, dy_dtype, lddy, x, ldx, gamma, mean, rstd, dres1, dres2, dx,
+                                                                               dx_act, act_dtype, ld_act, dgamma, dbeta, rows, c);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_l2norm_fwd(const float* x, int64_t ldx, float* y, void* y_act, int act_dtype, int64_t ld_act, float* inv_norm, int64_t rows,
+                              int c, float eps, void* stream) {
+  SVL_CHECK_ARG(x && (y || y_act), "svl_l2norm_fwd: null pointer");
+  if (rows == 0) return SVL_OK;
+  l2norm_fwd_kernel<<<grid_for_rows(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(x, ldx, y, y_act, act_dtype, ld_act, inv_norm, rows, c, eps);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* y, const float* inv_norm, float* dx, int64_t lddx,
+                              int accumulate, int64_t rows, int c, void* stream) {
+  SVL_CHECK_ARG(dy && y && inv_norm && dx, "svl_l2norm_bwd: null pointer");
+  if (rows == 0) return SVL_OK;
+  l2norm_bwd_kernel<<<grid_for_rows(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, dy_dtype, lddy, y, inv_norm, dx, lddx, accumulate,
+                                                                                        rows, c);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows, int cols,
+                        float scale, void* stream) {
+  SVL_CHECK_ARG(src && dst, "svl_cast: null pointer");
+  if (rows == 0 || cols == 0) return SVL_OK;
+  cast_kernel<<<ew_grid(rows * ((cols + 7) / 8)), 256, 0, (cudaStream_t)stream>>>(src, src_dtype, ld_src, dst, dst_dtype, ld_dst, rows, cols,
+                                                                                 scale == 0.f ? 1.f : scale);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
+  SVL_CHECK_ARG(x && out, "svl_colsum: null pointer");
+  if (rows == 0 || cols == 0) return SVL_OK;
+  int64_t ysplit = cdiv(rows, 8 * 64);
+  if (ysplit > 256) ysplit = 256;
+  dim3 grid((cols + 31) / 32, (unsigned)ysplit);
+  colsum_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_batch_sum(const float* x, float* out, int b, int64_t inner, int accumulate, void* stream) {
+  SVL_CHECK_ARG(x && out, "svl_batch_sum: null pointer");
+  if (inner == 0) return SVL_OK;
+  batch_sum_kernel<<<ew_grid(inner), 256, 0, (cudaStream_t)stream>>>(x, out, b, inner, accumulate);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream) {
+  SVL_CHECK_ARG(dst && src, "svl_axpy: null pointer");
+  if (n == 0) return SVL_OK;
+  axpy_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dst, src, alpha, n);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}

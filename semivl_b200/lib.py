@@ -67,6 +67,35 @@ _lib.svl_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
 _lib.svl_wgrad.restype = C.c_int
 _lib.svl_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
 
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_PROTOS = {
+    "svl_patchify": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "svl_layernorm_fwd": [_P, _L, _P, _P, _P, _I, _L, _P, _P, _L, _I, _F, _P],
+    "svl_layernorm_bwd": [_P, _I, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _L, _P, _P, _L, _I, _P],
+    "svl_l2norm_fwd": [_P, _L, _P, _P, _I, _L, _P, _L, _I, _F, _P],
+    "svl_l2norm_bwd": [_P, _I, _L, _P, _P, _P, _L, _I, _L, _I, _P],
+    "svl_cast": [_P, _I, _L, _P, _I, _L, _L, _I, _F, _P],
+    "svl_colsum": [_P, _I, _L, _L, _I, _P, _P],
+    "svl_batch_sum": [_P, _P, _I, _L, _I, _P],
+    "svl_axpy": [_P, _P, _F, _L, _P],
+    "svl_attention_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P],
+    "svl_attention_bwd": [_P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _I, _I, _I, _F, _P],
+}
+for _name, _args in _PROTOS.items():
+    _fn = getattr(_lib, _name)
+    _fn.restype = C.c_int
+    _fn.argtypes = _args
+
+
+def call(name, *args, n_launch=1):
+    """Call an svl_* entry point; tensors are passed as data pointers, the current stream is appended."""
+    global launches
+    conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
+    check(getattr(_lib, name)(*conv, torch.cuda.current_stream().cuda_stream), name)
+    launches += n_launch
+
+
 launches = 0     # number of kernels launched through this binding (bench.py reports it as gpu_launches)
 
 

@@ -125,3 +125,113 @@ def wgrad(dy, x, dw, *, m, n, precise=False, conv=None, filt=None, dy_koff=0, x_
     d.splits = splits
     L.raw_wgrad(d)
     return dw
+
+
+# ---------------------------------------------------------------------------------------------- token kernels
+def act_dtype(precise):
+    return L.BF16X2 if precise else L.BF16
+
+
+def new_act(rows, cols, precise, device="cuda"):
+    """Uninitialised GEMM-operand tensor [rows, cols] (bf16) or its split form [rows, 2*cols]."""
+    return torch.empty(rows, cols * (2 if precise else 1), device=device, dtype=torch.bfloat16)
+
+
+def patchify(img, precise, patch=16):
+    b, _, H, W = img.shape
+    hp, wp = -(-H // patch), -(-W // patch)
+    out = new_act(b * hp * wp, 3 * patch * patch, precise)
+    L.call("svl_patchify", img, out, act_dtype(precise), b, H, W, patch, hp, wp)
+    return out, hp, wp
+
+
+def assemble_tokens(patches, cls, pos, b, hw):
+    c = patches.shape[-1]
+    x = torch.empty(b, hw + 1, c, device=patches.device, dtype=torch.float32)
+    L.call("svl_assemble_tokens", patches, cls, pos, x, b, hw, c)
+    return x
+
+
+def layernorm_fwd(x2d, gamma, beta, eps, *, out=None, out_dtype=None, precise=False, save_stats=True, ldx=None):
+    """x2d: f32 [rows, c] (row stride ldx).  Returns (y, mean, rstd); y is an operand tensor unless out_dtype == F32."""
+    rows, c = x2d.shape
+    odt = out_dtype if out_dtype is not None else act_dtype(precise)
+    if out is None:
+        out = torch.empty(rows, c, device=x2d.device, dtype=torch.float32) if odt == L.F32 else new_act(rows, c, odt == L.BF16X2)
+    mean = torch.empty(rows, device=x2d.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(rows, device=x2d.device, dtype=torch.float32) if save_stats else None
+    L.call("svl_layernorm_fwd", x2d, ldx if ldx is not None else x2d.stride(0), gamma, beta, out, odt, out.shape[-1], mean, rstd, rows, c, eps)
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, dy_dtype, x2d, gamma, mean, rstd, *, dres1=None, dres2=None, want_dx=True, act_precise=None,
+                  dgamma=None, dbeta=None):
+    """Returns (dx f32 or None, dx_act or None)."""
+    rows, c = x2d.shape
+    dx = torch.empty(rows, c, device=x2d.device, dtype=torch.float32) if want_dx else None
+    dx_act = new_act(rows, c, act_precise) if act_precise is not None else None
+    L.call("svl_layernorm_bwd", dy, dy_dtype, dy.shape[-1], x2d, x2d.stride(0), gamma, mean, rstd, dres1, dres2, dx, dx_act,
+           act_dtype(bool(act_precise)), dx_act.shape[-1] if dx_act is not None else 0, dgamma, dbeta, rows, c)
+    return dx, dx_act
+
+
+def l2norm_fwd(x2d, *, want_f32=True, act_precise=None, eps=1e-12, ldx=None):
+    rows, c = x2d.shape
+    y = torch.empty(rows, c, device=x2d.device, dtype=torch.float32) if want_f32 else None
+    y_act = new_act(rows, c, act_precise) if act_precise is not None else None
+    inv = torch.empty(rows, device=x2d.device, dtype=torch.float32)
+    L.call("svl_l2norm_fwd", x2d, ldx if ldx is not None else x2d.stride(0), y, y_act, act_dtype(bool(act_precise)),
+           y_act.shape[-1] if y_act is not None else 0, inv, rows, c, eps)
+    return y, y_act, inv
+
+
+def l2norm_bwd(dy, dy_dtype, y, inv, dx, *, accumulate=False, lddy=None):
+    rows, c = y.shape
+    L.call("svl_l2norm_bwd", dy, dy_dtype, lddy if lddy is not None else dy.shape[-1], y, inv, dx, dx.stride(0), 1 if accumulate else 0, rows, c)
+    return dx
+
+
+def cast(src, src_dtype, dst, dst_dtype, rows, cols, *, ld_src=None, ld_dst=None, scale=1.0):
+    L.call("svl_cast", src, src_dtype, ld_src if ld_src is not None else src.shape[-1], dst, dst_dtype,
+           ld_dst if ld_dst is not None else dst.shape[-1], rows, cols, scale)
+    return dst
+
+
+def to_act(x2d, precise):
+    """f32 [rows, c] -> GEMM operand."""
+    rows, c = x2d.shape
+    return cast(x2d, L.F32, new_act(rows, c, precise), act_dtype(precise), rows, c, ld_src=x2d.stride(0))
+
+
+def colsum(x, x_dtype, rows, cols, out, ld=None):
+    L.call("svl_colsum", x, x_dtype, ld if ld is not None else x.shape[-1], rows, cols, out)
+    return out
+
+
+def batch_sum(x, out, accumulate=False):
+    b = x.shape[0]
+    L.call("svl_batch_sum", x, out, b, x.numel() // b, 1 if accumulate else 0)
+    return out
+
+
+def axpy(dst, src, alpha=1.0):
+    L.call("svl_axpy", dst, src, alpha, dst.numel())
+    return dst
+
+
+def attention_fwd(qkv, b, seq, heads, precise, want_lse=True):
+    """qkv operand [b*seq, 3E] (6E when precise) -> (out operand [b*seq, E], lse [b, heads, seq])."""
+    E = heads * 64
+    out = new_act(b * seq, E, precise, qkv.device)
+    lse = torch.empty(b, heads, seq, device=qkv.device, dtype=torch.float32) if want_lse else None
+    L.call("svl_attention_fwd", qkv, 1 if precise else 0, out, lse, b, seq, heads, 0.125)
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, b, seq, heads, precise, dv_add=None, dv_add_dtype=L.F32):
+    E = heads * 64
+    dqkv = new_act(b * seq, 3 * E, precise, qkv.device)
+    delta = torch.empty(b, heads, seq, device=qkv.device, dtype=torch.float32)
+    L.call("svl_attention_bwd", qkv, out, dout, 1 if precise else 0, lse, delta, dv_add, dv_add_dtype,
+           dv_add.shape[-1] if dv_add is not None else 0, dqkv, b, seq, heads, 0.125, n_launch=3)
+    return dqkv

@@ -1,0 +1,133 @@
+"""GPU parity of the token / normalisation kernels and of flash attention (fwd + bwd) against plain PyTorch fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from semivl_b200 import lib, ops
+    lib.check_device()
+    return ops
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+def _val(t, precise):
+    """operand tensor -> f32 value"""
+    if precise:
+        c = t.shape[-1] // 2
+        return t[..., :c].float() + t[..., c:].float()
+    return t.float()
+
+
+@pytest.mark.parametrize("precise", [False, True])
+@pytest.mark.parametrize("H,W", [(64, 64), (72, 72), (224, 224)])
+def test_patchify_assemble(ops, precise, H, W):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    b = 2
+    img = torch.randn(b, 3, H, W, device="cuda", generator=g)
+    out, hp, wp = ops.patchify(img, precise)
+    pad = F.pad(img, [0, wp * 16 - W, 0, hp * 16 - H])
+    ref = F.unfold(pad, 16, stride=16).transpose(1, 2).reshape(b * hp * wp, 768)
+    assert _rel(_val(out, precise), ref) < (1e-5 if precise else 5e-3)
+    patches = torch.randn(b * hp * wp, 768, device="cuda", generator=g)
+    cls = torch.randn(768, device="cuda", generator=g)
+    pos = torch.randn(hp * wp + 1, 768, device="cuda", generator=g)
+    x = ops.assemble_tokens(patches, cls, pos, b, hp * wp)
+    refx = torch.cat((cls.expand(b, 1, 768), patches.view(b, hp * wp, 768)), 1) + pos
+    assert torch.equal(x, refx)
+
+
+@pytest.mark.parametrize("rows,c", [(37, 768), (4100, 768), (501, 256)])
+def test_layernorm(ops, rows, c):
+    from semivl_b200 import lib as L
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(rows, c, device="cuda", generator=g) * 2 + 0.5
+    gamma = torch.randn(c, device="cuda", generator=g)
+    beta = torch.randn(c, device="cuda", generator=g)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (c,), gr, br, 1e-6)
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-6, out_dtype=L.F32)
+    assert _rel(y, ref) < 1e-5
+    yp, _, _ = ops.layernorm_fwd(x, gamma, beta, 1e-6, precise=True)
+    assert _rel(_val(yp, True), ref) < 2e-5
+    yb, _, _ = ops.layernorm_fwd(x, gamma, beta, 1e-6, precise=False)
+    assert _rel(yb, ref) < 5e-3
+    dy = torch.randn(rows, c, device="cuda", generator=g)
+    r1 = torch.randn(rows, c, device="cuda", generator=g)
+    ref.backward(dy)
+    dgamma, dbeta = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dx, dxa = ops.layernorm_bwd(dy, L.F32, x, gamma, mean, rstd, dres1=r1, act_precise=True, dgamma=dgamma, dbeta=dbeta)
+    assert _rel(dx, xr.grad + r1) < 2e-5
+    assert _rel(_val(dxa, True), xr.grad + r1) < 3e-5
+    assert _rel(dgamma, gr.grad) < 1e-4 and _rel(dbeta, br.grad) < 1e-4
+    # bf16 dy input, no weight grads
+    dx2, _ = ops.layernorm_bwd(dy.to(torch.bfloat16), L.BF16, x, gamma, mean, rstd)
+    xr.grad = None
+    F.layer_norm(xr, (c,), gamma, beta, 1e-6).backward(dy.to(torch.bfloat16).float())
+    assert _rel(dx2, xr.grad) < 2e-5
+
+
+def test_l2norm_cast_colsum(ops):
+    from semivl_b200 import lib as L
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(1000, 512, device="cuda", generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = F.normalize(xr, dim=1)
+    y, ya, inv = ops.l2norm_fwd(x, act_precise=True)
+    assert _rel(y, ref) < 1e-6 and _rel(_val(ya, True), ref) < 2e-5
+    dy = torch.randn(1000, 512, device="cuda", generator=g)
+    ref.backward(dy)
+    dx = torch.zeros(1000, 512, device="cuda")
+    ops.l2norm_bwd(dy, L.F32, y, inv, dx)
+    assert _rel(dx, xr.grad) < 1e-5
+    a = ops.to_act(x, True)
+    assert _rel(_val(a, True), x) < 2e-5
+    out = torch.ones(512, device="cuda")
+    ops.colsum(a, L.BF16X2, 1000, 512, out)
+    assert _rel(out, 1 + _val(a, True).sum(0)) < 1e-5
+    acc = torch.ones(3, 7, device="cuda")
+    ops.batch_sum(torch.arange(2 * 21, device="cuda", dtype=torch.float32).view(2, 3, 7), acc, accumulate=True)
+    assert torch.equal(acc, 1 + torch.arange(21, device="cuda").view(3, 7) * 2.0 + 21)
+
+
+def _attn_ref(qkv, b, L_, heads):
+    E = heads * 64
+    q, k, v = qkv.view(b, L_, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    o = s.softmax(-1) @ v
+    return o.transpose(1, 2).reshape(b * L_, E), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("b,L_,heads", [(2, 197, 12), (1, 1025, 12), (3, 21, 4), (2, 64, 2), (1, 130, 1)])
+@pytest.mark.parametrize("precise", [False, True])
+def test_attention(ops, b, L_, heads, precise):
+    from semivl_b200 import lib as L
+    E = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(L_)
+    qkv = torch.randn(b * L_, 3 * E, device="cuda", generator=g)
+    dout = torch.randn(b * L_, E, device="cuda", generator=g)
+    dvadd = torch.randn(b * L_, E, device="cuda", generator=g)
+    if not precise:
+        qkv, dout = qkv.to(torch.bfloat16).float(), dout.to(torch.bfloat16).float()
+    qr = qkv.clone().requires_grad_(True)
+    ref, ref_lse = _attn_ref(qr, b, L_, heads)
+    ref.backward(dout)
+    ref_d = qr.grad.clone()
+    ref_d[:, 2 * E:] += dvadd
+    a = ops.split_bf16(qkv) if precise else qkv.to(torch.bfloat16)
+    out, lse = ops.attention_fwd(a, b, L_, heads, precise)
+    tol = 3e-5 if precise else 1e-2
+    assert _rel(_val(out, precise), ref) < tol
+    assert _rel(lse, ref_lse) < (1e-5 if precise else 1e-3)
+    da = ops.split_bf16(dout) if precise else dout.to(torch.bfloat16)
+    dqkv = ops.attention_bwd(a, out, da, lse, b, L_, heads, precise, dv_add=dvadd, dv_add_dtype=L.F32)
+    assert _rel(_val(dqkv, precise), ref_d) < (1e-4 if precise else 2e-2)

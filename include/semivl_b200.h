@@ -142,9 +142,10 @@ int svl_l2norm_fwd(const float* x, int64_t ldx, float* y, void* y_act, int act_d
                    int c, float eps, void* stream);
 int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* y, const float* inv_norm, float* dx, int64_t lddx,
                    int accumulate, int64_t rows, int c, void* stream);
-/* dst = scale * src with a storage-type change (scale 0 is treated as 1) */
-int svl_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows, int cols,
-             float scale, void* stream);
+/* dst = scale * src with a storage-type change (scale 0 is treated as 1); `batch` blocks of `rows` rows, block b starting at
+ * element b*batch_stride (dropping / re-inserting the cls token row of [b, L, c] token tensors, maskclip_vit.py:543-546) */
+int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t src_batch_stride, void* dst, int dst_dtype, int64_t ld_dst,
+             int64_t dst_batch_stride, int batch, int64_t rows, int cols, float scale, void* stream);
 /* out[col] += sum_rows x[row, col]  (bias gradients) */
 int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
 /* out[i] (+)= sum_b x[b, i]  (pos_embed gradient, maskclip_vit.py:500) */

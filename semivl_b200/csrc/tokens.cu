@@ -249,21 +249,22 @@ l2norm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const
 }
 
 // ---------------------------------------------------------------------------------------------- utilities
-__global__ void cast_kernel(const void* __restrict__ src, int src_dtype, int64_t ld_src, void* __restrict__ dst, int dst_dtype, int64_t ld_dst,
-                            int64_t rows, int cols, float scale) {
+__global__ void cast_kernel(const void* __restrict__ src, int src_dtype, int64_t ld_src, int64_t sbs, void* __restrict__ dst, int dst_dtype,
+                            int64_t ld_dst, int64_t dbs, int64_t rows_per_batch, int64_t rows, int cols, float scale) {
   const int groups = (cols + 7) / 8;
   const int64_t total = rows * groups;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(idx % groups);
     const int64_t row = idx / groups;
+    const int64_t bi = row / rows_per_batch, ri = row % rows_per_batch;
     const int cnt = min(8, cols - g * 8);
     float f[8];
-    ld8(src, src_dtype, row * ld_src + g * 8, ld_src / 2, cnt, f);
+    ld8(src, src_dtype, bi * sbs + ri * ld_src + g * 8, ld_src / 2, cnt, f);
     if (scale != 1.f) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] *= scale;
     }
-    st8(dst, dst_dtype, row * ld_dst + g * 8, ld_dst / 2, cnt, f);
+    st8(dst, dst_dtype, bi * dbs + ri * ld_dst + g * 8, ld_dst / 2, cnt, f);
   }
 }
 
@@ -370,12 +371,12 @@ extern "C" int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
   return SVL_OK;
 }
 
-extern "C" int svl_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows, int cols,
-                        float scale, void* stream) {
-  SVL_CHECK_ARG(src && dst, "svl_cast: null pointer");
+extern "C" int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t src_batch_stride, void* dst, int dst_dtype, int64_t ld_dst,
+                        int64_t dst_batch_stride, int batch, int64_t rows, int cols, float scale, void* stream) {
+  SVL_CHECK_ARG(src && dst && batch >= 1, "svl_cast: bad arguments");
   if (rows == 0 || cols == 0) return SVL_OK;
-  cast_kernel<<<ew_grid(rows * ((cols + 7) / 8)), 256, 0, (cudaStream_t)stream>>>(src, src_dtype, ld_src, dst, dst_dtype, ld_dst, rows, cols,
-                                                                                 scale == 0.f ? 1.f : scale);
+  cast_kernel<<<ew_grid(batch * rows * ((cols + 7) / 8)), 256, 0, (cudaStream_t)stream>>>(
+      src, src_dtype, ld_src, src_batch_stride, dst, dst_dtype, ld_dst, dst_batch_stride, rows, batch * rows, cols, scale == 0.f ? 1.f : scale);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

@@ -1,0 +1,297 @@
+"""CLIP ViT-B/16 image encoder with MaskCLIP v-path taps: forward and hand-scheduled backward over the C-ABI kernels.
+
+Mirrors MaskClipVisionTransformer.forward / TransformerEncoderLayer.forward(+forward_qkv)
+(third_party/maskclip/models/backbones/maskclip_vit.py:110-144,492-596) for the in-scope configuration
+(pre_norm, final_norm, return_clip_embed, return_qkv, with_cls_token).
+
+Data layout: tokens are rows of [B*L, E]; the residual stream is fp32, every GEMM operand is bf16 (fast) or a split
+bf16 pair (precise).  Only `attn.*` weights/biases and `pos_embed` receive gradients (model/vlm.py:80-88): the backward
+runs dgrad everywhere and wgrad only for in_proj / out_proj.
+"""
+import torch
+import torch.nn.functional as F
+
+from .. import lib as L
+from .. import ops
+
+
+class WeightCache:
+    """bf16 (or split) GEMM-operand copies of fp32 parameters, refreshed when the parameter's version changes."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, key, param, fn):
+        ver = (param.data_ptr(), param._version)
+        hit = self._c.get(key)
+        if hit is None or hit[0] != ver:
+            with torch.no_grad():
+                hit = (ver, fn(param.detach()))
+            self._c[key] = hit
+        return hit[1]
+
+    def clear(self):
+        self._c.clear()
+
+
+class VitCfg:
+    def __init__(self, embed=768, heads=12, layers=12, patch=16, out_indices=(0, 4, 12), eps=1e-6, proj_dim=512, img_size=512):
+        self.embed, self.heads, self.layers, self.patch = embed, heads, layers, patch
+        self.out_indices, self.eps, self.proj_dim, self.img_size = tuple(out_indices), eps, proj_dim, img_size
+
+
+class VitEngine:
+    """Functional encoder over a parameter dict `p` (reference names without prefix, e.g. 'layers.0.attn.attn.in_proj_weight')."""
+
+    def __init__(self, cfg, precise=False):
+        self.cfg = cfg
+        self.precise = precise
+        self.cache = WeightCache()
+
+    # ------------------------------------------------------------------ weights
+    def _w(self, p, name, transpose=False, rows=None):
+        """GEMM operand of parameter `name` viewed as 2-D [out, in] (transpose=True -> [in, out] for data gradients)."""
+        prm = p[name]
+        key = (name, transpose, self.precise)
+
+        def make(t):
+            t2 = t.reshape(t.shape[0], -1).float()
+            if transpose:
+                t2 = t2.t().contiguous()
+            return ops.prep_weight(t2, self.precise)
+        return self.cache.get(key, prm, make)
+
+    def _tap_layers(self):
+        c = self.cfg
+        taps = {i for i in c.out_indices if i < c.layers}
+        taps.add(c.layers - 1)
+        return taps
+
+    # ------------------------------------------------------------------ pos embed (maskclip_vit.py:431-490)
+    def _pos(self, p, hp, wp, need_grad):
+        pos = p["pos_embed"]                                  # [1, 1 + g*g, E]
+        if pos.shape[1] == hp * wp + 1:
+            return pos[0], None
+        g = int(round((pos.shape[1] - 1) ** 0.5))
+        src = pos.detach()
+        if need_grad:
+            src = src.clone().requires_grad_(True)
+        with torch.enable_grad() if need_grad else torch.no_grad():
+            grid = src[:, 1:].reshape(1, g, g, -1).permute(0, 3, 1, 2)
+            grid = F.interpolate(grid, size=(hp, wp), mode="bicubic", align_corners=False)      # ATen bicubic (rare path: crop % 16 != 0)
+            out = torch.cat((src[:, :1], grid.flatten(2).transpose(1, 2)), dim=1)[0]
+        return out.detach().contiguous(), ((src, out) if need_grad else None)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, img, p, need_grad=True, want_global=True):
+        """img f32 [B,3,H,W] -> (feats: list of f32 [B,h,w,C] contiguous NHWC (taps..., clip embedding), global [B,512] or None, ctx)."""
+        c, pr = self.cfg, self.precise
+        E, H = c.embed, c.heads
+        B = img.shape[0]
+        img = img.contiguous().float()
+        a, hp, wp = ops.patchify(img, pr, c.patch)
+        hw = hp * wp
+        Lq = hw + 1
+        M = B * Lq
+        dev = img.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        ctx = dict(B=B, hp=hp, wp=wp, layers=[]) if need_grad else None
+
+        patches = torch.empty(B * hw, E, **f32)
+        ops.gemm(a, self._w(p, "patch_embed.projection.weight"), patches, n=E, k=3 * c.patch * c.patch, precise=pr,
+                 bias=p.get("patch_embed.projection.bias"))
+        pos, pos_ctx = self._pos(p, hp, wp, need_grad)
+        x0 = ops.assemble_tokens(patches, p["cls_token"].reshape(-1), pos, B, hw).view(M, E)
+        x, mu0, rs0 = ops.layernorm_fwd(x0, p["ln0.weight"], p["ln0.bias"], c.eps, out_dtype=L.F32, save_stats=need_grad)
+        if need_grad:
+            ctx.update(x0=x0, mu0=mu0, rs0=rs0, pos_ctx=pos_ctx)
+
+        taps = self._tap_layers()
+        feats_v = {}
+        pre_dt = torch.float32 if pr else torch.bfloat16
+        for i in range(c.layers):
+            pre = f"layers.{i}."
+            want_v = i in taps
+            last = i == c.layers - 1
+            S = {}
+            y, mu1, rs1 = ops.layernorm_fwd(x, p[pre + "ln1.weight"], p[pre + "ln1.bias"], c.eps, precise=pr, save_stats=need_grad)
+            qkv = ops.new_act(M, 3 * E, pr, dev)
+            ops.gemm(y, self._w(p, pre + "attn.attn.in_proj_weight"), qkv, n=3 * E, k=E, precise=pr, bias=p[pre + "attn.attn.in_proj_bias"],
+                     out_dtype=ops.act_dtype(pr))
+            wout = self._w(p, pre + "attn.attn.out_proj.weight")
+            bout = p[pre + "attn.attn.out_proj.bias"]
+            w1, b1 = self._w(p, pre + "ffn.layers.0.0.weight"), p[pre + "ffn.layers.0.0.bias"]
+            w2, b2 = self._w(p, pre + "ffn.layers.1.weight"), p[pre + "ffn.layers.1.bias"]
+            g2, be2 = p[pre + "ln2.weight"], p[pre + "ln2.bias"]
+            x_in = x
+            need_x = (not last) or want_global           # the x path after the last layer only feeds the global embedding
+            if need_x:
+                att, lse = ops.attention_fwd(qkv, B, Lq, H, pr, want_lse=need_grad)
+                x_mid = torch.empty(M, E, **f32)
+                ops.gemm(att, wout, x_mid, n=E, k=E, precise=pr, bias=bout, residual=x_in)
+                y2, mu2, rs2 = ops.layernorm_fwd(x_mid, g2, be2, c.eps, precise=pr, save_stats=need_grad)
+                hpre = torch.empty(M, 4 * E, device=dev, dtype=pre_dt) if (need_grad and not last) else None
+                hact = ops.new_act(M, 4 * E, pr, dev)
+                ops.gemm(y2, w1, hact, n=4 * E, k=E, precise=pr, bias=b1, act=L.ACT_GELU, preact_out=hpre, out_dtype=ops.act_dtype(pr))
+                x = torch.empty(M, E, **f32)
+                ops.gemm(hact, w2, x, n=E, k=4 * E, precise=pr, bias=b2, residual=x_mid)
+                del hact, y2
+                if need_grad and not last:
+                    S.update(att=att, lse=lse, x_mid=x_mid, mu2=mu2, rs2=rs2, hpre=hpre)
+            if want_v:
+                # MaskCLIP v-path (forward_qkv, maskclip_vit.py:110-118,131-132): out_proj applied to V, + x, then the FFN block
+                v1 = torch.empty(M, E, **f32)
+                ops.gemm(qkv, wout, v1, n=E, k=E, precise=pr, a_koff=2 * E, bias=bout, residual=x_in)
+                yv, muv, rsv = ops.layernorm_fwd(v1, g2, be2, c.eps, precise=pr, save_stats=need_grad)
+                vpre = torch.empty(M, 4 * E, device=dev, dtype=pre_dt) if need_grad else None
+                hv = ops.new_act(M, 4 * E, pr, dev)
+                ops.gemm(yv, w1, hv, n=4 * E, k=E, precise=pr, bias=b1, act=L.ACT_GELU, preact_out=vpre, out_dtype=ops.act_dtype(pr))
+                v2 = torch.empty(M, E, **f32)
+                ops.gemm(hv, w2, v2, n=E, k=4 * E, precise=pr, bias=b2, residual=v1)
+                del hv, yv
+                feats_v[i] = v2
+                if need_grad:
+                    S.update(v1=v1, muv=muv, rsv=rsv, vpre=vpre)
+            if need_grad:
+                S.update(x_in=x_in, y=y, qkv=qkv, mu1=mu1, rs1=rs1, has_x=need_x and not last, has_v=want_v)
+                ctx["layers"].append(S)
+
+        # final norm + CLIP projection (maskclip_vit.py:538-555,588-589)
+        gf, bf = p["ln1.weight"], p["ln1.bias"]
+        wproj = self._w(p, "proj.weight")
+        v_last = feats_v[c.layers - 1]
+        vn, muf, rsf = ops.layernorm_fwd(v_last, gf, bf, c.eps, precise=pr, save_stats=need_grad)
+        emb_raw = torch.empty(M, c.proj_dim, **f32)
+        ops.gemm(vn, wproj, emb_raw, n=c.proj_dim, k=E, precise=pr)
+        emb_n, _, inv = ops.l2norm_fwd(emb_raw, eps=0.0)          # x / x.norm() (no eps clamp in the reference)
+        glob = None
+        if want_global:
+            xn, _, _ = ops.layernorm_fwd(x.view(B, Lq * E)[:, :E], gf, bf, c.eps, precise=pr, save_stats=False, ldx=Lq * E)
+            graw = torch.empty(B, c.proj_dim, **f32)
+            ops.gemm(xn, wproj, graw, n=c.proj_dim, k=E, precise=pr)
+            glob, _, _ = ops.l2norm_fwd(graw, eps=0.0)
+        if need_grad:
+            ctx.update(v_last=v_last, muf=muf, rsf=rsf, emb_n=emb_n, inv=inv)
+
+        def drop_cls(t, C):
+            out = torch.empty(B, hp, wp, C, **f32)
+            ops.cast(t, L.F32, out, L.F32, hw, C, ld_src=C, ld_dst=C, batch=B, src_batch_stride=Lq * C, dst_batch_stride=hw * C, src_offset=C)
+            return out
+        feats = [drop_cls(feats_v[i], E) for i in c.out_indices if i < c.layers]
+        if c.layers in c.out_indices:
+            feats.append(drop_cls(emb_n, c.proj_dim))
+        return feats, glob, ctx
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, ctx, dfeats, p, grads):
+        """dfeats: list (same order as forward's feats) of f32 [B,h,w,C] contiguous or None.
+        `grads` maps parameter name -> f32 gradient tensor (same shape as the parameter), accumulated in place."""
+        c, pr = self.cfg, self.precise
+        E, H = c.embed, c.heads
+        B, hp, wp = ctx["B"], ctx["hp"], ctx["wp"]
+        hw = hp * wp
+        Lq = hw + 1
+        M = B * Lq
+        dev = ctx["x0"].device
+        f32 = dict(device=dev, dtype=torch.float32)
+        gdt = L.F32 if pr else L.BF16                       # storage of intermediate (non-operand) gradients
+        gtorch = torch.float32 if pr else torch.bfloat16
+
+        def add_cls(g, C):
+            out = torch.zeros(B, Lq, C, **f32)
+            ops.cast(g.contiguous(), L.F32, out, L.F32, hw, C, ld_src=C, ld_dst=C, batch=B, src_batch_stride=hw * C, dst_batch_stride=Lq * C,
+                     dst_offset=C)
+            return out.view(M, C)
+
+        tap_ids = [i for i in c.out_indices if i < c.layers]
+        dv = {}
+        for i, g in zip(tap_ids, dfeats[:len(tap_ids)]):
+            if g is not None:
+                dv[i] = add_cls(g, E)
+        demb = dfeats[len(tap_ids)] if c.layers in c.out_indices and len(dfeats) > len(tap_ids) else None
+        if demb is not None:
+            d_embn = add_cls(demb, c.proj_dim)
+            d_raw = torch.empty(M, c.proj_dim, **f32)
+            ops.l2norm_bwd(d_embn, L.F32, ctx["emb_n"], ctx["inv"], d_raw)
+            d_vn = torch.empty(M, E, device=dev, dtype=gtorch)
+            ops.gemm(ops.to_act(d_raw, pr), self._w(p, "proj.weight", transpose=True), d_vn, n=E, k=c.proj_dim, precise=pr)
+            last = c.layers - 1
+            dlast, _ = ops.layernorm_bwd(d_vn, gdt, ctx["v_last"], p["ln1.weight"], ctx["muf"], ctx["rsf"], dres1=dv.get(last))
+            dv[last] = dlast
+
+        def wg(name):
+            return grads[name]
+
+        dx, dx_act = None, None          # gradient of the residual stream entering the layer above
+        for i in reversed(range(c.layers)):
+            S = ctx["layers"][i]
+            pre = f"layers.{i}."
+            wout_t = self._w(p, pre + "attn.attn.out_proj.weight", transpose=True)
+            win_t = self._w(p, pre + "attn.attn.in_proj_weight", transpose=True)
+            w1_t = self._w(p, pre + "ffn.layers.0.0.weight", transpose=True)
+            w2_t = self._w(p, pre + "ffn.layers.1.weight", transpose=True)
+            g_wout, g_bout = wg(pre + "attn.attn.out_proj.weight"), wg(pre + "attn.attn.out_proj.bias")
+            g_win, g_bin = wg(pre + "attn.attn.in_proj_weight"), wg(pre + "attn.attn.in_proj_bias")
+            g2 = p[pre + "ln2.weight"]
+            dv2 = dv.get(i) if S["has_v"] else None
+            dv1 = dvv = None
+            have_x = dx is not None and S["has_x"]
+            if dv2 is not None:
+                dhv = ops.new_act(M, 4 * E, pr, dev)
+                ops.gemm(ops.to_act(dv2, pr), w2_t, dhv, n=4 * E, k=E, precise=pr, dact_src=S["vpre"], dact_kind=L.ACT_GELU,
+                         out_dtype=ops.act_dtype(pr))
+                dyv = torch.empty(M, E, device=dev, dtype=gtorch)
+                ops.gemm(dhv, w1_t, dyv, n=E, k=4 * E, precise=pr)
+                del dhv
+                dv1, dv1_act = ops.layernorm_bwd(dyv, gdt, S["v1"], g2, S["muv"], S["rsv"], dres1=dv2, act_precise=pr)
+                ops.wgrad(dv1_act, S["qkv"], g_wout, m=E, n=E, precise=pr, x_koff=2 * E)
+                ops.colsum(dv1, L.F32, M, E, g_bout)
+                if have_x:
+                    dvv = torch.empty(M, E, device=dev, dtype=gtorch)
+                    ops.gemm(dv1_act, wout_t, dvv, n=E, k=E, precise=pr)
+                else:                                        # consumed as a GEMM operand below
+                    dvv = ops.new_act(M, E, pr, dev)
+                    ops.gemm(dv1_act, wout_t, dvv, n=E, k=E, precise=pr, out_dtype=ops.act_dtype(pr))
+            if have_x:
+                if dx_act is None:
+                    dx_act = ops.to_act(dx, pr)
+                dh = ops.new_act(M, 4 * E, pr, dev)
+                ops.gemm(dx_act, w2_t, dh, n=4 * E, k=E, precise=pr, dact_src=S["hpre"], dact_kind=L.ACT_GELU, out_dtype=ops.act_dtype(pr))
+                dy2 = torch.empty(M, E, device=dev, dtype=gtorch)
+                ops.gemm(dh, w1_t, dy2, n=E, k=4 * E, precise=pr)
+                del dh
+                dx_mid, dx_mid_act = ops.layernorm_bwd(dy2, gdt, S["x_mid"], g2, S["mu2"], S["rs2"], dres1=dx, act_precise=pr)
+                ops.wgrad(dx_mid_act, S["att"], g_wout, m=E, n=E, precise=pr)
+                ops.colsum(dx_mid, L.F32, M, E, g_bout)
+                datt = ops.new_act(M, E, pr, dev)
+                ops.gemm(dx_mid_act, wout_t, datt, n=E, k=E, precise=pr, out_dtype=ops.act_dtype(pr))
+                dqkv = ops.attention_bwd(S["qkv"], S["att"], datt, S["lse"], B, Lq, H, pr, dv_add=dvv, dv_add_dtype=gdt)
+                ops.wgrad(dqkv, S["y"], g_win, m=3 * E, n=E, precise=pr)
+                ops.colsum(dqkv, ops.act_dtype(pr), M, 3 * E, g_bin)
+                dy1 = torch.empty(M, E, device=dev, dtype=gtorch)
+                ops.gemm(dqkv, win_t, dy1, n=E, k=3 * E, precise=pr)
+                dx, dx_act = ops.layernorm_bwd(dy1, gdt, S["x_in"], p[pre + "ln1.weight"], S["mu1"], S["rs1"], dres1=dx_mid, dres2=dv1,
+                                               act_precise=pr)
+            elif dvv is not None:
+                # only the V third of in_proj sees a gradient (no gradient reaches this layer's attention output)
+                dvv_act = dvv
+                ops.wgrad(dvv_act, S["y"], g_win[2 * E:], m=E, n=E, precise=pr)
+                ops.colsum(dvv, ops.act_dtype(pr), M, E, g_bin[2 * E:])
+                dy1 = torch.empty(M, E, device=dev, dtype=gtorch)
+                wv_t = self._w(p, pre + "attn.attn.in_proj_weight", transpose=True)            # [E, 3E]: columns 2E.. are the V rows
+                ops.gemm(dvv_act, wv_t, dy1, n=E, k=E, precise=pr, b_col0=2 * E)
+                dx, dx_act = ops.layernorm_bwd(dy1, gdt, S["x_in"], p[pre + "ln1.weight"], S["mu1"], S["rs1"], dres1=dx, dres2=dv1,
+                                               act_precise=pr)
+            # else: nothing reaches this layer (cannot happen with the reference's tap configuration)
+
+        if dx is not None:
+            dx0, _ = ops.layernorm_bwd(dx, L.F32, ctx["x0"], p["ln0.weight"], ctx["mu0"], ctx["rs0"])
+            dpos = torch.empty(Lq, E, **f32)
+            ops.batch_sum(dx0.view(B, Lq * E), dpos.view(-1))
+            if ctx["pos_ctx"] is None:
+                ops.axpy(grads["pos_embed"].view(-1), dpos.view(-1))
+            else:
+                src, out = ctx["pos_ctx"]
+                out.backward(dpos)                               # ATen bicubic backward (crop % 16 != 0 only)
+                ops.axpy(grads["pos_embed"].view(-1), src.grad.contiguous().view(-1))
+        return grads

@@ -33,7 +33,7 @@ def _set_taps(d, taps):
 def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0, a_koff=0, out_dtype=None, ldc=None,
          bias=None, act=L.ACT_NONE, alpha=1.0, residual=None, preact_out=None, dact_src=None, dact_kind=L.ACT_NONE,
          dact_split=False, row_bias=None, row_bias_div=1, accumulate=False, out_mode=L.OUT_LINEAR, out_hw=None,
-         block_n=0, m=None, lda=None, a_cols=None):
+         block_n=0, m=None, lda=None, a_cols=None, b_col0=0):
     """out = epilogue(sum_taps A_t @ B_t^T).
 
     a     : bf16 tensor; 2-D [M, lda] or (conv=(nb,h,w)) NHWC [nb,h,w,lda]; split (hi|lo) when precise
@@ -61,10 +61,10 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
     taps = []
     for t, (dy, dx) in enumerate(filt if filt is not None else [(0, 0)]):
         br = t * b_row_stride
-        taps.append((dy, dx, a_koff, br, 0))
+        taps.append((dy, dx, a_koff, br, b_col0))
         if precise:
-            taps.append((dy, dx, a_koff, br, kl_b))
-            taps.append((dy, dx, a_koff + kl_a, br, 0))
+            taps.append((dy, dx, a_koff, br, b_col0 + kl_b))
+            taps.append((dy, dx, a_koff + kl_a, br, b_col0))
     _set_taps(d, taps)
     d.out = out.data_ptr()
     d.out_dtype = out_dtype if out_dtype is not None else L.dtype_of(out)
@@ -191,9 +191,13 @@ def l2norm_bwd(dy, dy_dtype, y, inv, dx, *, accumulate=False, lddy=None):
     return dx
 
 
-def cast(src, src_dtype, dst, dst_dtype, rows, cols, *, ld_src=None, ld_dst=None, scale=1.0):
-    L.call("svl_cast", src, src_dtype, ld_src if ld_src is not None else src.shape[-1], dst, dst_dtype,
-           ld_dst if ld_dst is not None else dst.shape[-1], rows, cols, scale)
+def cast(src, src_dtype, dst, dst_dtype, rows, cols, *, ld_src=None, ld_dst=None, scale=1.0, batch=1, src_batch_stride=0,
+         dst_batch_stride=0, src_offset=0, dst_offset=0):
+    """dst = scale * src, changing the storage type; `batch` blocks of `rows` rows (block strides / element offsets optional)."""
+    esz_s, esz_d = src.element_size(), dst.element_size()
+    L.call("svl_cast", src.data_ptr() + src_offset * esz_s, src_dtype, ld_src if ld_src is not None else src.shape[-1], src_batch_stride,
+           dst.data_ptr() + dst_offset * esz_d, dst_dtype, ld_dst if ld_dst is not None else dst.shape[-1], dst_batch_stride, batch, rows,
+           cols, scale)
     return dst
 
 

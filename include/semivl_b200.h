@@ -62,7 +62,9 @@ typedef struct {
   int64_t m;            /* output rows */
   int64_t lda;          /* elements per row / pixel */
   int64_t a_cols;       /* valid columns from `a` (TMA inner extent); 0 = lda */
-  int nb, h, w;         /* a_conv geometry */
+  int nb, h, w;         /* a_conv geometry (of the output pixel grid) */
+  int a_map_w;          /* a_conv: row length (pixels) of the A tensor when it differs from w (0 = w).  Used to read a
+                           [nb, 2h, 2w, c] tensor as [nb, h, 2w', 2c] with w' = w: the transposed-conv data gradient */
   /* ---- B operand: weights, bf16, [b_rows, ldb], K contiguous ---- */
   const void* b;
   int64_t b_rows;
@@ -113,6 +115,7 @@ typedef struct {
   int tap_dy[SVL_MAX_TAPS], tap_dx[SVL_MAX_TAPS];   /* x is read at pixel + (dy, dx), zero outside the image */
   int tap_dy_koff[SVL_MAX_TAPS], tap_x_koff[SVL_MAX_TAPS];
   int tap_slot[SVL_MAX_TAPS];                       /* output slot per tap; ascending, taps of one slot contiguous */
+  int x_map_w;                                      /* conv: row length (pixels) of the x tensor when it differs from w (0 = w); see svl_gemm_desc.a_map_w */
   float* dw; int64_t ld_dw; int64_t slot_stride;
   float alpha;                                      /* 0 is treated as 1 */
   int splits;                                       /* 0 = auto */
@@ -163,6 +166,77 @@ int svl_attention_fwd(const void* qkv, int split, void* out, float* lse, int b, 
 int svl_attention_bwd(const void* qkv, const void* out, const void* dout, int split, const float* lse, float* delta_ws,
                       const void* dv_add, int dv_add_dtype, int64_t ld_dv_add, void* dqkv, int b, int L, int heads, float scale,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VLG decode head kernels (model/decode_heads/vlg_head.py).  Activations are NHWC, a "map" is one (image, class) pair,
+ * maps ordered (image, class).  HBM-bound: vectorised 16-byte accesses, one pass (two for GroupNorm, second L2-resident).
+ * ---------------------------------------------------------------------------------------------- */
+/* out = relu(GroupNorm(x)) (+ res); statistics per (map, group) saved to mean/rstd [maps, G]   (vlg_head.py:99-111,132-135) */
+int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
+                    int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, int64_t maps, int hw, int C,
+                    int G, float eps, void* stream);
+/* dx = GN'(dy * [y > 0]); dgamma/dbeta += (atomics) */
+int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const float* gamma,
+                    const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int64_t lddx, float* dgamma,
+                    float* dbeta, int64_t maps, int hw, int C, int G, void* stream);
+/* im2col of the per-class similarity maps for conv1 (ks x ks, 1 -> C; vlg_head.py:169,220-221) and its transpose */
+int svl_sim_im2col(const float* sim, int64_t ld_sim, void* out, int out_dtype, int64_t ldo, int B, int N, int h, int w, int ks, int kpad,
+                   void* stream);
+int svl_sim_col2im(const void* dcol, int dtype, int64_t ld, void* dsim, int ds_dtype, int64_t ld_ds, int ncols, int B, int N, int h,
+                   int w, int ks, void* stream);
+/* out[map, c] = scale * sum_pix x[map, pix, c] (ASPP image pooling, vlg_head.py:70-81);  x[map, pix, c] += scale * v[map, c] */
+int svl_map_sum(const void* x, int dtype, int64_t ld, float* out, int64_t maps, int hw, int C, float scale, void* stream);
+int svl_map_bcast_add(float* x, const void* v, int v_dtype, int64_t ldv, int64_t maps, int hw, int C, float scale, void* stream);
+/* SemanticTransformer (vlg_head.py:39-67): tokens [(b, py, px), n, C + Ct] = (avg-pooled feature | projected text);
+ * un-pooling = bilinear (align_corners=True) of the first C token channels added to the feature map. */
+int svl_pool_tokens(const void* x, int x_dtype, int64_t ldx, const float* text, float* tok, int B, int N, int h, int w, int C, int Ct,
+                    int pool, void* stream);
+int svl_pool_tokens_bwd(const float* dtok, int64_t ldt, float* dx, int B, int N, int h, int w, int C, int pool, void* stream);
+int svl_unpool_add(const void* x, int x_dtype, int64_t ldx, const float* tok, int64_t ldt, void* out, int out_dtype, int64_t ldo, int B,
+                   int N, int h, int w, int C, int hp, int wp, void* stream);
+int svl_unpool_bwd(const void* dout, int dtype, int64_t ld, float* dtok, int64_t ldt, int B, int N, int h, int w, int C, int hp, int wp,
+                   void* stream);
+/* Up (vlg_head.py:116-137): channels [c0, c0+Cs) of the concat buffer = bilinear (align_corners=True) skip, repeated over classes;
+ * gradient w.r.t. the pre-ReLU skip projection. */
+int svl_skip_fill(const void* skip, int s_dtype, int64_t lds, void* cat, int c_dtype, int64_t ldc, int c0, int B, int N, int h, int w,
+                  int Cs, int H2, int W2, void* stream);
+int svl_skip_grad(const void* dcat, int d_dtype, int64_t ldd, int c0, const void* skip, int s_dtype, int64_t lds, void* dskip,
+                  int o_dtype, int64_t ldo, int B, int N, int h, int w, int Cs, int H2, int W2, void* stream);
+/* output conv 3x3, C -> 1 (vlg_head.py:190,239-240); wgt/dw layout [9][C] */
+int svl_conv_out1_fwd(const void* x, int dtype, int64_t ld, const float* wgt, const float* bias, float* out, int64_t maps, int h, int w,
+                      int C, void* stream);
+int svl_conv_out1_bwd(const float* dout, const void* x, int x_dtype, int64_t ldx, const float* wgt, void* dx, int dx_dtype, int64_t lddx,
+                      float* dw, float* dbias, int64_t maps, int h, int w, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Logit-side kernels.  `low` are the head's 4x-resolution class maps [R, N, hl, wl] f32; full-resolution logits
+ * [R, N, H, W] = bilinear(low, align_corners=False) (vlg_head.py:247-248; the second resize of builder.py:93-97 is the identity).
+ * ---------------------------------------------------------------------------------------------- */
+int svl_upsample_bilinear(const float* low, float* out, int64_t planes, int hl, int wl, int H, int W, void* stream);
+int svl_upsample_bilinear_bwd(const float* dout, float* dlow, int64_t planes, int hl, int wl, int H, int W, void* stream);   /* dlow += */
+/* conf = max_n softmax(scale * logits), label = argmax; label = 255 where conf < thresh (thresh > 0)
+ * (semivl.py:231-232,251-252; model/vlm.py:103-109 with scale 100) -- the full-resolution logits are never materialised */
+int svl_softmax_max(const float* low, float* conf, int64_t* label, int64_t R, int N, int hl, int wl, int H, int W, float scale,
+                    float thresh, void* stream);
+/* Fused upsample + per-pixel cross-entropy forward AND backward for up to 3 target sets on the same logits:
+ *   loss[t] += coef[t] * sum_pix weight_t[pix] * CE(logits[pix], label_t[pix])      (label == ignore_index contributes 0)
+ *   dlow    += gscale * d(sum_t loss[t]) / d low                                     (skipped when dlow == NULL)
+ * labels[t]: int64 [R,H,W]; weights[t]: f32 [R,H,W] or NULL; coefs[t]: DEVICE scalar (e.g. 1/valid-count, no host sync).
+ * replaces semivl.py:52-58,266-323 and utils/train_utils.py:30-49 (F.cross_entropy x7 + masks + reductions). */
+int svl_upsample_ce(const float* low, float* dlow, int R, int N, int hl, int wl, int H, int W, int num_targets,
+                    const int64_t* const* labels, const float* const* weights, const float* const* coefs, float* loss, float gscale,
+                    int ignore_index, void* stream);
+int svl_count_valid(const int64_t* label, int64_t n, int ignore_index, float* count, void* stream);        /* count += #(label != ignore) */
+int svl_reciprocal(const float* count, float* out, float numer, float floor_, void* stream);               /* out = numer / max(count, floor) */
+/* CutMix of pseudo-labels / confidences / ignore masks (utils/train_utils.py:24-27) fused with the 'pixelwise' confidence
+ * weight of utils/train_utils.py:36-39: w = (conf >= thresh) & (ign != 255); valid_count += #(ign != 255).  NULL inputs are skipped. */
+int svl_cutmix_weights(const int64_t* lab_a, const int64_t* lab_b, const float* conf_a, const float* conf_b, const int64_t* ign_a,
+                       const int64_t* ign_b, const float* box, int64_t* lab_out, float* w_out, int64_t* ign_out, float* valid_count,
+                       int64_t n, float thresh, void* stream);
+int svl_cutmix_img(const float* a, const float* b, const float* box, float* out, int B, int C, int64_t hw, void* stream);
+/* torch.optim.AdamW single-tensor update on a flat buffer (semivl.py:326-328; experiments.py:246-255); g is scaled by gscale first */
+int svl_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+              int step, float gscale, void* stream);
 
 #ifdef __cplusplus
 }

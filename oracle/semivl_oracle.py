@@ -182,7 +182,7 @@ def vlg_head_forward(feats, text, p, cfg, pre="decode_head.", class_to_concept=N
     img = feats[-1]
     skips = list(feats[:-1])[::-1]
     B, C, H, W = img.shape
-    text = text.float()[None].expand(B, -1, -1)
+    text = text.to(img.dtype)[None].expand(B, -1, -1)
     N = text.shape[1]
     x = torch.einsum("bchw,bnc->bnhw", F.normalize(img, dim=1), F.normalize(text, dim=-1))
     x = x.reshape(B * N, 1, H, W)
@@ -232,7 +232,7 @@ def forward_maskclip(img, p, mcc_text, cfg, conf_thresh, pos_img_size=512, class
     """VLM.forward_maskclip (vlm.py:90-110): frozen clip_encoder -> labels int64, 255 = low confidence."""
     with torch.no_grad():
         feats, _ = vit_forward(img, p, cfg, pre="clip_encoder.", out_indices=(cfg.layers,), pos_img_size=pos_img_size)
-        dense = F.conv2d(feats[-1], mcc_text.float()[:, :, None, None])
+        dense = F.conv2d(feats[-1], mcc_text.to(feats[-1].dtype)[:, :, None, None])
         if class_to_concept is not None:
             dense = aggregate_concepts(dense, class_to_concept)
         dense = F.interpolate(dense, size=img.shape[-2:], mode="bilinear", align_corners=cfg.align_corners)

@@ -318,8 +318,9 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     SVL_CHECK_ARG(mt < (1ll << 30), "svl_gemm: too many tiles");
     p.num_m_tiles = (int)mt;
     p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
-    uint64_t dims[4] = {(uint64_t)a_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
-    uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->w, (uint64_t)d->lda * 2 * d->w * d->h};
+    const uint64_t mw = d->a_map_w > 0 ? d->a_map_w : d->w;
+    uint64_t dims[4] = {(uint64_t)a_cols, mw, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * mw, (uint64_t)d->lda * 2 * mw * d->h};
     uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     if (int rc = tma_encode_bf16(&tmA, d->a, 4, dims, strides, box)) return rc;
   } else {

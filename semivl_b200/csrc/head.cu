@@ -1,0 +1,578 @@
+// HBM-bound kernels of the VLG decode head (model/decode_heads/vlg_head.py): GroupNorm+ReLU fwd/bwd, the 7x7 im2col of the
+// similarity maps and its transpose, global-average pooling, the class-token pooling / un-pooling around the
+// SemanticTransformer, the skip-feature upsample + concat and its gradient, and the 32->1 output conv.
+// Activations are NHWC; a "map" is one (image, class) pair, maps are ordered (image, class).
+#include "common.cuh"
+
+namespace svl {
+namespace {
+
+inline int ew_grid(int64_t total, int block = 256) {
+  int64_t b = cdiv(total, block);
+  int64_t cap = 148 * 32;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm + ReLU
+// one CTA per map; pass 1 statistics, pass 2 (L2-resident re-read) normalise + ReLU (+ residual)
+constexpr int kGnThreads = 512;
+constexpr int kMaxGroups = 16;
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_relu_fwd_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   void* __restrict__ out, int out_dtype, int64_t ldo, const void* __restrict__ res, int res_dtype, int64_t ldres,
+                   float* __restrict__ mean, float* __restrict__ rstd, int hw, int C, int G, float eps) {
+  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups], s_mu[kMaxGroups], s_rs[kMaxGroups];
+  const int map = blockIdx.x;
+  const int vpp = C / 8;                         // 8-channel vectors per pixel
+  const int cpg = C / G;
+  const int64_t nvec = (int64_t)hw * vpp;
+  if (threadIdx.x < kMaxGroups) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int64_t xbase = (int64_t)map * hw * ldx;
+  // kGnThreads % vpp == 0 -> a thread always sees the same 8 channels, hence one group
+  const int c8 = (threadIdx.x % vpp) * 8;
+  const int g = c8 / cpg;
+  float pa = 0.f, pb = 0.f;
+  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
+    float f[8];
+    ld8(x, x_dtype, xbase + (v / vpp) * ldx + c8, ldx / 2, 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pa += f[i]; pb += f[i] * f[i]; }
+  }
+  atomicAdd(&s_sum[g], pa);
+  atomicAdd(&s_sq[g], pb);
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const float n = (float)hw * cpg;
+    const float mu = s_sum[threadIdx.x] / n;
+    const float var = fmaxf(s_sq[threadIdx.x] / n - mu * mu, 0.f);
+    const float rs = rsqrtf(var + eps);
+    s_mu[threadIdx.x] = mu;
+    s_rs[threadIdx.x] = rs;
+    if (mean) mean[(int64_t)map * G + threadIdx.x] = mu;
+    if (rstd) rstd[(int64_t)map * G + threadIdx.x] = rs;
+  }
+  __syncthreads();
+  const float mu = s_mu[g], rs = s_rs[g];
+  float ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i] * rs; be[i] = beta[c8 + i] - mu * ga[i]; }
+  const int64_t obase = (int64_t)map * hw * ldo, rbase = (int64_t)map * hw * ldres;
+  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
+    const int64_t pix = v / vpp;
+    float f[8];
+    ld8(x, x_dtype, xbase + pix * ldx + c8, ldx / 2, 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i] * ga[i] + be[i], 0.f);
+    if (res) {
+      float r[8];
+      ld8(res, res_dtype, rbase + pix * ldres + c8, ldres / 2, 8, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+    st8(out, out_dtype, obase + pix * ldo + c8, ldo / 2, 8, f);
+  }
+}
+
+// dx = GN'(dy * relu'(y)); dgamma/dbeta accumulated with atomics
+__global__ void __launch_bounds__(kGnThreads)
+gn_relu_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const void* __restrict__ x, int x_dtype, int64_t ldx,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, void* __restrict__ dx, int dx_dtype, int64_t lddx, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, int hw, int C, int G) {
+  __shared__ float s_s1[kMaxGroups], s_s2[kMaxGroups];
+  __shared__ float s_dg[256], s_db[256];
+  const int map = blockIdx.x;
+  const int vpp = C / 8, cpg = C / G;
+  const int64_t nvec = (int64_t)hw * vpp;
+  if (threadIdx.x < kMaxGroups) s_s1[threadIdx.x] = s_s2[threadIdx.x] = 0.f;
+  if (threadIdx.x < 256) s_dg[threadIdx.x] = s_db[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int c8 = (threadIdx.x % vpp) * 8;
+  const int g = c8 / cpg;
+  const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
+  float ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i]; be[i] = beta[c8 + i]; }
+  const int64_t xbase = (int64_t)map * hw * ldx, ybase = (int64_t)map * hw * lddy, obase = (int64_t)map * hw * lddx;
+  float s1 = 0.f, s2 = 0.f, dg[8], db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
+  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
+    const int64_t pix = v / vpp;
+    float xv[8], d[8];
+    ld8(x, x_dtype, xbase + pix * ldx + c8, ldx / 2, 8, xv);
+    ld8(dy, dy_dtype, ybase + pix * lddy + c8, lddy / 2, 8, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (xv[i] - mu) * rs;
+      const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
+      dg[i] += dd * xh;
+      db[i] += dd;
+      const float gg = dd * ga[i];
+      s1 += gg;
+      s2 += gg * xh;
+    }
+  }
+  atomicAdd(&s_s1[g], s1);
+  atomicAdd(&s_s2[g], s2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { atomicAdd(&s_dg[c8 + i], dg[i]); atomicAdd(&s_db[c8 + i], db[i]); }
+  __syncthreads();
+  if (threadIdx.x < C && dgamma) {
+    atomicAdd(dgamma + threadIdx.x, s_dg[threadIdx.x]);
+    atomicAdd(dbeta + threadIdx.x, s_db[threadIdx.x]);
+  }
+  const float n = (float)hw * cpg;
+  const float m1 = s_s1[g] / n, m2 = s_s2[g] / n;
+  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
+    const int64_t pix = v / vpp;
+    float xv[8], d[8], o[8];
+    ld8(x, x_dtype, xbase + pix * ldx + c8, ldx / 2, 8, xv);
+    ld8(dy, dy_dtype, ybase + pix * lddy + c8, lddy / 2, 8, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (xv[i] - mu) * rs;
+      const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
+      o[i] = rs * (dd * ga[i] - m1 - xh * m2);
+    }
+    st8(dx, dx_dtype, obase + pix * lddx + c8, lddx / 2, 8, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- 7x7 im2col of the similarity maps
+// sim f32 [B*hw, ld_sim] (pixel-major, class = column)  ->  out operand [(b, n, y, x), kpad] with column t = (dy+r)*ks + (dx+r)
+__global__ void sim_im2col_kernel(const float* __restrict__ sim, int64_t ld_sim, void* __restrict__ out, int out_dtype, int64_t ldo, int B, int N,
+                                  int h, int w, int ks, int kpad) {
+  const int r = ks / 2;
+  const int groups = kpad / 8;
+  const int64_t total = (int64_t)B * N * h * w * groups;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int gi = (int)(idx % groups);
+    int64_t row = idx / groups;
+    const int x = (int)(row % w), y = (int)((row / w) % h);
+    const int n = (int)((row / ((int64_t)w * h)) % N), b = (int)(row / ((int64_t)w * h * N));
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = gi * 8 + i;
+      float v = 0.f;
+      if (t < ks * ks) {
+        const int yy = y + t / ks - r, xx = x + t % ks - r;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(sim + ((int64_t)(b * h + yy) * w + xx) * ld_sim + n);
+      }
+      f[i] = v;
+    }
+    st8(out, out_dtype, row * ldo + gi * 8, ldo / 2, 8, f);
+  }
+}
+// transpose of the above: dsim[(b,y,x), n] = sum_t dcol[(b, n, y - dy_t, x - dx_t), t]; columns >= N of dsim are zeroed
+__global__ void sim_col2im_kernel(const void* __restrict__ dcol, int dtype, int64_t ld, void* __restrict__ dsim, int ds_dtype, int64_t ld_ds,
+                                  int ncols, int B, int N, int h, int w, int ks) {
+  const int r = ks / 2;
+  const int64_t total = (int64_t)B * h * w * ncols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % ncols);
+    const int64_t pix = idx / ncols;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+    float s = 0.f;
+    if (n < N) {
+      for (int t = 0; t < ks * ks; ++t) {
+        const int yy = y - (t / ks - r), xx = x - (t % ks - r);
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+          s += load_as_f32(dcol, dtype, ((((int64_t)b * N + n) * h + yy) * w + xx) * ld + t, ld / 2);
+      }
+    }
+    store_from_f32(dsim, ds_dtype, pix * ld_ds + n, s, ld_ds / 2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- per-map spatial sums / broadcasts
+// out[map, c] = scale * sum_pix x[map, pix, c]
+__global__ void map_sum_kernel(const void* __restrict__ x, int dtype, int64_t ld, float* __restrict__ out, int hw, int C, float scale) {
+  __shared__ float red[8][129];
+  const int map = blockIdx.x;
+  const int c = threadIdx.x;           // blockDim = (C, 1024 / C ... ) handled by caller: blockDim.x = C (<=128), blockDim.y = rows
+  float s = 0.f;
+  for (int p = threadIdx.y; p < hw; p += blockDim.y) s += load_as_f32(x, dtype, ((int64_t)map * hw + p) * ld + c, ld / 2);
+  red[threadIdx.y][c] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+    for (int i = 0; i < blockDim.y; ++i) t += red[i][c];
+    out[(int64_t)map * C + c] = t * scale;
+  }
+}
+// x[map, pix, c] += scale * v[map, c]   (f32 x)
+__global__ void map_bcast_add_kernel(float* __restrict__ x, const void* __restrict__ v, int v_dtype, int64_t ldv, int64_t maps, int hw, int C,
+                                     float scale) {
+  const int64_t total = maps * hw * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t map = idx / ((int64_t)hw * C);
+    x[idx] += scale * load_as_f32(v, v_dtype, map * ldv + c, ldv / 2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- SemanticTransformer pooling
+// tok[(b, py, px), n, 0:C] = avgpool_{pool x pool} x[(b, n), :, :, 0:C];  tok[..., C:C+Ct] = text[n, :]      (vlg_head.py:41-51)
+__global__ void pool_tokens_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const float* __restrict__ text, float* __restrict__ tok,
+                                   int B, int N, int h, int w, int C, int Ct, int pool) {
+  const int hp = h / pool, wp = w / pool;
+  const int Cd = C + Ct;
+  const int64_t total = (int64_t)B * hp * wp * N * Cd;
+  const float inv = 1.f / (pool * pool);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cd);
+    int64_t t = idx / Cd;
+    const int n = (int)(t % N); t /= N;
+    const int px = (int)(t % wp), py = (int)((t / wp) % hp), b = (int)(t / ((int64_t)wp * hp));
+    float v;
+    if (c >= C) {
+      v = text[n * Ct + c - C];
+    } else {
+      float s = 0.f;
+      const int64_t base = (((int64_t)b * N + n) * h + py * pool) * w + px * pool;
+      for (int i = 0; i < pool; ++i)
+        for (int j = 0; j < pool; ++j) s += load_as_f32(x, x_dtype, (base + (int64_t)i * w + j) * ldx + c, ldx / 2);
+      v = s * inv;
+    }
+    tok[idx] = v;
+  }
+}
+
+__device__ __forceinline__ void bilin_src(int o, float scale, int in_size, int& i0, int& i1, float& w1) {
+  // align_corners=True source coordinate
+  const float s = o * scale;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + 1 < in_size ? i0 + 1 : i0;
+  w1 = s - i0;
+}
+
+// out[(b,n), y, x, c] = x[(b,n), y, x, c] + bilinear_ac(tok[(b, :, :), n, c])   (vlg_head.py:60-66)
+__global__ void unpool_add_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const float* __restrict__ tok, int64_t ldt,
+                                  void* __restrict__ out, int out_dtype, int64_t ldo, int B, int N, int h, int w, int C, int hp, int wp) {
+  const int vpp = C / 8;
+  const int64_t total = (int64_t)B * N * h * w * vpp;
+  const float sy = hp > 1 && h > 1 ? (float)(hp - 1) / (h - 1) : 0.f, sx = wp > 1 && w > 1 ? (float)(wp - 1) / (w - 1) : 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % vpp) * 8;
+    int64_t pix = idx / vpp;
+    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    const int n = (int)((pix / ((int64_t)w * h)) % N), b = (int)(pix / ((int64_t)w * h * N));
+    int y0, y1, x0, x1;
+    float wy, wx;
+    bilin_src(yy, sy, hp, y0, y1, wy);
+    bilin_src(xx, sx, wp, x0, x1, wx);
+    float f[8];
+    ld8(x, x_dtype, pix * ldx + c8, ldx / 2, 8, f);
+    const float* t00 = tok + ((((int64_t)b * hp + y0) * wp + x0) * N + n) * ldt + c8;
+    const float* t01 = tok + ((((int64_t)b * hp + y0) * wp + x1) * N + n) * ldt + c8;
+    const float* t10 = tok + ((((int64_t)b * hp + y1) * wp + x0) * N + n) * ldt + c8;
+    const float* t11 = tok + ((((int64_t)b * hp + y1) * wp + x1) * N + n) * ldt + c8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      f[i] += (1.f - wy) * ((1.f - wx) * t00[i] + wx * t01[i]) + wy * ((1.f - wx) * t10[i] + wx * t11[i]);
+    st8(out, out_dtype, pix * ldo + c8, ldo / 2, 8, f);
+  }
+}
+// dtok[(b,py,px), n, c] = sum_{y,x} W(y,py) W(x,px) dout[(b,n), y, x, c]   for c < C;  columns [C, ldt) are zeroed
+__global__ void unpool_bwd_kernel(const void* __restrict__ dout, int dtype, int64_t ld, float* __restrict__ dtok, int64_t ldt, int B, int N, int h,
+                                  int w, int C, int hp, int wp) {
+  const int64_t total = (int64_t)B * hp * wp * N * ldt;
+  const float sy = hp > 1 && h > 1 ? (float)(hp - 1) / (h - 1) : 0.f, sx = wp > 1 && w > 1 ? (float)(wp - 1) / (w - 1) : 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % ldt);
+    int64_t t = idx / ldt;
+    const int n = (int)(t % N); t /= N;
+    const int px = (int)(t % wp), py = (int)((t / wp) % hp), b = (int)(t / ((int64_t)wp * hp));
+    float s = 0.f;
+    if (c < C) {
+      // output rows whose source interval touches py
+      const int ylo = sy > 0.f ? max(0, (int)ceilf((py - 1) / sy)) : 0, yhi = sy > 0.f ? min(h - 1, (int)floorf((py + 1) / sy)) : h - 1;
+      const int xlo = sx > 0.f ? max(0, (int)ceilf((px - 1) / sx)) : 0, xhi = sx > 0.f ? min(w - 1, (int)floorf((px + 1) / sx)) : w - 1;
+      for (int yy = ylo; yy <= yhi; ++yy) {
+        int y0, y1; float wy;
+        bilin_src(yy, sy, hp, y0, y1, wy);
+        const float ay = (y0 == py ? 1.f - wy : 0.f) + (y1 == py ? wy : 0.f);
+        if (ay == 0.f) continue;
+        for (int xx = xlo; xx <= xhi; ++xx) {
+          int x0, x1; float wx;
+          bilin_src(xx, sx, wp, x0, x1, wx);
+          const float ax = (x0 == px ? 1.f - wx : 0.f) + (x1 == px ? wx : 0.f);
+          if (ax == 0.f) continue;
+          s += ay * ax * load_as_f32(dout, dtype, ((((int64_t)b * N + n) * h + yy) * w + xx) * ld + c, ld / 2);
+        }
+      }
+    }
+    dtok[idx] = s;
+  }
+}
+// dx[(b,n), y, x, c] (+)= dtok[(b, y/pool, x/pool), n, c] / pool^2  for y < hp*pool, x < wp*pool        (f32 dx)
+__global__ void pool_tokens_bwd_kernel(const float* __restrict__ dtok, int64_t ldt, float* __restrict__ dx, int B, int N, int h, int w, int C,
+                                       int pool) {
+  const int hp = h / pool, wp = w / pool;
+  const int64_t total = (int64_t)B * N * h * w * C;
+  const float inv = 1.f / (pool * pool);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    int64_t pix = idx / C;
+    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    const int n = (int)((pix / ((int64_t)w * h)) % N), b = (int)(pix / ((int64_t)w * h * N));
+    const int py = yy / pool, px = xx / pool;
+    if (py < hp && px < wp) dx[idx] += inv * dtok[((((int64_t)b * hp + py) * wp + px) * N + n) * ldt + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- skip features of `Up`
+// cat[(b,n), Y, X, c0 + c] = bilinear_ac(skip[b, :, :, c]) for every class n     (vlg_head.py:127-131: resize + repeat + cat)
+__global__ void skip_fill_kernel(const void* __restrict__ skip, int s_dtype, int64_t lds, void* __restrict__ cat, int c_dtype, int64_t ldc, int c0,
+                                 int B, int N, int h, int w, int Cs, int H2, int W2) {
+  const int64_t total = (int64_t)B * H2 * W2 * Cs;
+  const float sy = h > 1 && H2 > 1 ? (float)(h - 1) / (H2 - 1) : 0.f, sx = w > 1 && W2 > 1 ? (float)(w - 1) / (W2 - 1) : 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cs);
+    int64_t pix = idx / Cs;
+    const int X = (int)(pix % W2), Y = (int)((pix / W2) % H2), b = (int)(pix / ((int64_t)W2 * H2));
+    int y0, y1, x0, x1;
+    float wy, wx;
+    bilin_src(Y, sy, h, y0, y1, wy);
+    bilin_src(X, sx, w, x0, x1, wx);
+    auto S = [&](int yy, int xx) { return load_as_f32(skip, s_dtype, (((int64_t)b * h + yy) * w + xx) * lds + c, lds / 2); };
+    const float v = (1.f - wy) * ((1.f - wx) * S(y0, x0) + wx * S(y0, x1)) + wy * ((1.f - wx) * S(y1, x0) + wx * S(y1, x1));
+    for (int n = 0; n < N; ++n)
+      store_from_f32(cat, c_dtype, ((((int64_t)b * N + n) * H2 + Y) * W2 + X) * ldc + c0 + c, v, ldc / 2);
+  }
+}
+// dskip_pre[b, y, x, c] = relu'(skip) * sum_n sum_{Y,X} W(Y,y) W(X,x) dcat[(b,n), Y, X, c0 + c]
+__global__ void skip_grad_kernel(const void* __restrict__ dcat, int d_dtype, int64_t ldd, int c0, const void* __restrict__ skip, int s_dtype,
+                                 int64_t lds, void* __restrict__ dskip, int o_dtype, int64_t ldo, int B, int N, int h, int w, int Cs, int H2,
+                                 int W2) {
+  const int64_t total = (int64_t)B * h * w * Cs;
+  const float sy = h > 1 && H2 > 1 ? (float)(h - 1) / (H2 - 1) : 0.f, sx = w > 1 && W2 > 1 ? (float)(w - 1) / (W2 - 1) : 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cs);
+    int64_t pix = idx / Cs;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+    float s = 0.f;
+    if (load_as_f32(skip, s_dtype, pix * lds + c, lds / 2) > 0.f) {
+      const int Ylo = sy > 0.f ? max(0, (int)ceilf((y - 1) / sy)) : 0, Yhi = sy > 0.f ? min(H2 - 1, (int)floorf((y + 1) / sy)) : H2 - 1;
+      const int Xlo = sx > 0.f ? max(0, (int)ceilf((x - 1) / sx)) : 0, Xhi = sx > 0.f ? min(W2 - 1, (int)floorf((x + 1) / sx)) : W2 - 1;
+      for (int Y = Ylo; Y <= Yhi; ++Y) {
+        int y0, y1; float wy;
+        bilin_src(Y, sy, h, y0, y1, wy);
+        const float ay = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
+        if (ay == 0.f) continue;
+        for (int X = Xlo; X <= Xhi; ++X) {
+          int x0, x1; float wx;
+          bilin_src(X, sx, w, x0, x1, wx);
+          const float ax = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
+          if (ax == 0.f) continue;
+          float t = 0.f;
+          for (int n = 0; n < N; ++n) t += load_as_f32(dcat, d_dtype, ((((int64_t)b * N + n) * H2 + Y) * W2 + X) * ldd + c0 + c, ldd / 2);
+          s += ay * ax * t;
+        }
+      }
+    }
+    store_from_f32(dskip, o_dtype, pix * ldo + c, s, ldo / 2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- output conv 3x3, C -> 1
+// out[map, y, x] = bias + sum_{t, c} w[t*C + c] * x[map, y+dy_t, x+dx_t, c]            (vlg_head.py:190,239-240); one warp per pixel group
+__global__ void conv_out1_fwd_kernel(const void* __restrict__ x, int dtype, int64_t ld, const float* __restrict__ wgt, const float* __restrict__ bias,
+                                     float* __restrict__ out, int64_t maps, int h, int w, int C) {
+  extern __shared__ float s_w[];        // [9*C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
+  __syncthreads();
+  const int64_t total = maps * h * w;
+  for (int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    float s = bias[0];
+    for (int t = 0; t < 9; ++t) {
+      const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+      if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
+      const int64_t base = (pix + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * ld;
+      for (int c = 0; c < C; c += 8) {
+        float f[8];
+        ld8(x, dtype, base + c, ld / 2, 8, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += f[i] * s_w[t * C + c + i];
+      }
+    }
+    out[pix] = s;
+  }
+}
+// dx[map, y, x, c] = sum_t w[t*C + c] * dout[map, y-dy_t, x-dx_t]
+__global__ void conv_out1_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ wgt, void* __restrict__ dx, int dtype, int64_t ld,
+                                       int64_t maps, int h, int w, int C) {
+  extern __shared__ float s_w[];
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
+  __syncthreads();
+  const int vpp = C / 8;
+  const int64_t total = maps * h * w * vpp;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % vpp) * 8;
+    const int64_t pix = idx / vpp;
+    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      const int y2 = yy - (t / 3 - 1), x2 = xx - (t % 3 - 1);
+      if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
+      const float d = dout[pix - (int64_t)(t / 3 - 1) * w - (t % 3 - 1)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += d * s_w[t * C + c8 + i];
+    }
+    st8(dx, dtype, pix * ld + c8, ld / 2, 8, f);
+  }
+}
+// dw[t*C + c] += sum_pix dout[pix] * x[pix + tap_t, c];  dbias += sum dout
+__global__ void conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ x, int dtype, int64_t ld, float* __restrict__ dw,
+                                       float* __restrict__ dbias, int64_t maps, int h, int w, int C) {
+  // blockDim.x = 9*C threads (<= 288 for C = 32): thread = (t, c); pixels strided over the grid
+  const int t = threadIdx.x / C, c = threadIdx.x % C;
+  const int64_t total = maps * h * w;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per, p1 = p0 + per < total ? p0 + per : total;
+  float s = 0.f, sb = 0.f;
+  for (int64_t pix = p0; pix < p1; ++pix) {
+    const float d = dout[pix];
+    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+    if (threadIdx.x == 0) sb += d;
+    if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
+    s += d * load_as_f32(x, dtype, (pix + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * ld + c, ld / 2);
+  }
+  atomicAdd(dw + threadIdx.x, s);
+  if (threadIdx.x == 0) atomicAdd(dbias, sb);
+}
+
+}  // namespace
+}  // namespace svl
+
+using namespace svl;
+#define ST (cudaStream_t) stream
+
+extern "C" int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
+                               int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, int64_t maps, int hw, int C,
+                               int G, float eps, void* stream) {
+  SVL_CHECK_ARG(x && gamma && beta && out, "svl_gn_relu_fwd: null pointer");
+  SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
+                "svl_gn_relu_fwd: unsupported C=%d G=%d", C, G);
+  if (maps == 0) return SVL_OK;
+  gn_relu_fwd_kernel<<<(unsigned)maps, kGnThreads, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean, rstd, hw,
+                                                            C, G, eps);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const float* gamma,
+                               const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int64_t lddx, float* dgamma,
+                               float* dbeta, int64_t maps, int hw, int C, int G, void* stream) {
+  SVL_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx, "svl_gn_relu_bwd: null pointer");
+  SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
+                "svl_gn_relu_bwd: unsupported C=%d G=%d", C, G);
+  if (maps == 0) return SVL_OK;
+  gn_relu_bwd_kernel<<<(unsigned)maps, kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, dx, dx_dtype, lddx, dgamma,
+                                                            dbeta, hw, C, G);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_sim_im2col(const float* sim, int64_t ld_sim, void* out, int out_dtype, int64_t ldo, int B, int N, int h, int w, int ks, int kpad,
+                              void* stream) {
+  SVL_CHECK_ARG(sim && out && kpad % 8 == 0 && kpad >= ks * ks, "svl_sim_im2col: bad arguments");
+  sim_im2col_kernel<<<ew_grid((int64_t)B * N * h * w * (kpad / 8)), 256, 0, ST>>>(sim, ld_sim, out, out_dtype, ldo, B, N, h, w, ks, kpad);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_sim_col2im(const void* dcol, int dtype, int64_t ld, void* dsim, int ds_dtype, int64_t ld_ds, int ncols, int B, int N, int h,
+                              int w, int ks, void* stream) {
+  SVL_CHECK_ARG(dcol && dsim && ncols >= N, "svl_sim_col2im: bad arguments");
+  sim_col2im_kernel<<<ew_grid((int64_t)B * h * w * ncols), 256, 0, ST>>>(dcol, dtype, ld, dsim, ds_dtype, ld_ds, ncols, B, N, h, w, ks);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_map_sum(const void* x, int dtype, int64_t ld, float* out, int64_t maps, int hw, int C, float scale, void* stream) {
+  SVL_CHECK_ARG(x && out && C <= 128, "svl_map_sum: bad arguments");
+  if (maps == 0) return SVL_OK;
+  int ry = 1024 / C;
+  if (ry > 8) ry = 8;
+  map_sum_kernel<<<(unsigned)maps, dim3(C, ry), 0, ST>>>(x, dtype, ld, out, hw, C, scale);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_map_bcast_add(float* x, const void* v, int v_dtype, int64_t ldv, int64_t maps, int hw, int C, float scale, void* stream) {
+  SVL_CHECK_ARG(x && v, "svl_map_bcast_add: null pointer");
+  map_bcast_add_kernel<<<ew_grid(maps * hw * C), 256, 0, ST>>>(x, v, v_dtype, ldv, maps, hw, C, scale);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_pool_tokens(const void* x, int x_dtype, int64_t ldx, const float* text, float* tok, int B, int N, int h, int w, int C, int Ct,
+                               int pool, void* stream) {
+  SVL_CHECK_ARG(x && text && tok && pool > 0 && h >= pool && w >= pool, "svl_pool_tokens: bad arguments");
+  pool_tokens_kernel<<<ew_grid((int64_t)B * (h / pool) * (w / pool) * N * (C + Ct)), 256, 0, ST>>>(x, x_dtype, ldx, text, tok, B, N, h, w, C, Ct, pool);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_pool_tokens_bwd(const float* dtok, int64_t ldt, float* dx, int B, int N, int h, int w, int C, int pool, void* stream) {
+  SVL_CHECK_ARG(dtok && dx, "svl_pool_tokens_bwd: null pointer");
+  pool_tokens_bwd_kernel<<<ew_grid((int64_t)B * N * h * w * C), 256, 0, ST>>>(dtok, ldt, dx, B, N, h, w, C, pool);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_unpool_add(const void* x, int x_dtype, int64_t ldx, const float* tok, int64_t ldt, void* out, int out_dtype, int64_t ldo, int B,
+                              int N, int h, int w, int C, int hp, int wp, void* stream) {
+  SVL_CHECK_ARG(x && tok && out && C % 8 == 0, "svl_unpool_add: bad arguments");
+  unpool_add_kernel<<<ew_grid((int64_t)B * N * h * w * (C / 8)), 256, 0, ST>>>(x, x_dtype, ldx, tok, ldt, out, out_dtype, ldo, B, N, h, w, C, hp, wp);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_unpool_bwd(const void* dout, int dtype, int64_t ld, float* dtok, int64_t ldt, int B, int N, int h, int w, int C, int hp, int wp,
+                              void* stream) {
+  SVL_CHECK_ARG(dout && dtok, "svl_unpool_bwd: null pointer");
+  unpool_bwd_kernel<<<ew_grid((int64_t)B * hp * wp * N * ldt), 256, 0, ST>>>(dout, dtype, ld, dtok, ldt, B, N, h, w, C, hp, wp);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_skip_fill(const void* skip, int s_dtype, int64_t lds, void* cat, int c_dtype, int64_t ldc, int c0, int B, int N, int h, int w,
+                             int Cs, int H2, int W2, void* stream) {
+  SVL_CHECK_ARG(skip && cat, "svl_skip_fill: null pointer");
+  skip_fill_kernel<<<ew_grid((int64_t)B * H2 * W2 * Cs), 256, 0, ST>>>(skip, s_dtype, lds, cat, c_dtype, ldc, c0, B, N, h, w, Cs, H2, W2);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_skip_grad(const void* dcat, int d_dtype, int64_t ldd, int c0, const void* skip, int s_dtype, int64_t lds, void* dskip,
+                             int o_dtype, int64_t ldo, int B, int N, int h, int w, int Cs, int H2, int W2, void* stream) {
+  SVL_CHECK_ARG(dcat && skip && dskip, "svl_skip_grad: null pointer");
+  skip_grad_kernel<<<ew_grid((int64_t)B * h * w * Cs, 128), 128, 0, ST>>>(dcat, d_dtype, ldd, c0, skip, s_dtype, lds, dskip, o_dtype, ldo, B, N, h, w,
+                                                                         Cs, H2, W2);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_conv_out1_fwd(const void* x, int dtype, int64_t ld, const float* wgt, const float* bias, float* out, int64_t maps, int h, int w,
+                                 int C, void* stream) {
+  SVL_CHECK_ARG(x && wgt && bias && out && C % 8 == 0, "svl_conv_out1_fwd: bad arguments");
+  conv_out1_fwd_kernel<<<ew_grid(maps * h * w), 256, 9 * C * sizeof(float), ST>>>(x, dtype, ld, wgt, bias, out, maps, h, w, C);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_conv_out1_bwd(const float* dout, const void* x, int x_dtype, int64_t ldx, const float* wgt, void* dx, int dx_dtype, int64_t lddx,
+                                 float* dw, float* dbias, int64_t maps, int h, int w, int C, void* stream) {
+  SVL_CHECK_ARG(dout && x && wgt && dx && dw && dbias && C % 8 == 0 && 9 * C <= 1024, "svl_conv_out1_bwd: bad arguments");
+  conv_out1_dgrad_kernel<<<ew_grid(maps * h * w * (C / 8)), 256, 9 * C * sizeof(float), ST>>>(dout, wgt, dx, dx_dtype, lddx, maps, h, w, C);
+  SVL_LAUNCH_CHECK();
+  int64_t total = maps * h * w;
+  int grid = (int)(total / 2048 > 0 ? (total / 2048 < 148 * 8 ? total / 2048 : 148 * 8) : 1);
+  conv_out1_wgrad_kernel<<<grid, 9 * C, 0, ST>>>(dout, x, x_dtype, ldx, dw, dbias, maps, h, w, C);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}

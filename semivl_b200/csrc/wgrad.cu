@@ -247,8 +247,9 @@ extern "C" int svl_wgrad(const svl_wgrad_desc* d, void* stream) {
     uint64_t dims[4] = {(uint64_t)dy_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
     uint64_t st[3] = {(uint64_t)d->ld_dy * 2, (uint64_t)d->ld_dy * 2 * d->w, (uint64_t)d->ld_dy * 2 * d->w * d->h};
     if (int rc = tma_encode_bf16(&tmDY, d->dy, 4, dims, st, box)) return rc;
-    uint64_t dimsx[4] = {(uint64_t)x_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
-    uint64_t stx[3] = {(uint64_t)d->ld_x * 2, (uint64_t)d->ld_x * 2 * d->w, (uint64_t)d->ld_x * 2 * d->w * d->h};
+    const uint64_t xw = d->x_map_w > 0 ? d->x_map_w : d->w;
+    uint64_t dimsx[4] = {(uint64_t)x_cols, xw, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t stx[3] = {(uint64_t)d->ld_x * 2, (uint64_t)d->ld_x * 2 * xw, (uint64_t)d->ld_x * 2 * xw * d->h};
     if (int rc = tma_encode_bf16(&tmX, d->x, 4, dimsx, stx, box)) return rc;
   } else {
     p.num_kblocks = (d->rows + KB - 1) / KB;

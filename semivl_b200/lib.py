@@ -33,7 +33,7 @@ _TapArr = C.c_int * MAX_TAPS
 class GemmDesc(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_conv", C.c_int), ("m", C.c_int64), ("lda", C.c_int64), ("a_cols", C.c_int64),
-        ("nb", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("nb", C.c_int), ("h", C.c_int), ("w", C.c_int), ("a_map_w", C.c_int),
         ("b", C.c_void_p), ("b_rows", C.c_int64), ("ldb", C.c_int64),
         ("n", C.c_int), ("k_per_tap", C.c_int), ("num_taps", C.c_int),
         ("tap_dy", _TapArr), ("tap_dx", _TapArr), ("tap_a_koff", _TapArr), ("tap_b_row", _TapArr), ("tap_b_col", _TapArr),
@@ -52,7 +52,7 @@ class WgradDesc(C.Structure):
         ("x", C.c_void_p), ("ld_x", C.c_int64), ("x_cols", C.c_int64),
         ("conv", C.c_int), ("rows", C.c_int64), ("nb", C.c_int), ("h", C.c_int), ("w", C.c_int),
         ("m", C.c_int), ("n", C.c_int), ("num_taps", C.c_int),
-        ("tap_dy", _TapArr), ("tap_dx", _TapArr), ("tap_dy_koff", _TapArr), ("tap_x_koff", _TapArr), ("tap_slot", _TapArr),
+        ("tap_dy", _TapArr), ("tap_dx", _TapArr), ("tap_dy_koff", _TapArr), ("tap_x_koff", _TapArr), ("tap_slot", _TapArr), ("x_map_w", C.c_int),
         ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("slot_stride", C.c_int64),
         ("alpha", C.c_float), ("splits", C.c_int),
     ]
@@ -79,6 +79,29 @@ _PROTOS = {
     "svl_colsum": [_P, _I, _L, _L, _I, _P, _P],
     "svl_batch_sum": [_P, _P, _I, _L, _I, _P],
     "svl_axpy": [_P, _P, _F, _L, _P],
+    "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _L, _I, _I, _I, _F, _P],
+    "svl_gn_relu_bwd": [_P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _P, _L, _I, _I, _I, _P],
+    "svl_sim_im2col": [_P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
+    "svl_sim_col2im": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
+    "svl_map_sum": [_P, _I, _L, _P, _L, _I, _I, _F, _P],
+    "svl_map_bcast_add": [_P, _P, _I, _L, _L, _I, _I, _F, _P],
+    "svl_pool_tokens": [_P, _I, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_pool_tokens_bwd": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P],
+    "svl_unpool_add": [_P, _I, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_unpool_bwd": [_P, _I, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_skip_fill": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_skip_grad": [_P, _I, _L, _I, _P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_conv_out1_fwd": [_P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P],
+    "svl_conv_out1_bwd": [_P, _P, _I, _L, _P, _P, _I, _L, _P, _P, _L, _I, _I, _I, _P],
+    "svl_upsample_bilinear": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "svl_upsample_bilinear_bwd": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "svl_softmax_max": [_P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _F, _P],
+    "svl_upsample_ce": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P],
+    "svl_count_valid": [_P, _L, _I, _P, _P],
+    "svl_reciprocal": [_P, _P, _F, _F, _P],
+    "svl_cutmix_weights": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _P],
+    "svl_cutmix_img": [_P, _P, _P, _P, _I, _I, _L, _P],
+    "svl_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "svl_attention_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P],
     "svl_attention_bwd": [_P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _I, _I, _I, _F, _P],
 }

@@ -33,7 +33,7 @@ def _set_taps(d, taps):
 def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0, a_koff=0, out_dtype=None, ldc=None,
          bias=None, act=L.ACT_NONE, alpha=1.0, residual=None, preact_out=None, dact_src=None, dact_kind=L.ACT_NONE,
          dact_split=False, row_bias=None, row_bias_div=1, accumulate=False, out_mode=L.OUT_LINEAR, out_hw=None,
-         block_n=0, m=None, lda=None, a_cols=None, b_col0=0):
+         block_n=0, m=None, lda=None, a_cols=None, b_col0=0, a_map_w=0, taps=None, a_lo=None):
     """out = epilogue(sum_taps A_t @ B_t^T).
 
     a     : bf16 tensor; 2-D [M, lda] or (conv=(nb,h,w)) NHWC [nb,h,w,lda]; split (hi|lo) when precise
@@ -48,6 +48,7 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
     if conv is not None:
         d.a_conv = 1
         d.nb, d.h, d.w = conv
+        d.a_map_w = a_map_w
         d.m = conv[0] * conv[1] * conv[2]
     else:
         d.a_conv = 0
@@ -56,16 +57,17 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
     d.b_rows = b.shape[0]
     d.ldb = b.shape[1]
     d.n, d.k_per_tap = n, k
-    kl_a = d.lda // 2 if precise else 0      # lo offset of A
+    kl_a = (a_lo if a_lo is not None else d.lda // 2) if precise else 0      # lo offset of A
     kl_b = d.ldb // 2 if precise else 0
-    taps = []
-    for t, (dy, dx) in enumerate(filt if filt is not None else [(0, 0)]):
-        br = t * b_row_stride
-        taps.append((dy, dx, a_koff, br, b_col0))
+    if taps is None:
+        taps = [(dy, dx, a_koff, t * b_row_stride, b_col0) for t, (dy, dx) in enumerate(filt if filt is not None else [(0, 0)])]
+    full = []
+    for (dy, dx, ak, br, bc) in taps:          # logical taps: (pixel dy, dx, A column offset, B row offset, B column offset)
+        full.append((dy, dx, ak, br, bc))
         if precise:
-            taps.append((dy, dx, a_koff, br, b_col0 + kl_b))
-            taps.append((dy, dx, a_koff + kl_a, br, b_col0))
-    _set_taps(d, taps)
+            full.append((dy, dx, ak, br, bc + kl_b))
+            full.append((dy, dx, ak + kl_a, br, bc))
+    _set_taps(d, full)
     d.out = out.data_ptr()
     d.out_dtype = out_dtype if out_dtype is not None else L.dtype_of(out)
     d.ldc = ldc if ldc is not None else out.shape[-1]
@@ -90,7 +92,7 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
 
 
 def wgrad(dy, x, dw, *, m, n, precise=False, conv=None, filt=None, dy_koff=0, x_koff=0, ld_dw=None, slot_stride=None,
-          alpha=1.0, splits=0, rows=None, ld_dy=None, ld_x=None):
+          alpha=1.0, splits=0, rows=None, ld_dy=None, ld_x=None, x_map_w=0, x_lo=None, dy_lo=None, taps=None):
     """dw[slot, i, j] += alpha * sum_rows dy[row, dy_koff + i] * x[row shifted by filt[slot], x_koff + j]   (fp32 dw, atomically reduced).
 
     dy, x: bf16 [rows, ld] (or NHWC with conv=(nb,h,w)); split (hi|lo) when precise.  One output slot per filter position.
@@ -106,14 +108,18 @@ def wgrad(dy, x, dw, *, m, n, precise=False, conv=None, filt=None, dy_koff=0, x_
     else:
         d.rows = rows if rows is not None else dy.numel() // dy.shape[-1]
     d.m, d.n = m, n
-    lo_dy = d.ld_dy // 2 if precise else 0
-    lo_x = d.ld_x // 2 if precise else 0
-    taps = []
-    for s, (fy, fx) in enumerate(filt if filt is not None else [(0, 0)]):
-        taps.append((fy, fx, dy_koff, x_koff, s))
+    d.x_map_w = x_map_w
+    lo_dy = (dy_lo if dy_lo is not None else d.ld_dy // 2) if precise else 0
+    lo_x = (x_lo if x_lo is not None else d.ld_x // 2) if precise else 0
+    if taps is None:        # logical taps: (pixel dy, dx, dy column offset, x column offset, slot)
+        taps = [(fy, fx, dy_koff, x_koff, s) for s, (fy, fx) in enumerate(filt if filt is not None else [(0, 0)])]
+    full = []
+    for (fy, fx, ka, kx, s) in taps:
+        full.append((fy, fx, ka, kx, s))
         if precise:
-            taps.append((fy, fx, dy_koff, x_koff + lo_x, s))
-            taps.append((fy, fx, dy_koff + lo_dy, x_koff, s))
+            full.append((fy, fx, ka, kx + lo_x, s))
+            full.append((fy, fx, ka + lo_dy, kx, s))
+    taps = full
     assert len(taps) <= L.MAX_TAPS
     d.num_taps = len(taps)
     for i, (fy, fx, ka, kx, s) in enumerate(taps):
@@ -239,3 +245,23 @@ def attention_bwd(qkv, out, dout, lse, b, seq, heads, precise, dv_add=None, dv_a
     L.call("svl_attention_bwd", qkv, out, dout, 1 if precise else 0, lse, delta, dv_add, dv_add_dtype,
            dv_add.shape[-1] if dv_add is not None else 0, dqkv, b, seq, heads, 0.125, n_launch=3)
     return dqkv
+
+
+# ---------------------------------------------------------------------------------------------- head kernels
+def gn_relu_fwd(x, x_dtype, gamma, beta, out, out_dtype, maps, hw, C, G, *, ldx=None, ldo=None, out_col0=0, res=None, res_dtype=L.BF16,
+                ldres=None, save_stats=True, eps=1e-5):
+    dev = x.device
+    mean = torch.empty(maps, G, device=dev, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(maps, G, device=dev, dtype=torch.float32) if save_stats else None
+    L.call("svl_gn_relu_fwd", x, x_dtype, ldx if ldx is not None else x.shape[-1], gamma, beta,
+           out.data_ptr() + out_col0 * out.element_size(), out_dtype, ldo if ldo is not None else out.shape[-1],
+           res, res_dtype, (ldres if ldres is not None else (res.shape[-1] if res is not None else 0)), mean, rstd, maps, hw, C, G, eps)
+    return mean, rstd
+
+
+def gn_relu_bwd(dy, dy_dtype, x, x_dtype, gamma, beta, mean, rstd, dx, dx_dtype, dgamma, dbeta, maps, hw, C, G, *, lddy=None, dy_col0=0,
+                ldx=None, lddx=None):
+    L.call("svl_gn_relu_bwd", dy.data_ptr() + dy_col0 * dy.element_size(), dy_dtype, lddy if lddy is not None else dy.shape[-1],
+           x, x_dtype, ldx if ldx is not None else x.shape[-1], gamma, beta, mean, rstd, dx, dx_dtype,
+           lddx if lddx is not None else dx.shape[-1], dgamma, dbeta, maps, hw, C, G)
+    return dx

@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the SemiVL training hot path on B200 (BASELINE.json metric: training images/sec, 512x512, ViT-B/16).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU PyTorch path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): VOC 21-class synthetic, 512x512, ViT-B/16 + VLG head, per-GPU batch 16, one supervised
+training step = encoder fwd -> head fwd -> fused upsample+CE -> head bwd -> encoder bwd -> (NCCL grad all-reduce) -> AdamW.
+`--workload semivl` times the full SemiVL consistency step (teacher + MaskCLIP + 5-way student head) instead.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CROP, NCLASS, BATCH = 512, 21, 16
+# algorithmic GFLOP per image of the supervised step at 512^2 / N=21 (FlopCounterMode on the reference: matmul+conv, 2*MAC)
+GF_PER_IMG_SUPERVISED = 831.5
+GF_PER_UNIT_SEMIVL = 4542.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="supervised", choices=["supervised", "semivl"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--crop", type=int, default=CROP)
+    ap.add_argument("--nclass", type=int, default=NCLASS)
+    ap.add_argument("--precise", action="store_true", help="split-bf16 parity mode instead of the bf16 throughput mode")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-crop", type=int, default=CROP)
+    return ap.parse_args()
+
+
+def model_cfg(crop, nclass, precise):
+    return dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=nclass, crop_size=crop, dataset='pascal' if nclass == 21 else 'ade',
+                text_embedding_variant='single', mcc_text='single', pl_text='single', clip_encoder='mcvit16', disable_dropout=True,
+                fp_rate=0.5, model_args=dict(pretrained=None), clip_encoder_args=dict(pretrained=None), precise=precise)
+
+
+def synth_batch(torch, b, crop, nclass, seed, device, semivl):
+    """Synthetic inputs of SURVEY.md §8d: randn images, labels with a 5% ignore region, pad-strip ignore masks, CutMix boxes."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda: torch.randn(b, 3, crop, crop, generator=g)
+    mask = torch.randint(0, nclass, (b, crop, crop), generator=g)
+    mask[:, : crop // 5, : crop // 4] = 255
+    out = dict(img_x=r(), mask_x=mask)
+    if semivl:
+        for k in ("img_w", "img_s1", "img_s2", "img_w_other", "img_s1_other", "img_s2_other"):
+            out[k] = r()
+        ign = torch.zeros(b, crop, crop, dtype=torch.long)
+        ign[:, -crop // 10:, :] = 255
+        ign_o = torch.zeros(b, crop, crop, dtype=torch.long)
+        ign_o[:, :, -crop // 12:] = 255
+        def box(frac):
+            m = torch.zeros(b, crop, crop)
+            h = int(crop * frac)
+            m[::2, crop // 5: crop // 5 + h, crop // 4: crop // 4 + h] = 1
+            return m
+        out.update(ignore_mask=ign, ignore_mask_other=ign_o, mix1=box(0.5), mix2=box(0.3))
+    return {k: (v.pin_memory() if device != "cpu" else v) for k, v in out.items()}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None), "reasons": reasons}
+
+
+def cpu_reference_rate(args, steps, warmup, crop, b=1):
+    """The reference's CPU PyTorch path (oracle port, fp32) on the host cores: supervised step fwd + CE + bwd at batch b."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from oracle import semivl_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mc = O.ModelCfg(img_size=crop, num_classes=args.nclass)
+    sd = O.fixture_state_dict(O.param_shapes(mc, with_clip_encoder=False), seed=0)
+    p = {k: v.clone().requires_grad_(("attn" in k or "pos_embed" in k) if k.startswith("backbone.") else True) for k, v in sd.items()}
+    tname = "voc12_wbg_single" if args.nclass == 21 else "ade_single"
+    text = torch.from_numpy(np.load(os.path.join(ROOT, "semivl_b200", "configs", "_base_", "datasets", "text_embedding", tname + ".npy")))
+    batch = synth_batch(torch, b, crop, args.nclass, 1234, "cpu", False)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = O.supervised_step_loss(batch["img_x"], batch["mask_x"], p, text, mc)
+        loss.backward()
+        for v in p.values():
+            v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return b / (ms / 1e3), ms, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    value, ms, cores = cpu_reference_rate(args, steps, warmup, args.cpu_crop)
+    sample = f"supervised step fwd+CE+bwd at batch 1, {args.cpu_crop}x{args.cpu_crop}, N={args.nclass}, {steps} timed steps after {warmup} warm-up"
+    line = {"impl": "reference", "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"VOC {args.nclass}-class synthetic {args.cpu_crop}x{args.cpu_crop} ViT-B/16+VLG head supervised step",
+                                            "batch_per_step": 1, "note": "reference CPU path = oracle port of the reference (pure PyTorch fp32)"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    from semivl_b200 import lib as L
+    from semivl_b200 import ops
+    from semivl_b200.model import build_model
+    from semivl_b200.train import OptimCfg, Trainer
+    L.check_device()
+    semivl = args.workload == "semivl"
+    torch.manual_seed(0)
+    model = build_model(model_cfg(args.crop, args.nclass, args.precise)).to(dev)
+    tr = Trainer(model, OptimCfg(lr=1e-4, total_iters=100000))
+    b = args.batch
+    host = synth_batch(torch, b, args.crop, args.nclass, 1234 + rank, "cuda", semivl)
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def step(batch):
+        if semivl:
+            return tr.semivl_step(batch)[0]
+        return tr.supervised_step(batch["img_x"], batch["mask_x"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- device-timed region: inputs resident in HBM
+    l0 = L.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(resident)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (L.launches - l0) // args.steps
+    # ---- end-to-end region: host (pinned) buffers, H2D inside, loss read back every step
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        for k, v in host.items():
+            stage[k].copy_(v, non_blocking=True)
+        lv = float(step(stage).item())
+    f1.record()
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3) / args.steps
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    # ---- instrumented step: CUDA events around every tensor-core contraction launch (roofline of the dominant kernel)
+    ops.PROFILE = []
+    step(resident)
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(bv) for a, bv, _ in ops.PROFILE)
+    gemm_flops = sum(f for _, _, f in ops.PROFILE)
+    n_gemm = len(ops.PROFILE)
+    ops.PROFILE = None
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    unit_gf = GF_PER_UNIT_SEMIVL if semivl else GF_PER_IMG_SUPERVISED
+    step_tf = unit_gf * b / 1e3
+    value = world * b / (ms / 1e3)
+    line = {
+        "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3" if args.precise else "bf16",
+        "data": "synthetic",
+        "config": {"workload": (f"VOC {args.nclass}-class synthetic {args.crop}x{args.crop} ViT-B/16+VLG head, "
+                                + ("full SemiVL consistency step" if semivl else "supervised step fwd+bwd+AdamW")),
+                   "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
+                   "weights": "random init (reference init_weights)", "loss": float(loss.item())},
+        "e2e": {"value": world * b / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e, "last_loss": lv},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary() if sampler else None,
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel/wgrad_kernel (tcgen05 contraction engine)", "achieved": achieved_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "launches": n_gemm,
+                     "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / ms if ms else None,
+                     "measured_on": "one instrumented step after the timed region (CUDA events around every contraction launch)",
+                     "whole_step_algorithmic_tflops": step_tf / (ms / 1e3), "whole_step_frac": step_tf / (ms / 1e3) / peak_tf},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, cms, cores = cpu_reference_rate(args, 2, 1, args.cpu_crop)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle port of the reference (CPU PyTorch fp32), supervised step fwd+CE+bwd at batch 1, "
+                                              f"{args.cpu_crop}x{args.cpu_crop}, N={args.nclass}: 2 timed steps after 1 warm-up ({cms:.0f} ms/step)"}
+        except Exception as e:      # the baseline must never sink the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -218,6 +218,9 @@ int svl_upsample_bilinear_bwd(const float* dout, float* dlow, int64_t planes, in
  * (semivl.py:231-232,251-252; model/vlm.py:103-109 with scale 100) -- the full-resolution logits are never materialised */
 int svl_softmax_max(const float* low, float* conf, int64_t* label, int64_t R, int N, int hl, int wl, int H, int W, float scale,
                     float thresh, void* stream);
+/* pixel-major scores [R*hw, ld] -> class-major maps [R, N, hw] with a max over concept columns [offsets[n], offsets[n+1])
+ * (device int offsets[N+1]; aggregate_concept_predictions, model/text_embeddings.py:188-193; identity offsets = transpose) */
+int svl_group_max(const float* in, int64_t ld, const int* offsets, float* out, int64_t R, int N, int hw, void* stream);
 /* Fused upsample + per-pixel cross-entropy forward AND backward for up to 3 target sets on the same logits:
  *   loss[t] += coef[t] * sum_pix weight_t[pix] * CE(logits[pix], label_t[pix])      (label == ignore_index contributes 0)
  *   dlow    += gscale * d(sum_t loss[t]) / d low                                     (skipped when dlow == NULL)

@@ -100,6 +100,21 @@ __global__ void softmax_max_kernel(const float* __restrict__ low, float* __restr
   }
 }
 
+// pixel-major scores [R*hw, ld] (column = concept) -> class-major maps [R, N, hw]: out[r, n, p] = max_{k in [off[n], off[n+1])} in[r*hw + p, k]
+// (aggregate_concept_predictions, model/text_embeddings.py:188-193; identity grouping is a plain transpose)
+__global__ void group_max_kernel(const float* __restrict__ in, int64_t ld, const int* __restrict__ off, float* __restrict__ out, int64_t R, int N,
+                                 int hw) {
+  const int64_t total = R * N * hw;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % hw), n = (int)((idx / hw) % N);
+    const int64_t r = idx / ((int64_t)hw * N);
+    const float* row = in + (r * hw + p) * ld;
+    float m = -INFINITY;
+    for (int k = off[n]; k < off[n + 1]; ++k) m = fmaxf(m, row[k]);
+    out[idx] = m;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- fused upsample + CE fwd/bwd
 // For every full-resolution pixel: z = up(low)[:, Y, X];  for each target set t:  ce_t = logsumexp(z) - z[label_t] (0 when label_t == ignore);
 //   loss[t] += coef[t] * w_t(pix) * ce_t ;   dlow += up^T( sum_t gscale * coef[t] * w_t * (softmax(z) - onehot(label_t)) )
@@ -307,6 +322,13 @@ extern "C" int svl_softmax_max(const float* low, float* conf, int64_t* label, in
                                float thresh, void* stream) {
   SVL_CHECK_ARG(low && (conf || label), "svl_softmax_max: null pointer");
   softmax_max_kernel<<<ew_grid(R * H * W), 256, 0, ST>>>(low, conf, label, R, N, hl, wl, H, W, scale == 0.f ? 1.f : scale, thresh);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_group_max(const float* in, int64_t ld, const int* offsets, float* out, int64_t R, int N, int hw, void* stream) {
+  SVL_CHECK_ARG(in && offsets && out, "svl_group_max: null pointer");
+  group_max_kernel<<<ew_grid(R * N * hw), 256, 0, ST>>>(in, ld, offsets, out, R, N, hw);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

@@ -20,15 +20,21 @@ class WeightCache:
 
     def __init__(self):
         self._c = {}
+        self.gen = 0                 # bumped by whoever updates parameters behind torch's back (the fused AdamW kernel)
+        self.volatile = None         # optional set of parameter names that change every step
 
     def get(self, key, param, fn):
-        ver = (param.data_ptr(), param._version)
+        vol = self.volatile is not None and key[0] in self.volatile
+        ver = (param.data_ptr(), param._version, self.gen if vol else 0)
         hit = self._c.get(key)
         if hit is None or hit[0] != ver:
             with torch.no_grad():
                 hit = (ver, fn(param.detach()))
             self._c[key] = hit
         return hit[1]
+
+    def bump(self):
+        self.gen += 1
 
     def clear(self):
         self._c.clear()

@@ -96,6 +96,7 @@ _PROTOS = {
     "svl_upsample_bilinear": [_P, _P, _L, _I, _I, _I, _I, _P],
     "svl_upsample_bilinear_bwd": [_P, _P, _L, _I, _I, _I, _I, _P],
     "svl_softmax_max": [_P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _F, _P],
+    "svl_group_max": [_P, _L, _P, _P, _L, _I, _I, _P],
     "svl_upsample_ce": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P],
     "svl_count_valid": [_P, _L, _I, _P, _P],
     "svl_reciprocal": [_P, _P, _F, _F, _P],

@@ -10,6 +10,20 @@ import torch
 from . import lib as L
 
 
+PROFILE = None      # set to a list to record (start_event, end_event, flops) around every contraction launch (bench.py roofline)
+
+
+def _profiled(fn, flops):
+    if PROFILE is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((e0, e1, flops))
+
+
 def split_bf16(x):
     """fp32 [..., C] -> bf16 [..., 2C] = (hi | lo) with hi + lo ~= x to 2^-17."""
     hi = x.to(torch.bfloat16)
@@ -87,7 +101,7 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
         d.residual, d.res_dtype, d.ldres = residual.data_ptr(), L.dtype_of(residual), residual.shape[-1]
     d.accumulate = 1 if accumulate else 0
     d.block_n = block_n
-    L.raw_gemm(d)
+    _profiled(lambda: L.raw_gemm(d), 2.0 * d.m * n * k * len(taps))
     return out
 
 
@@ -129,7 +143,8 @@ def wgrad(dy, x, dw, *, m, n, precise=False, conv=None, filt=None, dy_koff=0, x_
     d.slot_stride = slot_stride if slot_stride is not None else (dw.shape[-2] * dw.shape[-1] if dw.dim() >= 2 else 0)
     d.alpha = alpha
     d.splits = splits
-    L.raw_wgrad(d)
+    nlog = len(taps) // (3 if precise else 1)
+    _profiled(lambda: L.raw_wgrad(d), 2.0 * d.rows * m * n * nlog)
     return dw
 
 

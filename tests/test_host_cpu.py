@@ -1,0 +1,114 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/semivl_b200.h declares, the ctypes descriptors
+match the C structs, the mmseg-style registry / Config / build_model mirror builds the reference's parameter inventory, and
+the data-parallel gradient exchange is exact under gloo with world_size 2.  (No compute kernels are called without a GPU.)"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    return ge.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "semivl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(svl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 40
+    lib = ctypes.CDLL(built)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    from semivl_b200 import lib as L
+    assert L.version() == 100
+    bound = set(L._PROTOS) | {"svl_gemm", "svl_wgrad", "svl_last_error", "svl_version", "svl_check_device"}
+    assert names == bound, (names - bound, bound - names)
+
+
+def test_descriptor_layout_matches_c(built, tmp_path):
+    """sizeof / offsetof of the two descriptor structs as seen by a C compiler == the ctypes mirror."""
+    from semivl_b200 import lib as L
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "semivl_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(svl_gemm_desc), offsetof(svl_gemm_desc, out), offsetof(svl_gemm_desc, block_n),'
+                   'sizeof(svl_wgrad_desc), offsetof(svl_wgrad_desc, dw), offsetof(svl_wgrad_desc, splits));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(L.GemmDesc), L.GemmDesc.out.offset, L.GemmDesc.block_n.offset,
+            ctypes.sizeof(L.WgradDesc), L.WgradDesc.dw.offset, L.WgradDesc.splits.offset]
+    assert got == want
+
+
+def test_no_gpu_calls_fail_loudly(built):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from semivl_b200 import lib as L
+    with pytest.raises(L.SvlError):
+        L.check_device()
+
+
+def test_registry_and_build_model_mirror_reference_inventory(built):
+    from oracle import semivl_oracle as O
+    from semivl_b200.model import build_model
+    from semivl_b200.registry import BACKBONES, HEADS, SEGMENTORS, Config
+    assert "MaskClipVisionTransformer" in BACKBONES and "VLGHead" in HEADS and "VLM" in SEGMENTORS
+    cfg = dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=21, crop_size=224, dataset='pascal', text_embedding_variant='single',
+               mcc_text='concept4_single', pl_text='single', clip_encoder='mcvit16', disable_dropout=True, fp_rate=0.5,
+               model_args=dict(pretrained=None), clip_encoder_args=dict(pretrained=None))
+    m = build_model(cfg)
+    sd = m.state_dict()
+    shapes = O.param_shapes(O.ModelCfg(img_size=224))
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    # SURVEY.md §8c probe numbers of the reference: total / backbone / trainable backbone / head parameters at 224^2
+    n = lambda it: sum(p.numel() for p in it)
+    assert n(m.parameters()) == 175238369
+    assert n(m.backbone.parameters()) == 86192640 + 0 or abs(n(m.backbone.parameters()) - 86.193e6) < 2e3
+    assert abs(n(p for p in m.backbone.parameters() if p.requires_grad) - 28.500e6) < 1e3
+    assert n(m.decode_head.parameters()) == 2217185
+    trainable = [k for k, p in m.named_parameters() if p.requires_grad and not k.startswith("clip_encoder")]
+    assert len(trainable) == 117                    # tensors that receive gradients in the reference
+    assert m.loaded_mcc_text_feat.shape == (98, 512)
+    from semivl_b200.text_embeddings import get_class_to_concept_idxs
+    g = get_class_to_concept_idxs(m.load_mcc_text_embedding)
+    assert len(g) == 21 and g[0] == list(range(45)) and g[20][-1] == 97
+    c = Config.fromfile(os.path.join(ROOT, "semivl_b200", "configs", "_base_", "models", "mcvit16.py"))
+    assert c.backbone.out_indices is None and c["backbone"]["embed_dims"] == 768
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semivl_b200.train import allreduce_sum_
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(1000, generator=g)
+    allreduce_sum_(flat)
+    q.put((rank, flat))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_gloo_world2(built):
+    """N-rank summed flat gradient == sum of the per-rank gradients (semivl.py:139-140 DDP semantics; the mean is folded into AdamW)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    want = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    assert torch.allclose(res[0], want) and torch.allclose(res[1], want)

@@ -431,24 +431,50 @@ __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dout, const flo
   }
 }
 // dw[t*C + c] += sum_pix dout[pix] * x[pix + tap_t, c];  dbias += sum dout
-__global__ void conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ x, int dtype, int64_t ld, float* __restrict__ dw,
-                                       float* __restrict__ dbias, int64_t maps, int h, int w, int C) {
-  // blockDim.x = 9*C threads (<= 288 for C = 32): thread = (t, c); pixels strided over the grid
-  const int t = threadIdx.x / C, c = threadIdx.x % C;
+// lane = channel (C == 32), one pixel per warp iteration, 9 tap accumulators per lane; block reduction through shared memory
+__global__ void __launch_bounds__(256)
+conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ x, int dtype, int64_t ld, float* __restrict__ dw,
+                       float* __restrict__ dbias, int64_t maps, int h, int w, int C) {
+  __shared__ float red[8][9][33];
+  __shared__ float redb[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = maps * h * w;
-  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
-  const int64_t p0 = blockIdx.x * per, p1 = p0 + per < total ? p0 + per : total;
-  float s = 0.f, sb = 0.f;
-  for (int64_t pix = p0; pix < p1; ++pix) {
-    const float d = dout[pix];
-    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
-    const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-    if (threadIdx.x == 0) sb += d;
-    if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
-    s += d * load_as_f32(x, dtype, (pix + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * ld + c, ld / 2);
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    float sb = 0.f;
+    for (int64_t pix = (int64_t)blockIdx.x * 8 + warp; pix < total; pix += (int64_t)gridDim.x * 8) {
+      const float d = dout[pix];
+      if (d == 0.f) continue;
+      sb += d;
+      const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+        if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w || c >= C) continue;
+        acc[t] += d * load_as_f32(x, dtype, (pix + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * ld + c, ld / 2);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) red[warp][t][lane] = acc[t];
+    if (lane == 0) redb[warp] = sb;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) {
+      const int t = i / 32, l = i % 32;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[k][t][l];
+      if (c0 + l < C && v != 0.f) atomicAdd(dw + t * C + c0 + l, v);
+    }
+    if (threadIdx.x == 0 && c0 == 0) {
+      float v = 0.f;
+      for (int k = 0; k < 8; ++k) v += redb[k];
+      atomicAdd(dbias, v);
+    }
+    __syncthreads();
   }
-  atomicAdd(dw + threadIdx.x, s);
-  if (threadIdx.x == 0) atomicAdd(dbias, sb);
 }
 
 }  // namespace
@@ -571,8 +597,8 @@ extern "C" int svl_conv_out1_bwd(const float* dout, const void* x, int x_dtype, 
   conv_out1_dgrad_kernel<<<ew_grid(maps * h * w * (C / 8)), 256, 9 * C * sizeof(float), ST>>>(dout, wgt, dx, dx_dtype, lddx, maps, h, w, C);
   SVL_LAUNCH_CHECK();
   int64_t total = maps * h * w;
-  int grid = (int)(total / 2048 > 0 ? (total / 2048 < 148 * 8 ? total / 2048 : 148 * 8) : 1);
-  conv_out1_wgrad_kernel<<<grid, 9 * C, 0, ST>>>(dout, x, x_dtype, ldx, dw, dbias, maps, h, w, C);
+  int grid = (int)(total / 64 > 0 ? (total / 64 < 148 * 8 ? total / 64 : 148 * 8) : 1);
+  conv_out1_wgrad_kernel<<<grid, 256, 0, ST>>>(dout, x, x_dtype, ldx, dw, dbias, maps, h, w, C);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

@@ -219,9 +219,14 @@ def main():
     ops.PROFILE = []
     step(resident)
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(bv) for a, bv, _ in ops.PROFILE)
-    gemm_flops = sum(f for _, _, f in ops.PROFILE)
+    gemm_ms = sum(a.elapsed_time(bv) for a, bv, _, _ in ops.PROFILE)
+    gemm_flops = sum(f for _, _, f, _ in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
+    if os.environ.get("SVL_PROFILE_DUMP") and rank == 0:
+        with open(os.environ["SVL_PROFILE_DUMP"], "w") as fh:
+            for a, bv, f, lab in ops.PROFILE:
+                t_ms = a.elapsed_time(bv)
+                fh.write(f"{t_ms * 1e3:10.1f} us {f / t_ms / 1e9 if t_ms > 0 else 0:8.1f} TF/s  {lab}\n")
     ops.PROFILE = None
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:

@@ -184,4 +184,71 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// 256-bit global stores (sm_100): one full 32-byte sector per thread per instruction
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+               "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 consecutive elements (fast path of the GEMM epilogue): BF16 -> one 32-byte store, F32 -> two; otherwise two st8
+__device__ __forceinline__ void st16(void* p, int dtype, int64_t off, int64_t lo_off, int cnt, const float* f) {
+  if (cnt == 16 && dtype == SVL_BF16) {
+    __nv_bfloat16* q = (__nv_bfloat16*)p + off;
+    if (((uintptr_t)q & 31) == 0) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        r[i] = *(uint32_t*)&h;
+      }
+      st_global_256(q, r);
+      return;
+    }
+  }
+  if (cnt == 16 && dtype == SVL_F32) {
+    float* q = (float*)p + off;
+    if (((uintptr_t)q & 31) == 0) {
+      st_global_256(q, (const uint32_t*)f);
+      st_global_256(q + 8, (const uint32_t*)(f + 8));
+      return;
+    }
+  }
+  st8(p, dtype, off, lo_off, cnt < 8 ? cnt : 8, f);
+  if (cnt > 8) st8(p, dtype, off + 8, lo_off, cnt - 8, f + 8);
+}
+__device__ __forceinline__ void ld16(const void* p, int dtype, int64_t off, int64_t lo_off, int cnt, float* f) {
+  ld8(p, dtype, off, lo_off, cnt < 8 ? cnt : 8, f);
+  if (cnt > 8) ld8(p, dtype, off + 8, lo_off, cnt - 8, f + 8);
+  else {
+#pragma unroll
+    for (int i = 8; i < 16; ++i) f[i] = 0.f;
+  }
+}
+
+// Fast exact-erf GELU for the bf16 throughput-mode epilogues: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. fp32-level),
+// one MUFU.RCP + one MUFU.EX2 instead of erff's branchy polynomial; the same exponential also gives the Gaussian of gelu'.
+__device__ __forceinline__ void erf_exp_fast(float u, float& erf_u, float& exp_mu2) {
+  const float a = fabsf(u);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.f)));      // MUFU.RCP, no IEEE fix-up branch
+  const float e = __expf(-a * a);
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float r = 1.f - pl * t * e;
+  erf_u = copysignf(r, u);
+  exp_mu2 = e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float er, ex;
+  erf_exp_fast(x * 0.70710678118654752f, er, ex);
+  return 0.5f * x * (1.f + er);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float er, ex;
+  erf_exp_fast(x * 0.70710678118654752f, er, ex);      // ex = exp(-x^2 / 2)
+  return 0.5f * (1.f + er) + x * 0.3989422804014327f * ex;
+}
+
 }  // namespace svl

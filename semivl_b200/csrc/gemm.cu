@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
-//   warps 2..5  : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global); warp w owns TMEM lane
+//                 quarter w % 4 and every other 32-column chunk
 //
 // Accumulators are double-buffered in TMEM (2 x block_n columns) so the epilogue of tile i overlaps the main
 // loop of tile i+1.  Tile = 128 output rows x block_n columns, K step 64 (one 128-byte swizzle row).
@@ -17,7 +18,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiGroups = 4;          // epilogue warps per TMEM lane quarter (each takes every kEpiGroups-th 32-column chunk)
+constexpr int kThreads = 64 + 128 * kEpiGroups;   // warp 0 TMA, warp 1 MMA, then 4 * kEpiGroups epilogue warps
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
 
@@ -57,6 +59,13 @@ __device__ __forceinline__ int64_t tile_row_to_global(const GemmParams& p, int m
   return ((int64_t)img * p.h + y) * p.w + x;
 }
 
+// Epilogue specialisations: the fully generic epilogue is ~8k instructions and starves the instruction cache (ncu: stall_no_inst
+// dominated, profiles/r01_gemm_epilogue.md), so the hot combinations are compiled with everything else pruned.
+//   OUT  : svl_dtype of the output            ACT : svl_act applied after bias
+//   PRE  : dtype of the saved pre-activation or -1         DACT: 0 none, 1 GELU' from a bf16 pre-activation
+//   RES  : dtype of the residual or -1        GEN : runtime-generic epilogue (all features, everything a runtime branch)
+//   EXT  : 0 linear output; 1 ConvT 2x2 scatter; 2 per-row-block bias (row_bias); 3 accumulate into an F32 output
+template <int OUT, int ACT, int PRE, int DACT, int RES, int EXT, bool GEN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -85,7 +94,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 4);
+      ptx::mbar_init(tempty_bar(s), 4 * kEpiGroups);
     }
     ptx::fence_barrier_init();
   }
@@ -162,6 +171,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int cgrp = (warp - 2) >> 2;       // which interleaved subset of the 32-column chunks
     const int r = q * 32 + lane;            // tile row of this thread
     const float alpha = p.alpha == 0.f ? 1.f : p.alpha;
     const int cq = p.out_mode == SVL_OUT_CONVT2X2 ? p.n / 4 : 0;
@@ -180,68 +190,147 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      if (GEN)
+      for (int c0 = cgrp * 32; c0 < p.block_n; c0 += kEpiGroups * 32) {
         if (n0 + c0 >= p.n) break;
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
         ptx::tmem_ld_wait();
-        if (grow < 0) continue;
+        if (GEN) {
+          if (grow < 0) continue;
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            const int col = n0 + c0 + g * 8;
+            const int cnt = min(8, p.n - col);
+            if (cnt <= 0) break;
+            float f[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = n0 + c0 + g * 8;
-          const int cnt = min(8, p.n - col);
-          if (cnt <= 0) break;
-          float f[8];
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * alpha;
+            if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]) * alpha;
-          if (p.bias) {
+              for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(p.bias + col + i);
+            }
+            if (p.row_bias) {
+              const float* rb = p.row_bias + (grow / p.row_bias_div) * p.row_bias_ld + col;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(p.bias + col + i);
+              for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(rb + i);
+            }
+            if (p.preact_out) st8(p.preact_out, p.preact_dtype, grow * p.ld_preact + col, 0, cnt, f);
+            if (p.act == SVL_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = gelu_exact(f[i]);
+            } else if (p.act == SVL_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (p.dact_src) {
+              float s[8];
+              ld8(p.dact_src, p.dact_dtype, grow * p.ld_dact + col, p.ld_dact / 2, cnt, s);
+              if (p.dact_kind == SVL_ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= gelu_grad(s[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = s[i] > 0.f ? f[i] : 0.f;
+              }
+            }
+            if (p.residual) {
+              float s[8];
+              ld8(p.residual, p.res_dtype, grow * p.ldres + col, 0, cnt, s);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += s[i];
+            }
+            int64_t off;
+            if (cq) {
+              const int qq = col / cq, cc = col % cq;       // cq % 8 == 0: an 8-group never straddles a quadrant
+              off = ct_base + ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
+            } else {
+              off = grow * p.ldc + col;
+            }
+            if (p.accumulate) {
+              float s[8];
+              ld8(p.out, SVL_F32, off, 0, cnt, s);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += s[i];
+            }
+            st8(p.out, p.out_dtype, off, p.ldc / 2, cnt, f);
           }
-          if (p.row_bias) {
-            const float* rb = p.row_bias + (grow / p.row_bias_div) * p.row_bias_ld + col;
+        } else {
+          // (unreachable: the specialised kernels use the slab loop below)
+        }
+      }
+      if (!GEN) {
+        // specialised epilogue: 32-column chunks, one output row per thread, 32-byte vector accesses (full sectors);
+        // bias / act / act' / residual fused in registers
+        for (int c0 = cgrp * 32; c0 < p.block_n; c0 += kEpiGroups * 32) {
+          if (n0 + c0 >= p.n) break;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
+          ptx::tmem_ld_wait();
+          if (grow < 0) continue;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(rb + i);
-          }
-          if (p.preact_out) st8(p.preact_out, p.preact_dtype, grow * p.ld_preact + col, 0, cnt, f);
-          if (p.act == SVL_ACT_GELU) {
+          for (int g = 0; g < 2; ++g) {
+            const int col = n0 + c0 + g * 16;
+            const int cnt = min(16, p.n - col);
+            if (cnt <= 0) break;
+            float f[16];
+            if (alpha != 1.f) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = gelu_exact(f[i]);
-          } else if (p.act == SVL_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (p.dact_src) {
-            float s[8];
-            ld8(p.dact_src, p.dact_dtype, grow * p.ld_dact + col, p.ld_dact / 2, cnt, s);
-            if (p.dact_kind == SVL_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] *= gelu_grad(s[i]);
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[g * 16 + i]) * alpha;
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = s[i] > 0.f ? f[i] : 0.f;
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[g * 16 + i]);
             }
-          }
-          if (p.residual) {
-            float s[8];
-            ld8(p.residual, p.res_dtype, grow * p.ldres + col, 0, cnt, s);
+            if (p.bias) {
+              if (cnt == 16 && (((uintptr_t)(p.bias + col)) & 15) == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += s[i];
-          }
-          int64_t off;
-          if (cq) {
-            const int qq = col / cq, cc = col % cq;       // cq % 8 == 0: an 8-group never straddles a quadrant
-            off = ct_base + ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
-          } else {
-            off = grow * p.ldc + col;
-          }
-          if (p.accumulate) {
-            float s[8];
-            ld8(p.out, SVL_F32, off, 0, cnt, s);
+                for (int j = 0; j < 4; ++j) {
+                  const float4 bb = __ldg((const float4*)(p.bias + col) + j);
+                  f[4 * j] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+                }
+              } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += s[i];
+                for (int i = 0; i < 16; ++i) if (i < cnt) f[i] += __ldg(p.bias + col + i);
+              }
+            }
+            if (EXT == 2) {
+              const float* rb = p.row_bias + (grow / p.row_bias_div) * p.row_bias_ld + col;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (i < cnt) f[i] += __ldg(rb + i);
+            }
+            if (PRE >= 0) st16(p.preact_out, PRE, grow * p.ld_preact + col, 0, cnt, f);
+            if (ACT == SVL_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = gelu_fast(f[i]);
+            } else if (ACT == SVL_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (DACT == 1) {
+              float sv[16];
+              ld16(p.dact_src, SVL_BF16, grow * p.ld_dact + col, 0, cnt, sv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] *= gelu_grad_fast(sv[i]);
+            }
+            if (RES >= 0) {
+              float sv[16];
+              ld16(p.residual, RES, grow * p.ldres + col, 0, cnt, sv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += sv[i];
+            }
+            int64_t off = grow * p.ldc + col;
+            if (EXT == 1) {                                  // cq % 16 == 0 is checked by the launcher for this variant
+              const int qq = col / cq, cc = col % cq;
+              off = ct_base + ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
+            }
+            if (EXT == 3) {
+              float sv[16];
+              ld16(p.out, SVL_F32, off, 0, cnt, sv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += sv[i];
+            }
+            st16(p.out, OUT, off, p.ldc / 2, cnt, f);
           }
-          st8(p.out, p.out_dtype, off, p.ldc / 2, cnt, f);
         }
       }
       ptx::tc_fence_before();
@@ -354,14 +443,42 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.accumulate = d->accumulate;
 
   const size_t smem = 1024 + (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 8 * (2 * kMaxStages + 4) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVL_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  const bool plain = !p.row_bias && !p.accumulate && p.out_mode == SVL_OUT_LINEAR;
+  const bool no_extra = !p.preact_out && !p.dact_src && !p.residual && p.act == SVL_ACT_NONE;
+#define SVL_LAUNCH_GEMM(...)                                                                                              \
+  do {                                                                                                                    \
+    static bool attr_set = false;                                                                                         \
+    if (!attr_set) {                                                                                                      \
+      SVL_CUDA(cudaFuncSetAttribute(gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
+      attr_set = true;                                                                                                    \
+    }                                                                                                                     \
+    gemm_kernel<__VA_ARGS__><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);                               \
+  } while (0)
+  if (plain && no_extra && p.out_dtype == SVL_BF16) {
+    SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 0, false);
+  } else if (plain && no_extra && p.out_dtype == SVL_F32) {
+    SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, -1, 0, false);
+  } else if (plain && p.out_dtype == SVL_F32 && p.residual && p.res_dtype == SVL_F32 && !p.preact_out && !p.dact_src && p.act == SVL_ACT_NONE) {
+    SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, SVL_F32, 0, false);
+  } else if (plain && p.out_dtype == SVL_BF16 && p.act == SVL_ACT_GELU && !p.dact_src && !p.residual &&
+             (!p.preact_out || p.preact_dtype == SVL_BF16)) {
+    if (p.preact_out) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU, SVL_BF16, 0, -1, 0, false);
+    else SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU, -1, 0, -1, 0, false);
+  } else if (plain && p.out_dtype == SVL_BF16 && p.dact_src && p.dact_kind == SVL_ACT_GELU && p.dact_dtype == SVL_BF16 && !p.preact_out &&
+             !p.residual && p.act == SVL_ACT_NONE) {
+    SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 1, -1, 0, false);
+  } else if (no_extra && p.out_mode == SVL_OUT_CONVT2X2 && p.out_dtype == SVL_BF16 && !p.row_bias && !p.accumulate && (p.n / 4) % 16 == 0) {
+    SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 1, false);
+  } else if (no_extra && p.out_mode == SVL_OUT_LINEAR && p.out_dtype == SVL_BF16 && p.row_bias && !p.accumulate) {
+    SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 2, false);
+  } else if (no_extra && p.out_mode == SVL_OUT_LINEAR && p.out_dtype == SVL_F32 && !p.row_bias && p.accumulate) {
+    SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, -1, 3, false);
+  } else {
+    SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, -1, 0, true);
+  }
+#undef SVL_LAUNCH_GEMM
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

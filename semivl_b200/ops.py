@@ -13,7 +13,7 @@ from . import lib as L
 PROFILE = None      # set to a list to record (start_event, end_event, flops) around every contraction launch (bench.py roofline)
 
 
-def _profiled(fn, flops):
+def _profiled(fn, flops, label=None):
     if PROFILE is None:
         fn()
         return
@@ -21,7 +21,7 @@ def _profiled(fn, flops):
     e0.record()
     fn()
     e1.record()
-    PROFILE.append((e0, e1, flops))
+    PROFILE.append((e0, e1, flops, label))
 
 
 def split_bf16(x):
@@ -101,7 +101,7 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
         d.residual, d.res_dtype, d.ldres = residual.data_ptr(), L.dtype_of(residual), residual.shape[-1]
     d.accumulate = 1 if accumulate else 0
     d.block_n = block_n
-    _profiled(lambda: L.raw_gemm(d), 2.0 * d.m * n * k * len(taps))
+    _profiled(lambda: L.raw_gemm(d), 2.0 * d.m * n * k * len(taps), f"gemm m{d.m} n{n} k{k} taps{len(taps)} conv{d.a_conv} out{d.out_dtype} mode{d.out_mode}")
     return out
 
 
@@ -144,7 +144,7 @@ def wgrad(dy, x, dw, *, m, n, precise=False, conv=None, filt=None, dy_koff=0, x_
     d.alpha = alpha
     d.splits = splits
     nlog = len(taps) // (3 if precise else 1)
-    _profiled(lambda: L.raw_wgrad(d), 2.0 * d.rows * m * n * nlog)
+    _profiled(lambda: L.raw_wgrad(d), 2.0 * d.rows * m * n * nlog, f"wgrad rows{d.rows} m{m} n{n} taps{nlog} conv{d.conv}")
     return dw
 
 

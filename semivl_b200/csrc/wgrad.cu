@@ -7,6 +7,8 @@
 // SWIZZLE_128B operand tile (8 K-rows per 1024-byte group, 64-channel chunks one box apart).  The contraction runs over
 // rows; it is split across CTAs (split-K) and the partial tiles are reduced with red.global.add.f32.
 // replaces: autograd's wgrad of nn.Linear / nn.Conv2d / nn.ConvTranspose2d on the hot path (semivl.py:327).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma.h"
@@ -187,6 +189,278 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Strip variant for k x k convolutions: the taps of one filter ROW (same dy, different dx) share one load of the dy tile and one
+// load of an x strip that is (bw + span) pixels wide; each tap's operand is the same strip read at a different K-row offset
+// (matrix-descriptor start address + base offset), so x is fetched 3x instead of 9x and dy 3x instead of 9x from L2.
+constexpr int kMaxGroupTaps = 4;
+struct StripParams {
+  int nb, h, w, bw, bh, bn, tiles_x, tiles_y;
+  int64_t num_kblocks;
+  int m, n, block_n, num_m_tiles, num_n_tiles, ngroups, splits;
+  int g_ntaps[8], g_dy[8], g_dxmin[8];
+  int g_dx[8][kMaxGroupTaps], g_slot[8][kMaxGroupTaps];
+  int dy_koff, x_koff;
+  int strip_w, strip_rows;
+  uint32_t strip_stride, a_chunks;
+  int stages, tmem_cols, bo_mode;
+  float* dw; int64_t ld_dw, slot_stride;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ StripParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  const int nchunks_b = p.block_n / 64;
+  const uint32_t a_stage = p.a_chunks * kBoxBytes, b_stage = (uint32_t)nchunks_b * p.strip_stride;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + p.stages * a_stage;
+  const uint32_t zero_buf = smem_b + p.stages * b_stage;             // 8 KB of zeros: the absent second dy chunk when m <= 64
+  const uint32_t bar_base = zero_buf + kBoxBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 1);
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int bid = blockIdx.x;
+  const int split = bid % p.splits; bid /= p.splits;
+  const int m_tile = bid % p.num_m_tiles; bid /= p.num_m_tiles;
+  const int n_tile = bid % p.num_n_tiles; bid /= p.num_n_tiles;
+  const int grp = bid;
+  const int64_t kb_per = (p.num_kblocks + p.splits - 1) / p.splits;
+  const int64_t kb0 = split * kb_per;
+  const int64_t kb1 = kb0 + kb_per < p.num_kblocks ? kb0 + kb_per : p.num_kblocks;
+  const int ntaps = p.g_ntaps[grp];
+  const bool has_work = kb1 > kb0;
+
+  if (p.a_chunks == 1) {
+    uint4* z = (uint4*)(smem_raw + (zero_buf - raw));
+    for (int i = threadIdx.x; i < (int)(kBoxBytes / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDY);
+    ptx::prefetch_tmap(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tfull_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (has_work) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = p.a_chunks * kBoxBytes + (uint32_t)nchunks_b * (uint32_t)p.strip_rows * 128u;
+        const int ca = p.dy_koff + m_tile * BM, cb = p.x_koff + n_tile * p.block_n;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
+          const int cx = (int)(kb % p.tiles_x) * p.bw;
+          const int cy = (int)((kb / p.tiles_x) % p.tiles_y) * p.bh;
+          const int cn = (int)(kb / ((int64_t)p.tiles_x * p.tiles_y)) * p.bn;
+          for (uint32_t c = 0; c < p.a_chunks; ++c) ptx::tma_load_4d(sa + c * kBoxBytes, &tmDY, full_bar(stage), ca + (int)c * 64, cx, cy, cn);
+          for (int c = 0; c < nchunks_b; ++c)
+            ptx::tma_load_4d(sb + c * p.strip_stride, &tmX, full_bar(stage), cb + c * 64, cx + p.g_dxmin[grp], cy + p.g_dy[grp], cn);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
+        // The issuing thread is alone: every integer instruction in this loop is exposed latency.  All descriptor arithmetic is
+        // hoisted: per (tap, K step) a descriptor relative to the stage base, per stage one 64-bit add.
+        uint64_t bdesc0[kMaxGroupTaps][KB / 16], adesc0[KB / 16];
+#pragma unroll
+        for (int ti = 0; ti < kMaxGroupTaps; ++ti) {
+          const int shift = ti < ntaps ? p.g_dx[grp][ti] - p.g_dxmin[grp] : 0;
+#pragma unroll
+          for (int kk = 0; kk < KB / 16; ++kk) {
+            const int prow = kk * 16;
+            const int srow = (prow / p.bw) * p.strip_w + (prow % p.bw) + shift;
+            bdesc0[ti][kk] = ptx::make_smem_desc((uint32_t)srow * 128u, p.strip_stride, 1024);
+          }
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t accum = 0;
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
+          const uint32_t a_lbo = p.a_chunks == 2 ? kBoxBytes : (zero_buf - sa);
+#pragma unroll
+          for (int kk = 0; kk < KB / 16; ++kk)   // the zero chunk (a_chunks == 1) is shared by all K steps: its offset must not advance with kk
+            adesc0[kk] = ptx::make_smem_desc(sa + kk * 2048, p.a_chunks == 2 ? a_lbo : a_lbo - kk * 2048, 1024);
+          const uint64_t sb16 = (uint64_t)(sb >> 4);
+#pragma unroll
+          for (int ti = 0; ti < kMaxGroupTaps; ++ti) {
+            if (ti < ntaps) {
+#pragma unroll
+              for (int kk = 0; kk < KB / 16; ++kk)
+                ptx::umma_bf16(tmem_base + (uint32_t)(ti * p.block_n), adesc0[kk], bdesc0[ti][kk] + sb16, idesc, kk > 0 ? 1u : accum);
+            }
+          }
+          accum = 1;
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int i = m_tile * BM + q * 32 + lane;
+      ptx::mbar_wait(tfull_bar, 0);
+      ptx::tc_fence_after();
+      const int n0 = n_tile * p.block_n;
+      for (int ti = 0; ti < ntaps; ++ti) {
+        float* row = p.dw + (int64_t)p.g_slot[grp][ti] * p.slot_stride + (int64_t)i * p.ld_dw;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          if (n0 + c0 >= p.n) break;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ti * p.block_n + c0), v);
+          ptx::tmem_ld_wait();
+          if (i >= p.m) continue;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = n0 + c0 + g * 4;
+            float* dst = row + col;
+            float f0 = __uint_as_float(v[g * 4]) * p.alpha, f1 = __uint_as_float(v[g * 4 + 1]) * p.alpha,
+                  f2 = __uint_as_float(v[g * 4 + 2]) * p.alpha, f3 = __uint_as_float(v[g * 4 + 3]) * p.alpha;
+            if (col + 4 <= p.n && ((uintptr_t)dst & 15) == 0) {
+              red_add_v4(dst, f0, f1, f2, f3);
+            } else {
+              if (col < p.n) atomicAdd(dst, f0);
+              if (col + 1 < p.n) atomicAdd(dst + 1, f1);
+              if (col + 2 < p.n) atomicAdd(dst + 2, f2);
+              if (col + 3 < p.n) atomicAdd(dst + 3, f3);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// Returns 1 when the strip kernel was launched, 0 when the problem does not qualify, < 0 on error.
+int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SVL_WGRAD_STRIP");
+    mode = e ? atoi(e) : 2;      // 2: descriptor start address only (the 128B swizzle is a function of the absolute smem address; verified on B200);
+                                 // 1: additionally set the descriptor base_offset field (wrong on B200, kept for experiments); 0: disabled
+  }
+  if (mode == 0 || !d->conv || d->num_taps < 2 || d->num_taps > SVL_MAX_TAPS) return 0;
+  if (d->x_map_w != 0 || d->w % 16 != 0) return 0;
+  StripParams p;
+  memset(&p, 0, sizeof(p));
+  p.bw = d->w < KB ? d->w : KB;
+  if (p.bw % 16 != 0) return 0;
+  p.bh = d->h < KB / p.bw ? d->h : KB / p.bw;
+  p.bn = d->nb < KB / (p.bw * p.bh) ? d->nb : KB / (p.bw * p.bh);
+  if (p.bw * p.bh * p.bn != KB) return 0;
+  // group taps by dy; every tap must be its own slot and share the column offsets
+  int span = 0;
+  for (int t = 0; t < d->num_taps; ++t) {
+    if (d->tap_dy_koff[t] != d->tap_dy_koff[0] || d->tap_x_koff[t] != d->tap_x_koff[0] || d->tap_slot[t] != t) return 0;
+    int g = -1;
+    for (int k = 0; k < p.ngroups; ++k) if (p.g_dy[k] == d->tap_dy[t]) g = k;
+    if (g < 0) {
+      if (p.ngroups == 8) return 0;
+      g = p.ngroups++;
+      p.g_dy[g] = d->tap_dy[t];
+      p.g_dxmin[g] = d->tap_dx[t];
+    }
+    if (p.g_ntaps[g] == kMaxGroupTaps) return 0;
+    p.g_dx[g][p.g_ntaps[g]] = d->tap_dx[t];
+    p.g_slot[g][p.g_ntaps[g]] = t;
+    p.g_ntaps[g]++;
+    if (d->tap_dx[t] < p.g_dxmin[g]) p.g_dxmin[g] = d->tap_dx[t];
+  }
+  int max_taps = 0;
+  for (int g = 0; g < p.ngroups; ++g) {
+    for (int k = 0; k < p.g_ntaps[g]; ++k) span = span > p.g_dx[g][k] - p.g_dxmin[g] ? span : p.g_dx[g][k] - p.g_dxmin[g];
+    max_taps = max_taps > p.g_ntaps[g] ? max_taps : p.g_ntaps[g];
+  }
+  if (max_taps * block_n > 512 || p.bw + span > 256) return 0;
+  p.nb = d->nb; p.h = d->h; p.w = d->w;
+  p.tiles_x = (d->w + p.bw - 1) / p.bw;
+  p.tiles_y = (d->h + p.bh - 1) / p.bh;
+  p.num_kblocks = (int64_t)p.tiles_x * p.tiles_y * ((d->nb + p.bn - 1) / p.bn);
+  p.m = d->m; p.n = d->n; p.block_n = block_n;
+  p.num_m_tiles = (d->m + BM - 1) / BM;
+  p.num_n_tiles = (d->n + block_n - 1) / block_n;
+  p.dy_koff = d->tap_dy_koff[0]; p.x_koff = d->tap_x_koff[0];
+  p.strip_w = p.bw + span;
+  p.strip_rows = p.strip_w * p.bh * p.bn;
+  p.strip_stride = ((uint32_t)p.strip_rows * 128u + 1023u) & ~1023u;
+  p.a_chunks = d->m <= 64 ? 1u : 2u;
+  p.bo_mode = mode;
+  p.dw = d->dw; p.ld_dw = d->ld_dw; p.slot_stride = d->slot_stride;
+  p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  const uint32_t stage_bytes = p.a_chunks * kBoxBytes + (uint32_t)(block_n / 64) * p.strip_stride;
+  p.stages = (int)((kSmemBudget - kBoxBytes) / stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages < 2) return 0;
+  p.tmem_cols = pow2ceil(max_taps * block_n < 32 ? 32 : max_taps * block_n);
+
+  const int64_t dy_cols = d->dy_cols > 0 ? d->dy_cols : d->ld_dy;
+  const int64_t x_cols = d->x_cols > 0 ? d->x_cols : d->ld_x;
+  CUtensorMap tmDY, tmX;
+  {
+    uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    uint64_t dims[4] = {(uint64_t)dy_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t st[3] = {(uint64_t)d->ld_dy * 2, (uint64_t)d->ld_dy * 2 * d->w, (uint64_t)d->ld_dy * 2 * d->w * d->h};
+    if (int rc = tma_encode_bf16(&tmDY, d->dy, 4, dims, st, box)) return rc;
+    uint32_t boxx[4] = {64u, (uint32_t)p.strip_w, (uint32_t)p.bh, (uint32_t)p.bn};
+    uint64_t dimsx[4] = {(uint64_t)x_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t stx[3] = {(uint64_t)d->ld_x * 2, (uint64_t)d->ld_x * 2 * d->w, (uint64_t)d->ld_x * 2 * d->w * d->h};
+    if (int rc = tma_encode_bf16(&tmX, d->x, 4, dimsx, stx, boxx)) return rc;
+  }
+  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * p.ngroups;
+  int splits = d->splits;
+  if (splits <= 0) {
+    int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles;
+    int64_t cap = p.num_kblocks / 8 > 0 ? p.num_kblocks / 8 : 1;
+    splits = (int)(want < cap ? want : cap);
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.num_kblocks) splits = (int)p.num_kblocks;
+  p.splits = splits;
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + kBoxBytes + 8 * (2 * kMaxStages + 2) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVL_CUDA(cudaFuncSetAttribute(wgrad_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  wgrad_strip_kernel<<<(unsigned)(tiles * splits), kThreads, smem, stream>>>(tmDY, tmX, p);
+  SVL_LAUNCH_CHECK();
+  return 1;
+}
+
 }  // namespace
 }  // namespace svl
 
@@ -226,6 +500,10 @@ extern "C" int svl_wgrad(const svl_wgrad_desc* d, void* stream) {
       if (pad < best_pad) { best = bn; best_pad = pad; }
     }
     p.block_n = best;
+  }
+  {
+    int rc = try_launch_strip(d, p.block_n, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : SVL_OK;
   }
   p.num_m_tiles = (d->m + BM - 1) / BM;
   p.num_n_tiles = (d->n + p.block_n - 1) / p.block_n;

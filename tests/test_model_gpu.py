@@ -112,7 +112,7 @@ def test_supervised_step_matches_oracle(text_dir, precise):
     nz = gs.abs() > 1e-6
     lr = torch.cat((torch.full((tr.n_bb,), 1e-4 * 0.01), torch.full((tr.n_hd,), 1e-4 * 10.0))).cuda()
     expect = -lr * gs / (gs.abs() + 1e-8) - lr * 0.01 * before           # step 1: m_hat / (sqrt(v_hat) + eps) = g / (|g| + eps)
-    assert ((delta - expect).abs()[nz] <= 1e-3 * lr[nz] + 1e-9).all()
+    assert ((delta - expect).abs()[nz] <= 1e-3 * lr[nz] + 2e-8).all()          # fp32 ulp of the parameters is ~2e-9
 
 
 @pytest.mark.parametrize("name", ["step_c64_b1", "step_c96_b2"])

@@ -14,131 +14,207 @@ inline int ew_grid(int64_t total, int block = 256) {
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm + ReLU
-// one CTA per map; pass 1 statistics, pass 2 (L2-resident re-read) normalise + ReLU (+ residual)
-constexpr int kGnThreads = 512;
+// Three phases, each a full grid of (map, split) CTAs so that small batches of large maps still fill the machine:
+//   stats    : per-(map, group) sum / sum of squares (block partials -> global atomics)
+//   finalize : sums -> mean / rstd (in place)
+//   apply    : y = relu((x - mean) * rstd * gamma + beta) (+ residual); a thread keeps the same 8 channels for all its pixels
+constexpr int kGnThreads = 256;
 constexpr int kMaxGroups = 16;
 
+__device__ __forceinline__ void gn_range(int hw, int splits, int split, int& p0, int& p1) {
+  const int per = (hw + splits - 1) / splits;
+  p0 = split * per;
+  p1 = p0 + per < hw ? p0 + per : hw;
+}
+
 __global__ void __launch_bounds__(kGnThreads)
-gn_relu_fwd_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   void* __restrict__ out, int out_dtype, int64_t ldo, const void* __restrict__ res, int res_dtype, int64_t ldres,
-                   float* __restrict__ mean, float* __restrict__ rstd, int hw, int C, int G, float eps) {
-  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups], s_mu[kMaxGroups], s_rs[kMaxGroups];
-  const int map = blockIdx.x;
-  const int vpp = C / 8;                         // 8-channel vectors per pixel
-  const int cpg = C / G;
-  const int64_t nvec = (int64_t)hw * vpp;
+gn_stats_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, float* __restrict__ sum, float* __restrict__ sq, int hw, int C, int G,
+                int splits) {
+  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;      // pixels per iteration
   if (threadIdx.x < kMaxGroups) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
   __syncthreads();
-  const int64_t xbase = (int64_t)map * hw * ldx;
-  // kGnThreads % vpp == 0 -> a thread always sees the same 8 channels, hence one group
-  const int c8 = (threadIdx.x % vpp) * 8;
-  const int g = c8 / cpg;
+  int p0, p1;
+  gn_range(hw, splits, split, p0, p1);
+  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
+  const int64_t xbase = (int64_t)map * hw * ldx + c8;
   float pa = 0.f, pb = 0.f;
-  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
-    float f[8];
-    ld8(x, x_dtype, xbase + (v / vpp) * ldx + c8, ldx / 2, 8, f);
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 4 * ppi) {
+    float f[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { pa += f[i]; pb += f[i] * f[i]; }
+    for (int u = 0; u < 4; ++u) {
+      if (pix + u * ppi < p1) ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, f[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { pa += f[u][i]; pb += f[u][i] * f[u][i]; }
+    }
   }
   atomicAdd(&s_sum[g], pa);
   atomicAdd(&s_sq[g], pb);
   __syncthreads();
   if (threadIdx.x < G) {
-    const float n = (float)hw * cpg;
-    const float mu = s_sum[threadIdx.x] / n;
-    const float var = fmaxf(s_sq[threadIdx.x] / n - mu * mu, 0.f);
-    const float rs = rsqrtf(var + eps);
-    s_mu[threadIdx.x] = mu;
-    s_rs[threadIdx.x] = rs;
-    if (mean) mean[(int64_t)map * G + threadIdx.x] = mu;
-    if (rstd) rstd[(int64_t)map * G + threadIdx.x] = rs;
+    atomicAdd(sum + (int64_t)map * G + threadIdx.x, s_sum[threadIdx.x]);
+    atomicAdd(sq + (int64_t)map * G + threadIdx.x, s_sq[threadIdx.x]);
   }
-  __syncthreads();
-  const float mu = s_mu[g], rs = s_rs[g];
+}
+__global__ void gn_finalize_kernel(float* __restrict__ mean, float* __restrict__ rstd, int64_t n, float count, float eps) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float mu = mean[i] / count;
+  const float var = fmaxf(rstd[i] / count - mu * mu, 0.f);
+  mean[i] = mu;
+  rstd[i] = rsqrtf(var + eps);
+}
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                void* __restrict__ out, int out_dtype, int64_t ldo, const void* __restrict__ res, int res_dtype, int64_t ldres,
+                const float* __restrict__ mean, const float* __restrict__ rstd, int hw, int C, int G, int splits) {
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;
+  int p0, p1;
+  gn_range(hw, splits, split, p0, p1);
+  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
+  const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
   float ga[8], be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i] * rs; be[i] = beta[c8 + i] - mu * ga[i]; }
-  const int64_t obase = (int64_t)map * hw * ldo, rbase = (int64_t)map * hw * ldres;
-  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
-    const int64_t pix = v / vpp;
-    float f[8];
-    ld8(x, x_dtype, xbase + pix * ldx + c8, ldx / 2, 8, f);
+  const int64_t xbase = (int64_t)map * hw * ldx + c8, obase = (int64_t)map * hw * ldo + c8, rbase = (int64_t)map * hw * ldres + c8;
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 4 * ppi) {
+    float f[4][8], r[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i] * ga[i] + be[i], 0.f);
-    if (res) {
-      float r[8];
-      ld8(res, res_dtype, rbase + pix * ldres + c8, ldres / 2, 8, r);
+    for (int u = 0; u < 4; ++u)
+      if (pix + u * ppi < p1) {
+        ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, f[u]);
+        if (res) ld8(res, res_dtype, rbase + (int64_t)(pix + u * ppi) * ldres, ldres / 2, 8, r[u]);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
-    }
-    st8(out, out_dtype, obase + pix * ldo + c8, ldo / 2, 8, f);
+    for (int u = 0; u < 4; ++u)
+      if (pix + u * ppi < p1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[u][i] = fmaxf(f[u][i] * ga[i] + be[i], 0.f);
+          if (res) f[u][i] += r[u][i];
+        }
+        st8(out, out_dtype, obase + (int64_t)(pix + u * ppi) * ldo, ldo / 2, 8, f[u]);
+      }
   }
 }
 
-// dx = GN'(dy * relu'(y)); dgamma/dbeta accumulated with atomics
+// backward: stats (s1 = sum g, s2 = sum g*xhat per (map, group), dgamma/dbeta) then apply  dx = rstd * (g - s1/n - xhat * s2/n)
 __global__ void __launch_bounds__(kGnThreads)
-gn_relu_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const void* __restrict__ x, int x_dtype, int64_t ldx,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, void* __restrict__ dx, int dx_dtype, int64_t lddx, float* __restrict__ dgamma,
-                   float* __restrict__ dbeta, int hw, int C, int G) {
+gn_bwd_stats_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const void* __restrict__ x, int x_dtype, int64_t ldx,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int hw,
+                    int C, int G, int splits) {
   __shared__ float s_s1[kMaxGroups], s_s2[kMaxGroups];
   __shared__ float s_dg[256], s_db[256];
-  const int map = blockIdx.x;
-  const int vpp = C / 8, cpg = C / G;
-  const int64_t nvec = (int64_t)hw * vpp;
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;
   if (threadIdx.x < kMaxGroups) s_s1[threadIdx.x] = s_s2[threadIdx.x] = 0.f;
-  if (threadIdx.x < 256) s_dg[threadIdx.x] = s_db[threadIdx.x] = 0.f;
+  s_dg[threadIdx.x] = s_db[threadIdx.x] = 0.f;
   __syncthreads();
-  const int c8 = (threadIdx.x % vpp) * 8;
-  const int g = c8 / cpg;
+  int p0, p1;
+  gn_range(hw, splits, split, p0, p1);
+  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
   const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
   float ga[8], be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i]; be[i] = beta[c8 + i]; }
-  const int64_t xbase = (int64_t)map * hw * ldx, ybase = (int64_t)map * hw * lddy, obase = (int64_t)map * hw * lddx;
+  const int64_t xbase = (int64_t)map * hw * ldx + c8, ybase = (int64_t)map * hw * lddy + c8;
   float s1 = 0.f, s2 = 0.f, dg[8], db[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
-  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
-    const int64_t pix = v / vpp;
-    float xv[8], d[8];
-    ld8(x, x_dtype, xbase + pix * ldx + c8, ldx / 2, 8, xv);
-    ld8(dy, dy_dtype, ybase + pix * lddy + c8, lddy / 2, 8, d);
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 2 * ppi) {
+    float xv[2][8], d[2][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (xv[i] - mu) * rs;
-      const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
-      dg[i] += dd * xh;
-      db[i] += dd;
-      const float gg = dd * ga[i];
-      s1 += gg;
-      s2 += gg * xh;
-    }
+    for (int u = 0; u < 2; ++u)
+      if (pix + u * ppi < p1) {
+        ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, xv[u]);
+        ld8(dy, dy_dtype, ybase + (int64_t)(pix + u * ppi) * lddy, lddy / 2, 8, d[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (pix + u * ppi < p1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[u][i] - mu) * rs;
+          const float dd = (xh * ga[i] + be[i] > 0.f) ? d[u][i] : 0.f;
+          dg[i] += dd * xh;
+          db[i] += dd;
+          const float gg = dd * ga[i];
+          s1 += gg;
+          s2 += gg * xh;
+        }
+      }
   }
   atomicAdd(&s_s1[g], s1);
   atomicAdd(&s_s2[g], s2);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { atomicAdd(&s_dg[c8 + i], dg[i]); atomicAdd(&s_db[c8 + i], db[i]); }
   __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(ws + ((int64_t)map * G + threadIdx.x) * 2, s_s1[threadIdx.x]);
+    atomicAdd(ws + ((int64_t)map * G + threadIdx.x) * 2 + 1, s_s2[threadIdx.x]);
+  }
   if (threadIdx.x < C && dgamma) {
     atomicAdd(dgamma + threadIdx.x, s_dg[threadIdx.x]);
     atomicAdd(dbeta + threadIdx.x, s_db[threadIdx.x]);
   }
+}
+__global__ void __launch_bounds__(kGnThreads)
+gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const void* __restrict__ x, int x_dtype, int64_t ldx,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ ws, void* __restrict__ dx, int dx_dtype, int64_t lddx, int hw, int C,
+                    int G, int splits) {
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;
+  int p0, p1;
+  gn_range(hw, splits, split, p0, p1);
+  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
+  const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
   const float n = (float)hw * cpg;
-  const float m1 = s_s1[g] / n, m2 = s_s2[g] / n;
-  for (int64_t v = threadIdx.x; v < nvec; v += kGnThreads) {
-    const int64_t pix = v / vpp;
-    float xv[8], d[8], o[8];
-    ld8(x, x_dtype, xbase + pix * ldx + c8, ldx / 2, 8, xv);
-    ld8(dy, dy_dtype, ybase + pix * lddy + c8, lddy / 2, 8, d);
+  const float m1 = ws[((int64_t)map * G + g) * 2] / n, m2 = ws[((int64_t)map * G + g) * 2 + 1] / n;
+  float ga[8], be[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (xv[i] - mu) * rs;
-      const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
-      o[i] = rs * (dd * ga[i] - m1 - xh * m2);
-    }
-    st8(dx, dx_dtype, obase + pix * lddx + c8, lddx / 2, 8, o);
+  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i]; be[i] = beta[c8 + i]; }
+  const int64_t xbase = (int64_t)map * hw * ldx + c8, ybase = (int64_t)map * hw * lddy + c8, obase = (int64_t)map * hw * lddx + c8;
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 2 * ppi) {
+    float xv[2][8], d[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (pix + u * ppi < p1) {
+        ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, xv[u]);
+        ld8(dy, dy_dtype, ybase + (int64_t)(pix + u * ppi) * lddy, lddy / 2, 8, d[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (pix + u * ppi < p1) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[u][i] - mu) * rs;
+          const float dd = (xh * ga[i] + be[i] > 0.f) ? d[u][i] : 0.f;
+          o[i] = rs * (dd * ga[i] - m1 - xh * m2);
+        }
+        st8(dx, dx_dtype, obase + (int64_t)(pix + u * ppi) * lddx, lddx / 2, 8, o);
+      }
   }
+}
+
+inline int gn_splits(int64_t maps, int hw, int C) {
+  // aim for >= 4 CTAs per SM in total, at least ~8 pixel iterations per thread
+  int64_t want = (148 * 4 + maps - 1) / maps;
+  int64_t cap = (int64_t)hw * (C / 8) / (kGnThreads * 8);
+  if (cap < 1) cap = 1;
+  int64_t s = want < cap ? want : cap;
+  return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));
 }
 
 // ---------------------------------------------------------------------------------------------- 7x7 im2col of the similarity maps
@@ -381,28 +457,49 @@ __global__ void skip_grad_kernel(const void* __restrict__ dcat, int d_dtype, int
 }
 
 // ---------------------------------------------------------------------------------------------- output conv 3x3, C -> 1
-// out[map, y, x] = bias + sum_{t, c} w[t*C + c] * x[map, y+dy_t, x+dx_t, c]            (vlg_head.py:190,239-240); one warp per pixel group
-__global__ void conv_out1_fwd_kernel(const void* __restrict__ x, int dtype, int64_t ld, const float* __restrict__ wgt, const float* __restrict__ bias,
-                                     float* __restrict__ out, int64_t maps, int h, int w, int C) {
-  extern __shared__ float s_w[];        // [9*C]
+// out[map, y, x] = bias + sum_{t, c} w[t*C + c] * x[map, y+dy_t, x+dx_t, c]            (vlg_head.py:190,239-240)
+// Tile = 8 x 32 output pixels.  Every pixel of the (8+2) x (32+2) halo region is read ONCE: its 9 per-tap partial dot products
+// z_t = <w[t, :], x[p, :]> go to shared memory, then each output pixel sums the 9 shifted entries.
+constexpr int kO1TH = 8, kO1TW = 32, kO1HW = (kO1TH + 2) * (kO1TW + 2);
+__global__ void __launch_bounds__(256)
+conv_out1_fwd_kernel(const void* __restrict__ x, int dtype, int64_t ld, const float* __restrict__ wgt, const float* __restrict__ bias,
+                     float* __restrict__ out, int h, int w, int C, int tiles_x, int tiles_y) {
+  extern __shared__ float s_o1[];       // [9*C] weights, then [9][kO1HW] partial sums
+  float* s_w = s_o1;
+  float* s_z = s_o1 + 9 * C;
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
+  const int64_t map = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = tx * kO1TW - 1, y0 = ty * kO1TH - 1;
   __syncthreads();
-  const int64_t total = maps * h * w;
-  for (int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * blockDim.x) {
-    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
-    float s = bias[0];
-    for (int t = 0; t < 9; ++t) {
-      const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-      if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
-      const int64_t base = (pix + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * ld;
+  for (int i = threadIdx.x; i < kO1HW; i += blockDim.x) {
+    const int yy = y0 + i / (kO1TW + 2), xx = x0 + i % (kO1TW + 2);
+    float z[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) z[t] = 0.f;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const int64_t base = ((map * h + yy) * w + xx) * ld;
       for (int c = 0; c < C; c += 8) {
         float f[8];
         ld8(x, dtype, base + c, ld / 2, 8, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += f[i] * s_w[t * C + c + i];
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) z[t] += f[k] * s_w[t * C + c + k];
+        }
       }
     }
-    out[pix] = s;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s_z[t * kO1HW + i] = z[t];
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kO1TW, lx = threadIdx.x % kO1TW;
+  const int yy = ty * kO1TH + ly, xx = tx * kO1TW + lx;
+  if (yy < h && xx < w) {
+    float s = bias[0];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s += s_z[t * kO1HW + (ly + t / 3) * (kO1TW + 2) + lx + t % 3];
+    out[(map * h + yy) * w + xx] = s;
   }
 }
 // dx[map, y, x, c] = sum_t w[t*C + c] * dout[map, y-dy_t, x-dx_t]
@@ -430,8 +527,9 @@ __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dout, const flo
     st8(dx, dtype, pix * ld + c8, ld / 2, 8, f);
   }
 }
-// dw[t*C + c] += sum_pix dout[pix] * x[pix + tap_t, c];  dbias += sum dout
-// lane = channel (C == 32), one pixel per warp iteration, 9 tap accumulators per lane; block reduction through shared memory
+// dw[t*C + c] += sum_q x[q, c] * dout[q - tap_t];  dbias += sum dout
+// lane = channel (32 channels per pass): ONE 64-byte x row per pixel and the 9 neighbouring dout scalars (broadcast loads);
+// 4 pixels in flight per warp; block reduction through shared memory, then 9*C atomics per block.
 __global__ void __launch_bounds__(256)
 conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ x, int dtype, int64_t ld, float* __restrict__ dw,
                        float* __restrict__ dbias, int64_t maps, int h, int w, int C) {
@@ -439,22 +537,34 @@ conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ 
   __shared__ float redb[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = maps * h * w;
+  const int hw = h * w;
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + lane;
     float acc[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
     float sb = 0.f;
-    for (int64_t pix = (int64_t)blockIdx.x * 8 + warp; pix < total; pix += (int64_t)gridDim.x * 8) {
-      const float d = dout[pix];
-      if (d == 0.f) continue;
-      sb += d;
-      const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (int64_t q0 = (int64_t)blockIdx.x * 8 + warp; q0 < total; q0 += 4 * stride) {
+      float xv[4];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-        if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w || c >= C) continue;
-        acc[t] += d * load_as_f32(x, dtype, (pix + (int64_t)(t / 3 - 1) * w + (t % 3 - 1)) * ld + c, ld / 2);
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = q0 + u * stride;
+        xv[u] = (q < total && c < C) ? load_as_f32(x, dtype, q * ld + c, ld / 2) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = q0 + u * stride;
+        if (q >= total) break;
+        const int rem = (int)(q % hw);
+        const int yy = rem / w, xx = rem - yy * w;
+        if (c0 == 0) sb += dout[q];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int y2 = yy - (t / 3 - 1), x2 = xx - (t % 3 - 1);          // output pixel that reads q through tap t
+          if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
+          acc[t] += xv[u] * __ldg(dout + q - (int64_t)(t / 3 - 1) * w - (t % 3 - 1));
+        }
       }
     }
 #pragma unroll
@@ -486,25 +596,39 @@ using namespace svl;
 extern "C" int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
                                int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, int64_t maps, int hw, int C,
                                int G, float eps, void* stream) {
-  SVL_CHECK_ARG(x && gamma && beta && out, "svl_gn_relu_fwd: null pointer");
+  SVL_CHECK_ARG(x && gamma && beta && out && mean && rstd, "svl_gn_relu_fwd: null pointer (mean/rstd double as the statistics workspace)");
   SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
                 "svl_gn_relu_fwd: unsupported C=%d G=%d", C, G);
   if (maps == 0) return SVL_OK;
-  gn_relu_fwd_kernel<<<(unsigned)maps, kGnThreads, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean, rstd, hw,
-                                                            C, G, eps);
+  const int splits = gn_splits(maps, hw, C);
+  SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_fwd: grid too large");
+  SVL_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * maps * G, ST));
+  SVL_CUDA(cudaMemsetAsync(rstd, 0, sizeof(float) * maps * G, ST));
+  gn_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, mean, rstd, hw, C, G, splits);
+  SVL_LAUNCH_CHECK();
+  gn_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(mean, rstd, maps * G, (float)hw * (C / G), eps);
+  SVL_LAUNCH_CHECK();
+  gn_apply_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean,
+                                                                   rstd, hw, C, G, splits);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
 
 extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const float* gamma,
                                const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int64_t lddx, float* dgamma,
-                               float* dbeta, int64_t maps, int hw, int C, int G, void* stream) {
-  SVL_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx, "svl_gn_relu_bwd: null pointer");
+                               float* dbeta, float* ws, int64_t maps, int hw, int C, int G, void* stream) {
+  SVL_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && ws, "svl_gn_relu_bwd: null pointer");
   SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
                 "svl_gn_relu_bwd: unsupported C=%d G=%d", C, G);
   if (maps == 0) return SVL_OK;
-  gn_relu_bwd_kernel<<<(unsigned)maps, kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, dx, dx_dtype, lddx, dgamma,
-                                                            dbeta, hw, C, G);
+  const int splits = gn_splits(maps, hw, C);
+  SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_bwd: grid too large");
+  SVL_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * maps * G * 2, ST));
+  gn_bwd_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dgamma,
+                                                                       dbeta, hw, C, G, splits);
+  SVL_LAUNCH_CHECK();
+  gn_bwd_apply_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dx, dx_dtype,
+                                                                       lddx, hw, C, G, splits);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
@@ -587,7 +711,10 @@ extern "C" int svl_skip_grad(const void* dcat, int d_dtype, int64_t ldd, int c0,
 extern "C" int svl_conv_out1_fwd(const void* x, int dtype, int64_t ld, const float* wgt, const float* bias, float* out, int64_t maps, int h, int w,
                                  int C, void* stream) {
   SVL_CHECK_ARG(x && wgt && bias && out && C % 8 == 0, "svl_conv_out1_fwd: bad arguments");
-  conv_out1_fwd_kernel<<<ew_grid(maps * h * w), 256, 9 * C * sizeof(float), ST>>>(x, dtype, ld, wgt, bias, out, maps, h, w, C);
+  const int tiles_x = (w + kO1TW - 1) / kO1TW, tiles_y = (h + kO1TH - 1) / kO1TH;
+  const size_t smem = (size_t)(9 * C + 9 * kO1HW) * sizeof(float);
+  SVL_CHECK_ARG(maps * tiles_x * tiles_y < (1ll << 31), "svl_conv_out1_fwd: grid too large");
+  conv_out1_fwd_kernel<<<(unsigned)(maps * tiles_x * tiles_y), 256, smem, ST>>>(x, dtype, ld, wgt, bias, out, h, w, C, tiles_x, tiles_y);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

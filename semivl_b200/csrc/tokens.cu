@@ -113,95 +113,116 @@ layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __re
   }
 }
 
-// dx = dres1 + dres2 + LN'(dy); optional activation-format copy of dx; optional dgamma/dbeta accumulation
+// dx = dres1 + dres2 + LN'(dy); optional activation-format copy of dx; optional dgamma/dbeta accumulation.
+// NV = float4 vectors per lane (row width / 128), WG = accumulate weight gradients.  Everything is 8/16-byte vector traffic.
+__device__ __forceinline__ void load4_any(const void* p, int dtype, int64_t off, int64_t lo_off, float* d) {
+  if (dtype == SVL_F32) {
+    const float4 t = *(const float4*)((const float*)p + off);
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+  } else {
+    const __nv_bfloat16* q = (const __nv_bfloat16*)p + off;
+    uint2 u = *(const uint2*)q;
+    float2 a = __bfloat1622float2(*(__nv_bfloat162*)&u.x), b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+    if (dtype == SVL_BF16X2) {
+      u = *(const uint2*)(q + lo_off);
+      a = __bfloat1622float2(*(__nv_bfloat162*)&u.x); b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
+      d[0] += a.x; d[1] += a.y; d[2] += b.x; d[3] += b.y;
+    }
+  }
+}
+__device__ __forceinline__ void store4_act(void* p, int dtype, int64_t off, int64_t lo_off, const float* o) {
+  if (dtype == SVL_F32) {
+    *(float4*)((float*)p + off) = make_float4(o[0], o[1], o[2], o[3]);
+    return;
+  }
+  __nv_bfloat16* q = (__nv_bfloat16*)p + off;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+  uint2 u;
+  u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1;
+  *(uint2*)q = u;
+  if (dtype == SVL_BF16X2) {
+    float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2bfloat162_rn(o[2] - f1.x, o[3] - f1.y);
+    u.x = *(uint32_t*)&l0; u.y = *(uint32_t*)&l1;
+    *(uint2*)(q + lo_off) = u;
+  }
+}
+
+template <int NV, bool WG>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const float* __restrict__ x, int64_t ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ dres1, const float* __restrict__ dres2, float* __restrict__ dx, void* __restrict__ dx_act,
-                     int act_dtype, int64_t ld_act, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int c) {
-  __shared__ float sg[1024], sb[1024];
+                     int act_dtype, int64_t ld_act, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
+  constexpr int c = NV * 128;
+  __shared__ float sg[WG ? c : 1], sb[WG ? c : 1];
   const int lane = threadIdx.x & 31;
-  const int nv = c / 128;
-  const bool want_wg = dgamma != nullptr;
-  float ag[kMaxVec * 4], ab[kMaxVec * 4];
-  if (want_wg) {
+  float ag[WG ? NV * 4 : 1], ab[WG ? NV * 4 : 1];
+  float gm[NV * 4];
 #pragma unroll
-    for (int i = 0; i < kMaxVec * 4; ++i) ag[i] = ab[i] = 0.f;
+  for (int i = 0; i < NV; ++i) {
+    const float4 t = __ldg((const float4*)(gamma + (i * 32 + lane) * 4));
+    gm[i * 4] = t.x; gm[i * 4 + 1] = t.y; gm[i * 4 + 2] = t.z; gm[i * 4 + 3] = t.w;
+  }
+  if (WG) {
+#pragma unroll
+    for (int i = 0; i < NV * 4; ++i) ag[i] = ab[i] = 0.f;
     for (int i = threadIdx.x; i < c; i += blockDim.x) sg[i] = sb[i] = 0.f;
     __syncthreads();
   }
   for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
     const float mu = mean[row], rs = rstd[row];
-    float xh[kMaxVec * 4], g[kMaxVec * 4];
+    float xh[NV * 4], g[NV * 4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) {
-        const int col = (i * 32 + lane) * 4;
-        float4 xv = *(const float4*)(x + row * ldx + col);
-        float4 gm = __ldg((const float4*)(gamma + col));
-        float d[4];
-        if (dy_dtype == SVL_F32) {
-          float4 t = *(const float4*)((const float*)dy + row * lddy + col);
-          d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-        } else {
-          const __nv_bfloat16* p = (const __nv_bfloat16*)dy + row * lddy + col;
-          uint2 u = *(const uint2*)p;
-          float2 a = __bfloat1622float2(*(__nv_bfloat162*)&u.x), b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
-          d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
-          if (dy_dtype == SVL_BF16X2) {
-            u = *(const uint2*)(p + lddy / 2);
-            a = __bfloat1622float2(*(__nv_bfloat162*)&u.x); b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
-            d[0] += a.x; d[1] += a.y; d[2] += b.x; d[3] += b.y;
-          }
-        }
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gm.x, gm.y, gm.z, gm.w};
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 xv = *(const float4*)(x + row * ldx + col);
+      float d[4];
+      load4_any(dy, dy_dtype, row * lddy + col, lddy / 2, d);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float h = (xs[j] - mu) * rs;
-          xh[i * 4 + j] = h;
-          if (want_wg) { ag[i * 4 + j] += d[j] * h; ab[i * 4 + j] += d[j]; }
-          const float gg = d[j] * gs[j];
-          g[i * 4 + j] = gg;
-          s1 += gg;
-          s2 += gg * h;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float h = (xs[j] - mu) * rs;
+        xh[i * 4 + j] = h;
+        if (WG) { ag[i * 4 + j] += d[j] * h; ab[i * 4 + j] += d[j]; }
+        const float gg = d[j] * gm[i * 4 + j];
+        g[i * 4 + j] = gg;
+        s1 += gg;
+        s2 += gg * h;
       }
-    s1 = warp_sum(s1) / c;
-    s2 = warp_sum(s2) / c;
+    }
+    s1 = warp_sum(s1) * (1.f / c);
+    s2 = warp_sum(s2) * (1.f / c);
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) {
-        const int col = (i * 32 + lane) * 4;
-        float o[4];
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = rs * (g[i * 4 + j] - s1 - xh[i * 4 + j] * s2);
-        if (dres1) {
-          float4 t = *(const float4*)(dres1 + row * (int64_t)c + col);
-          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-        }
-        if (dres2) {
-          float4 t = *(const float4*)(dres2 + row * (int64_t)c + col);
-          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-        }
-        if (dx) *(float4*)(dx + row * (int64_t)c + col) = make_float4(o[0], o[1], o[2], o[3]);
-        if (dx_act) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) store_from_f32(dx_act, act_dtype, row * ld_act + col + j, o[j], ld_act / 2);
-        }
+      for (int j = 0; j < 4; ++j) o[j] = rs * (g[i * 4 + j] - s1 - xh[i * 4 + j] * s2);
+      if (dres1) {
+        const float4 t = *(const float4*)(dres1 + row * (int64_t)c + col);
+        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
       }
+      if (dres2) {
+        const float4 t = *(const float4*)(dres2 + row * (int64_t)c + col);
+        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+      }
+      if (dx) *(float4*)(dx + row * (int64_t)c + col) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dx_act) store4_act(dx_act, act_dtype, row * ld_act + col, ld_act / 2, o);
+    }
   }
-  if (want_wg) {
+  if (WG) {
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i)
-      if (i < nv) {
-        const int col = (i * 32 + lane) * 4;
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          atomicAdd(&sg[col + j], ag[i * 4 + j]);
-          atomicAdd(&sb[col + j], ab[i * 4 + j]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sg[col + j], ag[i * 4 + j]);
+        atomicAdd(&sb[col + j], ab[i * 4 + j]);
       }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
       atomicAdd(dgamma + i, sg[i]);
@@ -346,8 +367,14 @@ extern "C" int svl_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, con
   if (rows == 0) return SVL_OK;
   int grid = grid_for_rows(rows);
   if (dgamma && grid > 296) grid = 296;     // fewer, longer-lived blocks: cheaper dgamma/dbeta reduction
-  layernorm_bwd_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, dy_dtype, lddy, x, ldx, gamma, mean, rstd, dres1, dres2, dx,
-                                                                               dx_act, act_dtype, ld_act, dgamma, dbeta, rows, c);
+  SVL_CHECK_ARG(c == 768 || c == 256, "svl_layernorm_bwd: rows of %d elements are not instantiated (768: ViT, 256: class attention)", c);
+  SVL_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "svl_layernorm_bwd: dgamma and dbeta go together");
+#define SVL_LN_BWD(NV, WG)                                                                                                                       \
+  layernorm_bwd_kernel<NV, WG><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, dy_dtype, lddy, x, ldx, gamma, mean, rstd, dres1, dres2, \
+                                                                                        dx, dx_act, act_dtype, ld_act, dgamma, dbeta, rows)
+  if (c == 768) { if (dgamma) SVL_LN_BWD(6, true); else SVL_LN_BWD(6, false); }
+  else { if (dgamma) SVL_LN_BWD(2, true); else SVL_LN_BWD(2, false); }
+#undef SVL_LN_BWD
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

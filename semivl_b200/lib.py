@@ -80,7 +80,7 @@ _PROTOS = {
     "svl_batch_sum": [_P, _P, _I, _L, _I, _P],
     "svl_axpy": [_P, _P, _F, _L, _P],
     "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _L, _I, _I, _I, _F, _P],
-    "svl_gn_relu_bwd": [_P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _P, _L, _I, _I, _I, _P],
+    "svl_gn_relu_bwd": [_P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P],
     "svl_sim_im2col": [_P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "svl_sim_col2im": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "svl_map_sum": [_P, _I, _L, _P, _L, _I, _I, _F, _P],

@@ -2,6 +2,8 @@
 // similarity maps and its transpose, global-average pooling, the class-token pooling / un-pooling around the
 // SemanticTransformer, the skip-feature upsample + concat and its gradient, and the 32->1 output conv.
 // Activations are NHWC; a "map" is one (image, class) pair, maps are ordered (image, class).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace svl {
@@ -72,38 +74,39 @@ __global__ void gn_finalize_kernel(float* __restrict__ mean, float* __restrict__
   mean[i] = mu;
   rstd[i] = rsqrtf(var + eps);
 }
-__global__ void __launch_bounds__(kGnThreads)
+// apply: one thread = the 16 channels of one (pixel, group) -- every GroupNorm of the head has 16 channels per group -- i.e. two
+// 16-byte vectors in flight per thread at ~40 registers, flat grid-stride indexing for full occupancy.
+__global__ void __launch_bounds__(256, 6)
 gn_apply_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                 void* __restrict__ out, int out_dtype, int64_t ldo, const void* __restrict__ res, int res_dtype, int64_t ldres,
-                const float* __restrict__ mean, const float* __restrict__ rstd, int hw, int C, int G, int splits) {
-  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
-  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;
-  int p0, p1;
-  gn_range(hw, splits, split, p0, p1);
-  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
-  const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
-  float ga[8], be[8];
+                const float* __restrict__ mean, const float* __restrict__ rstd, int64_t maps, int hw, int C, int G) {
+  const int64_t total = maps * hw * G;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const int64_t pix = idx / G;                 // global pixel index (map * hw + p)
+    const int64_t map = pix / hw;
+    const int c0 = g * 16;
+    float f[16];
+    ld8(x, x_dtype, pix * ldx + c0, ldx / 2, 8, f);
+    ld8(x, x_dtype, pix * ldx + c0 + 8, ldx / 2, 8, f + 8);
+    const float mu = __ldg(mean + map * G + g), rs = __ldg(rstd + map * G + g);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i] * rs; be[i] = beta[c8 + i] - mu * ga[i]; }
-  const int64_t xbase = (int64_t)map * hw * ldx + c8, obase = (int64_t)map * hw * ldo + c8, rbase = (int64_t)map * hw * ldres + c8;
-  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 4 * ppi) {
-    float f[4][8], r[4][8];
+    for (int j = 0; j < 4; ++j) {
+      const float4 ga = __ldg((const float4*)(gamma + c0) + j), be = __ldg((const float4*)(beta + c0) + j);
+      f[4 * j] = fmaxf((f[4 * j] - mu) * rs * ga.x + be.x, 0.f);
+      f[4 * j + 1] = fmaxf((f[4 * j + 1] - mu) * rs * ga.y + be.y, 0.f);
+      f[4 * j + 2] = fmaxf((f[4 * j + 2] - mu) * rs * ga.z + be.z, 0.f);
+      f[4 * j + 3] = fmaxf((f[4 * j + 3] - mu) * rs * ga.w + be.w, 0.f);
+    }
+    if (res) {
+      float r[16];
+      ld8(res, res_dtype, pix * ldres + c0, ldres / 2, 8, r);
+      ld8(res, res_dtype, pix * ldres + c0 + 8, ldres / 2, 8, r + 8);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (pix + u * ppi < p1) {
-        ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, f[u]);
-        if (res) ld8(res, res_dtype, rbase + (int64_t)(pix + u * ppi) * ldres, ldres / 2, 8, r[u]);
-      }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (pix + u * ppi < p1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          f[u][i] = fmaxf(f[u][i] * ga[i] + be[i], 0.f);
-          if (res) f[u][i] += r[u][i];
-        }
-        st8(out, out_dtype, obase + (int64_t)(pix + u * ppi) * ldo, ldo / 2, 8, f[u]);
-      }
+      for (int i = 0; i < 16; ++i) f[i] += r[i];
+    }
+    st8(out, out_dtype, pix * ldo + c0, ldo / 2, 8, f);
+    st8(out, out_dtype, pix * ldo + c0 + 8, ldo / 2, 8, f + 8);
   }
 }
 
@@ -209,6 +212,9 @@ gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, con
 }
 
 inline int gn_splits(int64_t maps, int hw, int C) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("SVL_GN_SPLITS"); forced = e ? atoi(e) : 0; }
+  if (forced > 0) return forced;
   // aim for >= 4 CTAs per SM in total, at least ~8 pixel iterations per thread
   int64_t want = (148 * 4 + maps - 1) / maps;
   int64_t cap = (int64_t)hw * (C / 8) / (kGnThreads * 8);
@@ -608,8 +614,9 @@ extern "C" int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const fl
   SVL_LAUNCH_CHECK();
   gn_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(mean, rstd, maps * G, (float)hw * (C / G), eps);
   SVL_LAUNCH_CHECK();
-  gn_apply_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean,
-                                                                   rstd, hw, C, G, splits);
+  SVL_CHECK_ARG(C / G == 16, "svl_gn_relu_fwd: the apply kernel is specialised for 16 channels per group");
+  gn_apply_kernel<<<ew_grid(maps * hw * G, 256), 256, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean, rstd, maps,
+                                                              hw, C, G);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

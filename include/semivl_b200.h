@@ -201,6 +201,8 @@ int svl_unpool_bwd(const void* dout, int dtype, int64_t ld, float* dtok, int64_t
  * gradient w.r.t. the pre-ReLU skip projection. */
 int svl_skip_fill(const void* skip, int s_dtype, int64_t lds, void* cat, int c_dtype, int64_t ldc, int c0, int B, int N, int h, int w,
                   int Cs, int H2, int W2, void* stream);
+/* out[b, p, c] = sum_n x[(b, n), p, c0 + c] (f32): collapses the per-class copies (transpose of the repeat in vlg_head.py:129) */
+int svl_class_sum(const void* x, int dtype, int64_t ld, int c0, float* out, int B, int N, int64_t P, int Cs, void* stream);
 int svl_skip_grad(const void* dcat, int d_dtype, int64_t ldd, int c0, const void* skip, int s_dtype, int64_t lds, void* dskip,
                   int o_dtype, int64_t ldo, int B, int N, int h, int w, int Cs, int H2, int W2, void* stream);
 /* output conv 3x3, C -> 1 (vlg_head.py:190,239-240); wgt/dw layout [9][C] */

@@ -9,6 +9,8 @@
 // loop of tile i+1.  Tile = 128 output rows x block_n columns, K step 64 (one 128-byte swizzle row).
 // In conv mode the 128 rows of a tile are a (bn images x bh rows x bw columns) box of an NHWC tensor, fetched with a
 // 4-D tensor map; a filter tap only shifts the box coordinates and TMA's out-of-bounds zero fill is the padding.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma.h"
@@ -42,6 +44,11 @@ struct GemmParams {
   const void* dact_src; int dact_dtype; int dact_kind; int64_t ld_dact;
   const void* residual; int res_dtype; int64_t ldres;
   int accumulate;
+  // row-strip convolution mode (tile = 128 pixels of one image row, k_per_tap <= 64, one N tile): the taps of a filter row share one
+  // A strip of (128 + span) pixels, read by each tap at its own row offset; all tap weights stay resident in shared memory
+  int strip, ng;
+  int g_dy[8], g_dxmin[8], g_ntaps[8], g_tap[8][4];
+  uint32_t strip_bytes, b_tile_bytes;
 };
 
 // global row index of tile row r, or -1 when the row is padding
@@ -73,12 +80,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + p.stages * p.a_stage_bytes;
-  const uint32_t bar_base = smem_b + p.stages * p.b_stage_bytes;          // 8-byte aligned (stage sizes are multiples of 1024)
+  // strip mode: smem_b holds the resident weights of all taps (num_taps tiles), the A ring holds strips
+  const uint32_t bar_base = smem_b + (p.strip ? (uint32_t)p.num_taps * p.b_tile_bytes : p.stages * p.b_stage_bytes);   // 1024-aligned
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 4);
+  const uint32_t wbar = bar_base + 8u * (2 * kMaxStages + 4);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 5);
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,6 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_init(tfull_bar(s), 1);
       ptx::mbar_init(tempty_bar(s), 4 * kEpiGroups);
     }
+    ptx::mbar_init(wbar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -112,6 +122,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.strip) {
+        ptx::mbar_arrive_expect_tx(wbar, (uint32_t)p.num_taps * p.b_tile_bytes);
+        for (int t = 0; t < p.num_taps; ++t) ptx::tma_load_2d(smem_b + t * p.b_tile_bytes, &tmB, wbar, p.tap_b_col[t], p.tap_b_row[t]);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int cx = (tile % p.tiles_x) * p.bw, cy = (tile / p.tiles_x) % p.tiles_y, cn = tile / (p.tiles_x * p.tiles_y);
+          for (int g = 0; g < p.ng; ++g) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.strip_bytes);
+            ptx::tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA, full_bar(stage), p.tap_a_koff[0], cx + p.g_dxmin[g], cy + p.g_dy[g], cn);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
         const int n0 = n_tile * p.block_n;
@@ -144,6 +167,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      if (p.strip) {
+        // The lone issuing thread pays every instruction's latency: all descriptor arithmetic is hoisted into registers
+        // (A descriptors relative to the stage base, B descriptors absolute: the weights are resident), loops fully unrolled.
+        const int nk = p.k_per_tap / 16;
+        const uint64_t tmpl = ptx::make_smem_desc(0, 16, 1024);
+        uint64_t aoff[4][4], bdesc[4][4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool on = g < p.ng && j < p.g_ntaps[g];
+            const int t = on ? p.g_tap[g][j] : 0;
+            aoff[g][j] = (uint64_t)(((uint32_t)(p.tap_dx[t] - (on ? p.g_dxmin[g] : p.tap_dx[t])) * 128u) >> 4);
+            bdesc[g][j] = tmpl + (uint64_t)((smem_b + t * p.b_tile_bytes) >> 4);
+          }
+        }
+        ptx::mbar_wait(wbar, 0);
+        ptx::tc_fence_after();
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+          uint32_t accum = 0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < p.ng) {
+              ptx::mbar_wait(full_bar(stage), phase);
+              ptx::tc_fence_after();
+              const uint64_t abase = tmpl + (uint64_t)((smem_a + stage * p.a_stage_bytes) >> 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < p.g_ntaps[g]) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    if (kk < nk) {
+                      ptx::umma_bf16(tmem_d, abase + aoff[g][j] + (uint64_t)(kk * 2), bdesc[g][j] + (uint64_t)(kk * 2), idesc, accum);
+                      accum = 1;
+                    }
+                  }
+                }
+              }
+              ptx::umma_commit(empty_bar(stage));
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          ptx::umma_commit(tfull_bar(as));
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
@@ -411,6 +483,41 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     uint64_t dims[4] = {(uint64_t)a_cols, mw, (uint64_t)d->h, (uint64_t)d->nb};
     uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * mw, (uint64_t)d->lda * 2 * mw * d->h};
     uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    // ---- row-strip mode?
+    static int strip_enabled = -1;
+    if (strip_enabled < 0) { const char* e = getenv("SVL_CONV_STRIP"); strip_enabled = e ? atoi(e) : 1; }
+    bool strip = strip_enabled && d->a_map_w == 0 && p.bw == BM && p.bh == 1 && p.bn == 1 && d->k_per_tap <= BK && p.num_n_tiles == 1 &&
+                 d->num_taps >= 2 && (size_t)d->num_taps * p.block_n * 128 <= 100 * 1024;
+    int span = 0;
+    if (strip) {
+      for (int t = 0; t < d->num_taps && strip; ++t) {
+        if (d->tap_a_koff[t] != d->tap_a_koff[0]) { strip = false; break; }
+        int g = -1;
+        for (int k = 0; k < p.ng; ++k) if (p.g_dy[k] == d->tap_dy[t]) g = k;
+        if (g < 0) {
+          if (p.ng == 4) { strip = false; break; }
+          g = p.ng++;
+          p.g_dy[g] = d->tap_dy[t];
+          p.g_dxmin[g] = d->tap_dx[t];
+        }
+        if (p.g_ntaps[g] == 4) { strip = false; break; }
+        p.g_tap[g][p.g_ntaps[g]++] = t;
+        if (d->tap_dx[t] < p.g_dxmin[g]) p.g_dxmin[g] = d->tap_dx[t];
+      }
+      for (int g = 0; g < p.ng && strip; ++g)
+        for (int j = 0; j < p.g_ntaps[g]; ++j) {
+          int sh = d->tap_dx[p.g_tap[g][j]] - p.g_dxmin[g];
+          span = span > sh ? span : sh;
+        }
+      if (BM + span > 256) strip = false;
+    }
+    if (strip) {
+      p.strip = 1;
+      p.strip_bytes = (uint32_t)(BM + span) * 128u;
+      box[1] = (uint32_t)(BM + span);
+    } else {
+      p.ng = 0;
+    }
     if (int rc = tma_encode_bf16(&tmA, d->a, 4, dims, strides, box)) return rc;
   } else {
     int64_t mt = (d->m + BM - 1) / BM;
@@ -430,8 +537,19 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   }
   p.a_stage_bytes = BM * 128u;
   p.b_stage_bytes = (uint32_t)p.block_n * 128u;      // block_n % 16 == 0 -> multiple of 2048, keeps every stage 1024-aligned
-  p.stages = (int)(kSmemBudget / (p.a_stage_bytes + p.b_stage_bytes));
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.b_tile_bytes = p.b_stage_bytes;
+  size_t smem_data;
+  if (p.strip) {
+    p.a_stage_bytes = (p.strip_bytes + 1023u) & ~1023u;
+    const size_t wbytes = (size_t)p.num_taps * p.b_tile_bytes;
+    p.stages = (int)((kSmemBudget - wbytes) / p.a_stage_bytes);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    smem_data = (size_t)p.stages * p.a_stage_bytes + wbytes;
+  } else {
+    p.stages = (int)(kSmemBudget / (p.a_stage_bytes + p.b_stage_bytes));
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    smem_data = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes);
+  }
   p.tmem_cols = pow2ceil(2 * p.block_n < 32 ? 32 : 2 * p.block_n);
 
   p.out = d->out; p.out_dtype = d->out_dtype; p.ldc = d->ldc; p.out_mode = d->out_mode; p.out_h = d->out_h; p.out_w = d->out_w;
@@ -442,7 +560,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.ldres = d->ldres;
   p.accumulate = d->accumulate;
 
-  const size_t smem = 1024 + (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 8 * (2 * kMaxStages + 4) + 16;
+  const size_t smem = 1024 + smem_data + 8 * (2 * kMaxStages + 5) + 16;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   const bool plain = !p.row_bias && !p.accumulate && p.out_mode == SVL_OUT_LINEAR;

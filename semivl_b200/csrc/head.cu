@@ -392,19 +392,26 @@ __global__ void unpool_bwd_kernel(const void* __restrict__ dout, int dtype, int6
     dtok[idx] = s;
   }
 }
-// dx[(b,n), y, x, c] (+)= dtok[(b, y/pool, x/pool), n, c] / pool^2  for y < hp*pool, x < wp*pool        (f32 dx)
+// dx[(b,n), y, x, c] (+)= dtok[(b, y/pool, x/pool), n, c] / pool^2  for y < hp*pool, x < wp*pool        (f32 dx, float4 per thread)
 __global__ void pool_tokens_bwd_kernel(const float* __restrict__ dtok, int64_t ldt, float* __restrict__ dx, int B, int N, int h, int w, int C,
                                        int pool) {
   const int hp = h / pool, wp = w / pool;
-  const int64_t total = (int64_t)B * N * h * w * C;
+  const int c4 = C / 4;
+  const int64_t total = (int64_t)B * N * h * w * c4;
   const float inv = 1.f / (pool * pool);
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    int64_t pix = idx / C;
+    const int c = (int)(idx % c4) * 4;
+    int64_t pix = idx / c4;
     const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
     const int n = (int)((pix / ((int64_t)w * h)) % N), b = (int)(pix / ((int64_t)w * h * N));
     const int py = yy / pool, px = xx / pool;
-    if (py < hp && px < wp) dx[idx] += inv * dtok[((((int64_t)b * hp + py) * wp + px) * N + n) * ldt + c];
+    if (py < hp && px < wp) {
+      const float4 t = *(const float4*)(dtok + ((((int64_t)b * hp + py) * wp + px) * N + n) * ldt + c);
+      float4* d = (float4*)(dx + pix * C + c);
+      float4 v = *d;
+      v.x += inv * t.x; v.y += inv * t.y; v.z += inv * t.z; v.w += inv * t.w;
+      *d = v;
+    }
   }
 }
 
@@ -428,37 +435,66 @@ __global__ void skip_fill_kernel(const void* __restrict__ skip, int s_dtype, int
       store_from_f32(cat, c_dtype, ((((int64_t)b * N + n) * H2 + Y) * W2 + X) * ldc + c0 + c, v, ldc / 2);
   }
 }
-// dskip_pre[b, y, x, c] = relu'(skip) * sum_n sum_{Y,X} W(Y,y) W(X,x) dcat[(b,n), Y, X, c0 + c]
+// out[b, p, c] = sum_n x[(b, n), p, c0 + c]   (f32 out; the per-class copies of the skip channels collapse back onto the image:
+// transpose of the `repeat` in vlg_head.py:129).  One thread per (b, pixel, 8 channels): N coalesced 16-byte loads.
+__global__ void class_sum_kernel(const void* __restrict__ x, int dtype, int64_t ld, int c0, float* __restrict__ out, int B, int N, int64_t P, int Cs) {
+  const int c8n = Cs / 8;
+  const int64_t total = (int64_t)B * P * c8n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c8n) * 8;
+    const int64_t pix = (idx / c8n) % P, b = idx / (c8n * P);
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    for (int n = 0; n < N; ++n) {
+      float f[8];
+      ld8(x, dtype, (((int64_t)b * N + n) * P + pix) * ld + c0 + c, ld / 2, 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+    st8(out, SVL_F32, ((int64_t)b * P + pix) * Cs + c, 0, 8, s);
+  }
+}
+
+// dskip_pre[b, y, x, c] = relu'(skip) * sum_n sum_{Y,X} W(Y,y) W(X,x) dcat[(b,n), Y, X, c0 + c]      (8 channels per thread)
 __global__ void skip_grad_kernel(const void* __restrict__ dcat, int d_dtype, int64_t ldd, int c0, const void* __restrict__ skip, int s_dtype,
                                  int64_t lds, void* __restrict__ dskip, int o_dtype, int64_t ldo, int B, int N, int h, int w, int Cs, int H2,
                                  int W2) {
-  const int64_t total = (int64_t)B * h * w * Cs;
+  const int c8n = Cs / 8;
+  const int64_t total = (int64_t)B * h * w * c8n;
   const float sy = h > 1 && H2 > 1 ? (float)(h - 1) / (H2 - 1) : 0.f, sx = w > 1 && W2 > 1 ? (float)(w - 1) / (W2 - 1) : 0.f;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % Cs);
-    int64_t pix = idx / Cs;
+    const int c = (int)(idx % c8n) * 8;
+    int64_t pix = idx / c8n;
     const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
-    float s = 0.f;
-    if (load_as_f32(skip, s_dtype, pix * lds + c, lds / 2) > 0.f) {
-      const int Ylo = sy > 0.f ? max(0, (int)ceilf((y - 1) / sy)) : 0, Yhi = sy > 0.f ? min(H2 - 1, (int)floorf((y + 1) / sy)) : H2 - 1;
-      const int Xlo = sx > 0.f ? max(0, (int)ceilf((x - 1) / sx)) : 0, Xhi = sx > 0.f ? min(W2 - 1, (int)floorf((x + 1) / sx)) : W2 - 1;
-      for (int Y = Ylo; Y <= Yhi; ++Y) {
-        int y0, y1; float wy;
-        bilin_src(Y, sy, h, y0, y1, wy);
-        const float ay = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
-        if (ay == 0.f) continue;
-        for (int X = Xlo; X <= Xhi; ++X) {
-          int x0, x1; float wx;
-          bilin_src(X, sx, w, x0, x1, wx);
-          const float ax = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
-          if (ax == 0.f) continue;
-          float t = 0.f;
-          for (int n = 0; n < N; ++n) t += load_as_f32(dcat, d_dtype, ((((int64_t)b * N + n) * H2 + Y) * W2 + X) * ldd + c0 + c, ldd / 2);
-          s += ay * ax * t;
+    float s[8], sk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    ld8(skip, s_dtype, pix * lds + c, lds / 2, 8, sk);
+    const int Ylo = sy > 0.f ? max(0, (int)ceilf((y - 1) / sy)) : 0, Yhi = sy > 0.f ? min(H2 - 1, (int)floorf((y + 1) / sy)) : H2 - 1;
+    const int Xlo = sx > 0.f ? max(0, (int)ceilf((x - 1) / sx)) : 0, Xhi = sx > 0.f ? min(W2 - 1, (int)floorf((x + 1) / sx)) : W2 - 1;
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+      int y0, y1; float wy;
+      bilin_src(Y, sy, h, y0, y1, wy);
+      const float ay = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
+      if (ay == 0.f) continue;
+      for (int X = Xlo; X <= Xhi; ++X) {
+        int x0, x1; float wx;
+        bilin_src(X, sx, w, x0, x1, wx);
+        const float ax = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
+        if (ax == 0.f) continue;
+        const float wgt = ay * ax;
+        for (int n = 0; n < N; ++n) {
+          float f[8];
+          ld8(dcat, d_dtype, ((((int64_t)b * N + n) * H2 + Y) * W2 + X) * ldd + c0 + c, ldd / 2, 8, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += wgt * f[i];
         }
       }
     }
-    store_from_f32(dskip, o_dtype, pix * ldo + c, s, ldo / 2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = sk[i] > 0.f ? s[i] : 0.f;
+    st8(dskip, o_dtype, pix * ldo + c, ldo / 2, 8, s);
   }
 }
 
@@ -534,42 +570,43 @@ __global__ void conv_out1_dgrad_kernel(const float* __restrict__ dout, const flo
   }
 }
 // dw[t*C + c] += sum_q x[q, c] * dout[q - tap_t];  dbias += sum dout
-// lane = channel (32 channels per pass): ONE 64-byte x row per pixel and the 9 neighbouring dout scalars (broadcast loads);
-// 4 pixels in flight per warp; block reduction through shared memory, then 9*C atomics per block.
+// Persistent CTAs over 8 x 32 pixel tiles: the (8+2) x (32+2) dout halo goes to shared memory, a warp walks the tile's pixels with
+// lane = channel (one 64-byte x row per pixel, 9 broadcast smem reads), 9 accumulators per lane live across all tiles of the CTA.
 __global__ void __launch_bounds__(256)
 conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ x, int dtype, int64_t ld, float* __restrict__ dw,
-                       float* __restrict__ dbias, int64_t maps, int h, int w, int C) {
+                       float* __restrict__ dbias, int h, int w, int C, int tiles_x, int tiles_y, int64_t num_tiles) {
+  __shared__ float s_d[kO1HW];
   __shared__ float red[8][9][33];
   __shared__ float redb[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t total = maps * h * w;
-  const int hw = h * w;
   for (int c0 = 0; c0 < C; c0 += 32) {
     const int c = c0 + lane;
     float acc[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
     float sb = 0.f;
-    const int64_t stride = (int64_t)gridDim.x * 8;
-    for (int64_t q0 = (int64_t)blockIdx.x * 8 + warp; q0 < total; q0 += 4 * stride) {
-      float xv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t q = q0 + u * stride;
-        xv[u] = (q < total && c < C) ? load_as_f32(x, dtype, q * ld + c, ld / 2) : 0.f;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+      const int64_t map = tile / ((int64_t)tiles_x * tiles_y);
+      const int x0 = tx * kO1TW - 1, y0 = ty * kO1TH - 1;
+      __syncthreads();
+      for (int i = threadIdx.x; i < kO1HW; i += blockDim.x) {
+        const int yy = y0 + i / (kO1TW + 2), xx = x0 + i % (kO1TW + 2);
+        s_d[i] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? dout[(map * h + yy) * w + xx] : 0.f;
       }
+      __syncthreads();
+      // warp `warp` takes tile row `warp`, 32 pixels
+      const int yy = ty * kO1TH + warp;
+      if (yy < h) {
+#pragma unroll 4
+        for (int lx = 0; lx < kO1TW; ++lx) {
+          const int xx = tx * kO1TW + lx;
+          if (xx >= w) break;
+          const float xv = c < C ? load_as_f32(x, dtype, ((map * h + yy) * w + xx) * ld + c, ld / 2) : 0.f;
+          // output pixel (yy - dy, xx - dx) reads this input pixel through tap (dy, dx): halo index (warp + 1 - dy, lx + 1 - dx)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t q = q0 + u * stride;
-        if (q >= total) break;
-        const int rem = (int)(q % hw);
-        const int yy = rem / w, xx = rem - yy * w;
-        if (c0 == 0) sb += dout[q];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int y2 = yy - (t / 3 - 1), x2 = xx - (t % 3 - 1);          // output pixel that reads q through tap t
-          if (y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
-          acc[t] += xv[u] * __ldg(dout + q - (int64_t)(t / 3 - 1) * w - (t % 3 - 1));
+          for (int t = 0; t < 9; ++t) acc[t] += xv * s_d[(warp + 1 - (t / 3 - 1)) * (kO1TW + 2) + lx + 1 - (t % 3 - 1)];
+          if (c0 == 0) sb += s_d[(warp + 1) * (kO1TW + 2) + lx + 1];
         }
       }
     }
@@ -680,7 +717,8 @@ extern "C" int svl_pool_tokens(const void* x, int x_dtype, int64_t ldx, const fl
 }
 extern "C" int svl_pool_tokens_bwd(const float* dtok, int64_t ldt, float* dx, int B, int N, int h, int w, int C, int pool, void* stream) {
   SVL_CHECK_ARG(dtok && dx, "svl_pool_tokens_bwd: null pointer");
-  pool_tokens_bwd_kernel<<<ew_grid((int64_t)B * N * h * w * C), 256, 0, ST>>>(dtok, ldt, dx, B, N, h, w, C, pool);
+  SVL_CHECK_ARG(C % 4 == 0 && ldt % 4 == 0, "svl_pool_tokens_bwd: C and ldt must be multiples of 4");
+  pool_tokens_bwd_kernel<<<ew_grid((int64_t)B * N * h * w * (C / 4)), 256, 0, ST>>>(dtok, ldt, dx, B, N, h, w, C, pool);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
@@ -706,11 +744,19 @@ extern "C" int svl_skip_fill(const void* skip, int s_dtype, int64_t lds, void* c
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
+extern "C" int svl_class_sum(const void* x, int dtype, int64_t ld, int c0, float* out, int B, int N, int64_t P, int Cs, void* stream) {
+  SVL_CHECK_ARG(x && out && Cs % 8 == 0, "svl_class_sum: bad arguments");
+  class_sum_kernel<<<ew_grid((int64_t)B * P * (Cs / 8)), 256, 0, ST>>>(x, dtype, ld, c0, out, B, N, P, Cs);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
 extern "C" int svl_skip_grad(const void* dcat, int d_dtype, int64_t ldd, int c0, const void* skip, int s_dtype, int64_t lds, void* dskip,
                              int o_dtype, int64_t ldo, int B, int N, int h, int w, int Cs, int H2, int W2, void* stream) {
   SVL_CHECK_ARG(dcat && skip && dskip, "svl_skip_grad: null pointer");
-  skip_grad_kernel<<<ew_grid((int64_t)B * h * w * Cs, 128), 128, 0, ST>>>(dcat, d_dtype, ldd, c0, skip, s_dtype, lds, dskip, o_dtype, ldo, B, N, h, w,
-                                                                         Cs, H2, W2);
+  SVL_CHECK_ARG(Cs % 8 == 0, "svl_skip_grad: Cs must be a multiple of 8");
+  skip_grad_kernel<<<ew_grid((int64_t)B * h * w * (Cs / 8), 128), 128, 0, ST>>>(dcat, d_dtype, ldd, c0, skip, s_dtype, lds, dskip, o_dtype, ldo, B, N, h,
+                                                                               w, Cs, H2, W2);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
@@ -730,9 +776,10 @@ extern "C" int svl_conv_out1_bwd(const float* dout, const void* x, int x_dtype, 
   SVL_CHECK_ARG(dout && x && wgt && dx && dw && dbias && C % 8 == 0 && 9 * C <= 1024, "svl_conv_out1_bwd: bad arguments");
   conv_out1_dgrad_kernel<<<ew_grid(maps * h * w * (C / 8)), 256, 9 * C * sizeof(float), ST>>>(dout, wgt, dx, dx_dtype, lddx, maps, h, w, C);
   SVL_LAUNCH_CHECK();
-  int64_t total = maps * h * w;
-  int grid = (int)(total / 64 > 0 ? (total / 64 < 148 * 8 ? total / 64 : 148 * 8) : 1);
-  conv_out1_wgrad_kernel<<<grid, 256, 0, ST>>>(dout, x, x_dtype, ldx, dw, dbias, maps, h, w, C);
+  const int tiles_x = (w + kO1TW - 1) / kO1TW, tiles_y = (h + kO1TH - 1) / kO1TH;
+  const int64_t num_tiles = maps * tiles_x * tiles_y;
+  const int grid = (int)(num_tiles < 148 * 4 ? num_tiles : 148 * 4);
+  conv_out1_wgrad_kernel<<<grid, 256, 0, ST>>>(dout, x, x_dtype, ldx, dw, dbias, h, w, C, tiles_x, tiles_y, num_tiles);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

@@ -173,8 +173,20 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, co
   }
   for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
     const float mu = mean[row], rs = rstd[row];
-    float xh[NV * 4], g[NV * 4];
+    float xh[NV * 4], g[NV * 4], rsd[NV * 4];
     float s1 = 0.f, s2 = 0.f;
+    // all of the row's global loads are issued before the first reduction (memory-level parallelism, not occupancy, feeds HBM here)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dres1) t = *(const float4*)(dres1 + row * (int64_t)c + col);
+      if (dres2) {
+        const float4 u = *(const float4*)(dres2 + row * (int64_t)c + col);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      rsd[i * 4] = t.x; rsd[i * 4 + 1] = t.y; rsd[i * 4 + 2] = t.z; rsd[i * 4 + 3] = t.w;
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = (i * 32 + lane) * 4;
@@ -200,15 +212,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, co
       const int col = (i * 32 + lane) * 4;
       float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = rs * (g[i * 4 + j] - s1 - xh[i * 4 + j] * s2);
-      if (dres1) {
-        const float4 t = *(const float4*)(dres1 + row * (int64_t)c + col);
-        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-      }
-      if (dres2) {
-        const float4 t = *(const float4*)(dres2 + row * (int64_t)c + col);
-        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-      }
+      for (int j = 0; j < 4; ++j) o[j] = rs * (g[i * 4 + j] - s1 - xh[i * 4 + j] * s2) + rsd[i * 4 + j];
       if (dx) *(float4*)(dx + row * (int64_t)c + col) = make_float4(o[0], o[1], o[2], o[3]);
       if (dx_act) store4_act(dx_act, act_dtype, row * ld_act + col, ld_act / 2, o);
     }
@@ -289,20 +293,34 @@ __global__ void cast_kernel(const void* __restrict__ src, int src_dtype, int64_t
   }
 }
 
-// out[col] (+)= sum_rows x[row, col]; grid (col tiles of 32, row splits); block 32 x 8
-__global__ void colsum_kernel(const void* __restrict__ x, int x_dtype, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int col = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (col < cols)
-    for (int64_t r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) s += load_as_f32(x, x_dtype, r * ld + col, ld / 2);
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && col < cols) {
-    float t = 0.f;
+// out[col] += sum_rows x[row, col]; a thread owns 8 consecutive columns (one 16-byte load per row), blockDim = (32 column groups, 8 row lanes),
+// grid = (column tiles of 256, row splits); block partials through shared memory, one atomic per column per block
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x, int x_dtype, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][257];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int cnt = min(8, cols - col);
+  float s[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    atomicAdd(out + col, t);
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (cnt > 0) {
+    for (int64_t r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
+      float f[8];
+      ld8(x, x_dtype, r * ld + col, ld / 2, cnt, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x * 8 + i] = s[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;            // 0..255: one column of the tile each
+  const int c = blockIdx.x * 256 + t;
+  if (c < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][t];
+    atomicAdd(out + c, v);
   }
 }
 
@@ -411,9 +429,11 @@ extern "C" int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t 
 extern "C" int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
   SVL_CHECK_ARG(x && out, "svl_colsum: null pointer");
   if (rows == 0 || cols == 0) return SVL_OK;
-  int64_t ysplit = cdiv(rows, 8 * 64);
-  if (ysplit > 256) ysplit = 256;
-  dim3 grid((cols + 31) / 32, (unsigned)ysplit);
+  const int xt = (cols + 255) / 256;
+  int64_t ysplit = cdiv(rows, 8 * 16);
+  const int64_t cap = (148 * 8 + xt - 1) / xt;
+  if (ysplit > cap) ysplit = cap;
+  dim3 grid(xt, (unsigned)ysplit);
   colsum_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, x_dtype, ld, rows, cols, out);
   SVL_LAUNCH_CHECK();
   return SVL_OK;

@@ -202,7 +202,9 @@ class HeadEngine:
         # skip branch: gradient w.r.t. the pre-ReLU skip projection
         sh, sw = S["skip_hw"]
         d_skip = ops.new_act(B * sh * sw, cs, pr, dev)
-        L.call("svl_skip_grad", d_cat, adt, ldp, cup, S["skip"], L.F32, cs, d_skip, adt, d_skip.shape[-1], B, N, sh, sw, cs, H2, W2)
+        d_sum = torch.empty(B, H2 * W2, cs, device=dev, dtype=torch.float32)            # sum over the N per-class copies first ...
+        L.call("svl_class_sum", d_cat, adt, ldp, cup, d_sum, B, N, H2 * W2, cs)
+        L.call("svl_skip_grad", d_sum, L.F32, cs, 0, S["skip"], L.F32, cs, d_skip, adt, d_skip.shape[-1], B, 1, sh, sw, cs, H2, W2)   # ... then resize^T
         # transposed conv: bias, weight and data gradients; d_cat is read as [nb, h, 2w', 2*ldp] (pixel (2y+qy, 2x+qx) -> x' = qy*w + x, column block qx)
         ops.colsum(d_cat, adt, nb * H2 * W2, cup, grads[name + "up.bias"], ld=ldp)
         taps_w = [(0, qy * w, 0, qx * ldp, qy * 2 + qx) for qy in range(2) for qx in range(2)]

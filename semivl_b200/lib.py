@@ -90,6 +90,7 @@ _PROTOS = {
     "svl_unpool_add": [_P, _I, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_unpool_bwd": [_P, _I, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_skip_fill": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_class_sum": [_P, _I, _L, _I, _P, _I, _I, _L, _I, _P],
     "svl_skip_grad": [_P, _I, _L, _I, _P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_conv_out1_fwd": [_P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P],
     "svl_conv_out1_bwd": [_P, _P, _I, _L, _P, _P, _I, _L, _P, _P, _L, _I, _I, _I, _P],

@@ -110,8 +110,9 @@ gn_apply_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const floa
   }
 }
 
-// backward: stats (s1 = sum g, s2 = sum g*xhat per (map, group), dgamma/dbeta) then apply  dx = rstd * (g - s1/n - xhat * s2/n)
-__global__ void __launch_bounds__(kGnThreads)
+// backward: stats (s1 = sum g, s2 = sum g*xhat per (map, group), dgamma/dbeta) then apply  dx = rstd * (g - s1/n - xhat * s2/n).
+// One thread = the 16 channels of one (pixel, group): four 16-byte loads (x, dy) in flight per thread, raw bf16 kept packed.
+__global__ void __launch_bounds__(kGnThreads, 3)
 gn_bwd_stats_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const void* __restrict__ x, int x_dtype, int64_t ldx,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ rstd, float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int hw,
@@ -119,48 +120,41 @@ gn_bwd_stats_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, con
   __shared__ float s_s1[kMaxGroups], s_s2[kMaxGroups];
   __shared__ float s_dg[256], s_db[256];
   const int map = blockIdx.x / splits, split = blockIdx.x % splits;
-  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;
+  const int ppi = kGnThreads / G;                     // pixels per iteration
   if (threadIdx.x < kMaxGroups) s_s1[threadIdx.x] = s_s2[threadIdx.x] = 0.f;
   s_dg[threadIdx.x] = s_db[threadIdx.x] = 0.f;
   __syncthreads();
   int p0, p1;
   gn_range(hw, splits, split, p0, p1);
-  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
+  const int g = threadIdx.x % G, c0 = g * 16;
   const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
-  float ga[8], be[8];
+  const int64_t xbase = (int64_t)map * hw * ldx + c0, ybase = (int64_t)map * hw * lddy + c0;
+  float s1 = 0.f, s2 = 0.f, dg[16], db[16];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i]; be[i] = beta[c8 + i]; }
-  const int64_t xbase = (int64_t)map * hw * ldx + c8, ybase = (int64_t)map * hw * lddy + c8;
-  float s1 = 0.f, s2 = 0.f, dg[8], db[8];
+  for (int i = 0; i < 16; ++i) dg[i] = db[i] = 0.f;
+#pragma unroll 1
+  for (int pix = p0 + threadIdx.x / G; pix < p1; pix += ppi) {
+    float xv[16], d[16];
+    ld8(x, x_dtype, xbase + (int64_t)pix * ldx, ldx / 2, 8, xv);
+    ld8(x, x_dtype, xbase + (int64_t)pix * ldx + 8, ldx / 2, 8, xv + 8);
+    ld8(dy, dy_dtype, ybase + (int64_t)pix * lddy, lddy / 2, 8, d);
+    ld8(dy, dy_dtype, ybase + (int64_t)pix * lddy + 8, lddy / 2, 8, d + 8);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
-  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 2 * ppi) {
-    float xv[2][8], d[2][8];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (pix + u * ppi < p1) {
-        ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, xv[u]);
-        ld8(dy, dy_dtype, ybase + (int64_t)(pix + u * ppi) * lddy, lddy / 2, 8, d[u]);
-      }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (pix + u * ppi < p1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (xv[u][i] - mu) * rs;
-          const float dd = (xh * ga[i] + be[i] > 0.f) ? d[u][i] : 0.f;
-          dg[i] += dd * xh;
-          db[i] += dd;
-          const float gg = dd * ga[i];
-          s1 += gg;
-          s2 += gg * xh;
-        }
-      }
+    for (int i = 0; i < 16; ++i) {
+      const float ga = __ldg(gamma + c0 + i), be = __ldg(beta + c0 + i);
+      const float xh = (xv[i] - mu) * rs;
+      const float dd = (xh * ga + be > 0.f) ? d[i] : 0.f;
+      dg[i] += dd * xh;
+      db[i] += dd;
+      const float gg = dd * ga;
+      s1 += gg;
+      s2 += gg * xh;
+    }
   }
   atomicAdd(&s_s1[g], s1);
   atomicAdd(&s_s2[g], s2);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { atomicAdd(&s_dg[c8 + i], dg[i]); atomicAdd(&s_db[c8 + i], db[i]); }
+  for (int i = 0; i < 16; ++i) { atomicAdd(&s_dg[c0 + i], dg[i]); atomicAdd(&s_db[c0 + i], db[i]); }
   __syncthreads();
   if (threadIdx.x < G) {
     atomicAdd(ws + ((int64_t)map * G + threadIdx.x) * 2, s_s1[threadIdx.x]);
@@ -171,43 +165,34 @@ gn_bwd_stats_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, con
     atomicAdd(dbeta + threadIdx.x, s_db[threadIdx.x]);
   }
 }
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(256, 4)
 gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, const void* __restrict__ x, int x_dtype, int64_t ldx,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ ws, void* __restrict__ dx, int dx_dtype, int64_t lddx, int hw, int C,
-                    int G, int splits) {
-  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
-  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;
-  int p0, p1;
-  gn_range(hw, splits, split, p0, p1);
-  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
-  const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
-  const float n = (float)hw * cpg;
-  const float m1 = ws[((int64_t)map * G + g) * 2] / n, m2 = ws[((int64_t)map * G + g) * 2 + 1] / n;
-  float ga[8], be[8];
+                    const float* __restrict__ rstd, const float* __restrict__ ws, void* __restrict__ dx, int dx_dtype, int64_t lddx, int64_t maps,
+                    int hw, int C, int G) {
+  const int64_t total = maps * hw * G;
+  const float n = (float)hw * 16.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const int64_t pix = idx / G;
+    const int64_t map = pix / hw;
+    const int c0 = g * 16;
+    float xv[16], d[16];
+    ld8(x, x_dtype, pix * ldx + c0, ldx / 2, 8, xv);
+    ld8(x, x_dtype, pix * ldx + c0 + 8, ldx / 2, 8, xv + 8);
+    ld8(dy, dy_dtype, pix * lddy + c0, lddy / 2, 8, d);
+    ld8(dy, dy_dtype, pix * lddy + c0 + 8, lddy / 2, 8, d + 8);
+    const float mu = __ldg(mean + map * G + g), rs = __ldg(rstd + map * G + g);
+    const float m1 = __ldg(ws + (map * G + g) * 2) / n, m2 = __ldg(ws + (map * G + g) * 2 + 1) / n;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c8 + i]; be[i] = beta[c8 + i]; }
-  const int64_t xbase = (int64_t)map * hw * ldx + c8, ybase = (int64_t)map * hw * lddy + c8, obase = (int64_t)map * hw * lddx + c8;
-  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 2 * ppi) {
-    float xv[2][8], d[2][8];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (pix + u * ppi < p1) {
-        ld8(x, x_dtype, xbase + (int64_t)(pix + u * ppi) * ldx, ldx / 2, 8, xv[u]);
-        ld8(dy, dy_dtype, ybase + (int64_t)(pix + u * ppi) * lddy, lddy / 2, 8, d[u]);
-      }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (pix + u * ppi < p1) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (xv[u][i] - mu) * rs;
-          const float dd = (xh * ga[i] + be[i] > 0.f) ? d[u][i] : 0.f;
-          o[i] = rs * (dd * ga[i] - m1 - xh * m2);
-        }
-        st8(dx, dx_dtype, obase + (int64_t)(pix + u * ppi) * lddx, lddx / 2, 8, o);
-      }
+    for (int i = 0; i < 16; ++i) {
+      const float ga = __ldg(gamma + c0 + i), be = __ldg(beta + c0 + i);
+      const float xh = (xv[i] - mu) * rs;
+      const float dd = (xh * ga + be > 0.f) ? d[i] : 0.f;
+      d[i] = rs * (dd * ga - m1 - xh * m2);
+    }
+    st8(dx, dx_dtype, pix * lddx + c0, lddx / 2, 8, d);
+    st8(dx, dx_dtype, pix * lddx + c0 + 8, lddx / 2, 8, d + 8);
   }
 }
 
@@ -662,6 +647,7 @@ extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const
                                const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int64_t lddx, float* dgamma,
                                float* dbeta, float* ws, int64_t maps, int hw, int C, int G, void* stream) {
   SVL_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && ws, "svl_gn_relu_bwd: null pointer");
+  SVL_CHECK_ARG(C / G == 16 && kGnThreads % G == 0, "svl_gn_relu_bwd: kernels are specialised for 16 channels per group");
   SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
                 "svl_gn_relu_bwd: unsupported C=%d G=%d", C, G);
   if (maps == 0) return SVL_OK;
@@ -671,8 +657,8 @@ extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const
   gn_bwd_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dgamma,
                                                                        dbeta, hw, C, G, splits);
   SVL_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dx, dx_dtype,
-                                                                       lddx, hw, C, G, splits);
+  gn_bwd_apply_kernel<<<ew_grid(maps * hw * G, 256), 256, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dx, dx_dtype, lddx,
+                                                                  maps, hw, C, G);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

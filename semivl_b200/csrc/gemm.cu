@@ -338,6 +338,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (n0 + c0 >= p.n) break;
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
+          // side inputs (act' source / residual) do not depend on the accumulator: their global loads are issued before the TMEM wait
+          float side[2][16];
+          if ((DACT == 1 || RES >= 0) && grow >= 0) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int col = n0 + c0 + g * 16;
+              const int cnt = min(16, p.n - col);
+              if (cnt > 0) {
+                if (DACT == 1) ld16(p.dact_src, SVL_BF16, grow * p.ld_dact + col, 0, cnt, side[g]);
+                else ld16(p.residual, RES, grow * p.ldres + col, 0, cnt, side[g]);
+              }
+            }
+          }
           ptx::tmem_ld_wait();
           if (grow < 0) continue;
 #pragma unroll
@@ -379,16 +392,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (DACT == 1) {
-              float sv[16];
-              ld16(p.dact_src, SVL_BF16, grow * p.ld_dact + col, 0, cnt, sv);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] *= gelu_grad_fast(sv[i]);
+              for (int i = 0; i < 16; ++i) f[i] *= gelu_grad_fast(side[g][i]);
             }
             if (RES >= 0) {
-              float sv[16];
-              ld16(p.residual, RES, grow * p.ldres + col, 0, cnt, sv);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] += sv[i];
+              for (int i = 0; i < 16; ++i) f[i] += side[g][i];
             }
             int64_t off = grow * p.ldc + col;
             if (EXT == 1) {                                  // cq % 16 == 0 is checked by the launcher for this variant

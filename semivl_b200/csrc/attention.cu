@@ -7,7 +7,10 @@
 // shared memory with cp.async, fp32 online softmax, bf16 mma.sync.m16n8k16 tensor-core products.
 // SPLIT = precise mode: operands are bf16 (hi | lo) pairs and every product is issued as hi*hi + hi*lo + lo*hi.
 // Backward is two kernels (dK/dV per key tile, dQ per query tile): no atomics, bitwise reproducible.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tma.h"
 
 namespace svl {
 namespace {
@@ -520,6 +523,12 @@ extern "C" int svl_attention_fwd(const void* qkv, int split, void* out, float* l
   SVL_CHECK_ARG(qkv && out && b > 0 && L > 0 && heads > 0, "svl_attention_fwd: bad arguments");
   const int E = heads * D;
   const int64_t ld = split ? 6 * E : 3 * E, ldo = split ? 2 * E : E;
+  static int tc_mode = -1;
+  if (tc_mode < 0) { const char* e = getenv("SVL_ATTN_TC"); tc_mode = e ? atoi(e) : 1; }
+  if (!split && tc_mode && L >= 64) {       // tcgen05 path (throughput mode); tiny sequences (class attention, L = #classes) stay on mma.sync
+    if (int rc = svl_check_device()) return rc;
+    return attention_fwd_tc(qkv, out, lse, b, L, heads, scale, (cudaStream_t)stream);
+  }
   dim3 grid((L + TQ - 1) / TQ, heads, b);
   const size_t smem = (size_t)(split ? 8 : 4) * kTileBytes;
   if (split) {

@@ -159,10 +159,11 @@ int svl_axpy(float* dst, const float* src, float alpha, int64_t n, void* stream)
  * Multi-head self-attention, head_dim 64 (nn.MultiheadAttention core, maskclip_vit.py:77-84,141; also the
  * class-attention of SemanticTransformer, vlg_head.py:39-67).  qkv packed [b, L, 3E] bf16 (q | k | v, heads contiguous
  * inside each third; split != 0: BF16X2 rows of 6E), out [b, L, E] (2E when split), lse [b, heads, L]; never materialises LxL.
- * Backward: delta_ws is a caller-provided [b, heads, L] f32 scratch; dv_add (optional, [b*L, E]) is added to dV before it is
+ * Backward: delta_ws is a caller-provided f32 scratch of svl_attention_bwd_workspace(split, b, L, heads) floats; dv_add (optional, [b*L, E]) is added to dV before it is
  * stored (the MaskCLIP v-path gradient, maskclip_vit.py:110-118); dqkv has the layout of qkv.
  * ---------------------------------------------------------------------------------------------- */
 int svl_attention_fwd(const void* qkv, int split, void* out, float* lse, int b, int L, int heads, float scale, void* stream);
+size_t svl_attention_bwd_workspace(int split, int b, int L, int heads);
 int svl_attention_bwd(const void* qkv, const void* out, const void* dout, int split, const float* lse, float* delta_ws,
                       const void* dv_add, int dv_add_dtype, int64_t ld_dv_add, void* dqkv, int b, int L, int heads, float scale,
                       void* stream);

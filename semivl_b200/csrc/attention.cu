@@ -519,13 +519,21 @@ int set_smem(K kernel, size_t bytes) {
 
 using namespace svl;
 
+static bool attention_uses_tc(int split, int L) {
+  static int tc_mode = -1;
+  if (tc_mode < 0) { const char* e = getenv("SVL_ATTN_TC"); tc_mode = e ? atoi(e) : 1; }
+  return !split && tc_mode && L >= 64;
+}
+
+extern "C" size_t svl_attention_bwd_workspace(int split, int b, int L, int heads) {
+  return attention_uses_tc(split, L) ? attention_bwd_tc_workspace(b, L, heads) : (size_t)b * heads * L;
+}
+
 extern "C" int svl_attention_fwd(const void* qkv, int split, void* out, float* lse, int b, int L, int heads, float scale, void* stream) {
   SVL_CHECK_ARG(qkv && out && b > 0 && L > 0 && heads > 0, "svl_attention_fwd: bad arguments");
   const int E = heads * D;
   const int64_t ld = split ? 6 * E : 3 * E, ldo = split ? 2 * E : E;
-  static int tc_mode = -1;
-  if (tc_mode < 0) { const char* e = getenv("SVL_ATTN_TC"); tc_mode = e ? atoi(e) : 1; }
-  if (!split && tc_mode && L >= 64) {       // tcgen05 path (throughput mode); tiny sequences (class attention, L = #classes) stay on mma.sync
+  if (attention_uses_tc(split, L)) {        // tcgen05 path (throughput mode); tiny sequences (class attention, L = #classes) stay on mma.sync
     if (int rc = svl_check_device()) return rc;
     return attention_fwd_tc(qkv, out, lse, b, L, heads, scale, (cudaStream_t)stream);
   }
@@ -549,6 +557,10 @@ extern "C" int svl_attention_bwd(const void* qkv, const void* out, const void* d
   const int E = heads * D;
   const int64_t ld = split ? 6 * E : 3 * E, ldo = split ? 2 * E : E;
   cudaStream_t st = (cudaStream_t)stream;
+  if (attention_uses_tc(split, L)) {
+    if (int rc = svl_check_device()) return rc;
+    return attention_bwd_tc(qkv, out, dout, lse, delta_ws, dv_add, dv_add_dtype, ld_dv_add, dqkv, b, L, heads, scale, st);
+  }
   const int64_t rows = (int64_t)b * L;
   int dgrid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
   attn_delta_kernel<<<dgrid, 256, 0, st>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, ldo, split, delta_ws, rows, L, heads);

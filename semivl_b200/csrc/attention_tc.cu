@@ -220,6 +220,357 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   }
 }
 
+
+// ================================================================================================ backward (tcgen05)
+// Workspace prepared by attn_prep_tc_kernel: delta_p / lse_p are [b*heads, Lp] (Lp = L rounded up to 64) so that 64-entry slices
+// are 256-byte aligned bulk copies; lse_p is pre-multiplied by log2(e) and padded with +inf (=> P = 0 for queries >= L).
+struct BwdParams {
+  const float* lse_p; const float* delta_p;
+  const void* dv_add; int dv_add_dtype; int64_t ld_dv_add;
+  __nv_bfloat16* dqkv; int64_t ldg;
+  int L, Lp, heads;
+  float scale;
+};
+
+__global__ void attn_prep_tc_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int64_t ldo,
+                                    const float* __restrict__ lse, float* __restrict__ lse_p, float* __restrict__ delta_p, int b, int L, int Lp,
+                                    int heads) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)b * Lp;
+  for (int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t bi = row / Lp, l = row % Lp;
+    for (int h = 0; h < heads; ++h) {
+      float s = 0.f, ls = INFINITY;
+      if (l < L) {
+        const int64_t src = (bi * L + l) * ldo + h * D + lane * 2;
+        const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)(out + src));
+        const float2 g = __bfloat1622float2(*(const __nv_bfloat162*)(dout + src));
+        s = warp_sum(a.x * g.x + a.y * g.y);
+        ls = lse[(bi * heads + h) * L + l] * kLog2e;
+      }
+      if (lane == 0) {
+        delta_p[(bi * heads + h) * Lp + l] = s;
+        lse_p[(bi * heads + h) * Lp + l] = ls;
+      }
+    }
+  }
+}
+
+// write one 128-byte operand row (64 bf16) of a K-major SWIZZLE_128B tile
+__device__ __forceinline__ void st_row64(uint8_t* row_base, int r, const float* v) {
+#pragma unroll
+  for (int piece = 0; piece < 8; ++piece) *(uint4*)(row_base + ((piece ^ (r & 7)) << 4)) = f32_to_bf16x8(v + piece * 8);
+}
+
+// dK, dV of one 128-key tile; streams 64-query tiles.  Thread = key row.
+//   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T = exp2(S^T*c - lse[q]), dS^T = P^T (dP^T - delta[q]) -> smem operands ->
+//   dV += P^T dO, dK += dS^T Q  (TMEM accumulators over all query tiles; Q / dO tiles are re-read MN-major from the same smem bytes)
+__global__ void __launch_bounds__(kThreads, 2)
+attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  if ((raw & 1023u) != 0) __trap();
+  constexpr uint32_t kHalf = kTile / 2;                  // 64-row tile: 8 KB
+  const uint32_t sK = raw, sV = raw + kTile, sQ = sV + kTile, sG = sQ + 2 * kHalf, sP = sG + 2 * kHalf, sS = sP + kTile;
+  const uint32_t sL = sS + kTile;                        // [2][64] lse_p | [2][64] delta_p
+  const uint32_t bar = sL + 1024;
+  const uint32_t kv_full = bar, s_full = bar + 8, s_empty = bar + 16, p_full = bar + 24, p_empty = bar + 32, acc_full = bar + 40;
+  auto q_full = [&](int s) { return bar + 8u * (6 + s); };
+  auto q_empty = [&](int s) { return bar + 8u * (8 + s); };
+  const uint32_t tmem_ptr_addr = bar + 8u * 10;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int E = p.heads * D;
+  const int nt = p.Lp / 64;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQKV);
+    ptx::prefetch_tmap(&tmQKV64);
+    ptx::prefetch_tmap(&tmDO);
+    ptx::mbar_init(kv_full, 1);
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_empty, 4);
+    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(p_empty, 1);
+    ptx::mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(q_full(s), 1);
+      ptx::mbar_init(q_empty(s), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;      // S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * kTile);
+      ptx::tma_load_3d(sK, &tmQKV, kv_full, E + h * D, k0, b);
+      ptx::tma_load_3d(sV, &tmQKV, kv_full, 2 * E + h * D, k0, b);
+      const float* lsrc = p.lse_p + ((int64_t)b * p.heads + h) * p.Lp;
+      const float* dsrc = p.delta_p + ((int64_t)b * p.heads + h) * p.Lp;
+      for (int j = 0; j < nt; ++j) {
+        const int st = j & 1, k = j >> 1;
+        ptx::mbar_wait(q_empty(st), (uint32_t)((k & 1) ^ 1));
+        ptx::mbar_arrive_expect_tx(q_full(st), 2 * kHalf + 512);
+        ptx::tma_load_3d(sQ + st * kHalf, &tmQKV64, q_full(st), h * D, j * 64, b);
+        ptx::tma_load_3d(sG + st * kHalf, &tmDO, q_full(st), h * D, j * 64, b);
+        ptx::bulk_load(sL + st * 256, lsrc + j * 64, 256, q_full(st));
+        ptx::bulk_load(sL + 512 + st * 256, dsrc + j * 64, 256, q_full(st));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);       // scores: both operands K-major (d contiguous)
+      const uint32_t idesc_a = ptx::make_idesc_bf16(128, 64, 0, 1);       // accumulates: B = Q / dO tile read MN-major
+      const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
+      const uint64_t kd = tmpl + (uint64_t)(sK >> 4), vd = tmpl + (uint64_t)(sV >> 4), pd = tmpl + (uint64_t)(sP >> 4), sd = tmpl + (uint64_t)(sS >> 4);
+      ptx::mbar_wait(kv_full, 0);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j & 1, k = j >> 1;
+        ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));
+        ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
+        ptx::tc_fence_after();
+        const uint64_t qd = tmpl + (uint64_t)((sQ + st * kHalf) >> 4), gd = tmpl + (uint64_t)((sG + st * kHalf) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base, kd + (uint64_t)(kk * 2), qd + (uint64_t)(kk * 2), idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base + 64u, vd + (uint64_t)(kk * 2), gd + (uint64_t)(kk * 2), idesc_s, kk > 0);
+        ptx::umma_commit(s_full);
+        ptx::mbar_wait(p_full, (uint32_t)(j & 1));
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)      // K = 64 queries: A 32 bytes per 16 queries inside the row, B 16 query rows = 2048 bytes
+          ptx::umma_bf16(tmem_base + 128u, pd + (uint64_t)(kk * 2), gd + (uint64_t)(kk * 128), idesc_a, (j > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_bf16(tmem_base + 192u, sd + (uint64_t)(kk * 2), qd + (uint64_t)(kk * 128), idesc_a, (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::umma_commit(p_empty);
+        ptx::umma_commit(q_empty(st));
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = p.scale * kLog2e;
+    uint8_t* prow = smem_raw + (sP - raw) + r * 128;
+    uint8_t* srow = smem_raw + (sS - raw) + r * 128;
+    const float* ls = (const float*)(smem_raw + (sL - raw));
+    for (int j = 0; j < nt; ++j) {
+      const int st = j & 1, k = j >> 1;
+      ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));            // lse / delta slices of this query tile
+      ptx::mbar_wait(s_full, (uint32_t)(j & 1));
+      ptx::tc_fence_after();
+      uint32_t sv[64], dv[64];
+      tmem_ld64(tl, sv);
+      tmem_ld64(tl + 64u, dv);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_empty);
+      float pt[64], ds[64];
+      const float* lq = ls + st * 64;
+      const float* dq = ls + 128 + st * 64;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        pt[i] = ex2(fmaf(__uint_as_float(sv[i]), sl2, -lq[i]));
+        ds[i] = pt[i] * (__uint_as_float(dv[i]) - dq[i]);
+      }
+      ptx::mbar_wait(p_empty, (uint32_t)((j & 1) ^ 1));         // the previous tile's accumulate MMAs have left the operand buffers
+      st_row64(prow, r, pt);
+      st_row64(srow, r, ds);
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    const int key = k0 + r;
+    uint32_t a[64];
+    float f[64];
+    // dV (+ v-path contribution)
+    tmem_ld64(tl + 128u, a);
+    if (key < p.L) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(a[i]);
+      if (p.dv_add) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float t[8];
+          ld8(p.dv_add, p.dv_add_dtype, ((int64_t)b * p.L + key) * p.ld_dv_add + h * D + g * 8, p.ld_dv_add / 2, 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[g * 8 + i] += t[i];
+        }
+      }
+      __nv_bfloat16* dst = p.dqkv + ((int64_t)b * p.L + key) * p.ldg + 2 * E + h * D;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *(uint4*)(dst + i * 8) = f32_to_bf16x8(f + i * 8);
+    }
+    tmem_ld64(tl + 192u, a);
+    if (key < p.L) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
+      __nv_bfloat16* dst = p.dqkv + ((int64_t)b * p.L + key) * p.ldg + E + h * D;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *(uint4*)(dst + i * 8) = f32_to_bf16x8(f + i * 8);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dQ of one 128-query tile; streams 64-key tiles.  Thread = query row.
+__global__ void __launch_bounds__(kThreads, 2)
+attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  if ((raw & 1023u) != 0) __trap();
+  constexpr uint32_t kHalf = kTile / 2;
+  const uint32_t sQ = raw, sG = raw + kTile, sK = sG + kTile, sV = sK + 2 * kHalf, sS = sV + 2 * kHalf;
+  const uint32_t bar = sS + kTile;
+  const uint32_t q_full = bar, s_full = bar + 8, s_empty = bar + 16, p_full = bar + 24, p_empty = bar + 32, acc_full = bar + 40;
+  auto kv_full = [&](int s) { return bar + 8u * (6 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (8 + s); };
+  const uint32_t tmem_ptr_addr = bar + 8u * 10;
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int E = p.heads * D;
+  const int nt = (p.L + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQKV);
+    ptx::prefetch_tmap(&tmQKV64);
+    ptx::prefetch_tmap(&tmDO);
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_empty, 4);
+    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(p_empty, 1);
+    ptx::mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(kv_full(s), 1);
+      ptx::mbar_init(kv_empty(s), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;      // S [0,64) | dP [64,128) | dQ [128,192)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, 2 * kTile);
+      ptx::tma_load_3d(sQ, &tmQKV, q_full, h * D, q0, b);
+      ptx::tma_load_3d(sG, &tmDO, q_full, h * D, q0, b);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j & 1, k = j >> 1;
+        ptx::mbar_wait(kv_empty(st), (uint32_t)((k & 1) ^ 1));
+        ptx::mbar_arrive_expect_tx(kv_full(st), 2 * kHalf);
+        ptx::tma_load_3d(sK + st * kHalf, &tmQKV64, kv_full(st), E + h * D, j * 64, b);
+        ptx::tma_load_3d(sV + st * kHalf, &tmQKV64, kv_full(st), 2 * E + h * D, j * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_a = ptx::make_idesc_bf16(128, 64, 0, 1);
+      const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
+      const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), gd = tmpl + (uint64_t)(sG >> 4), sd = tmpl + (uint64_t)(sS >> 4);
+      ptx::mbar_wait(q_full, 0);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j & 1, k = j >> 1;
+        ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
+        ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
+        ptx::tc_fence_after();
+        const uint64_t kd = tmpl + (uint64_t)((sK + st * kHalf) >> 4), vd = tmpl + (uint64_t)((sV + st * kHalf) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base + 64u, gd + (uint64_t)(kk * 2), vd + (uint64_t)(kk * 2), idesc_s, kk > 0);
+        ptx::umma_commit(s_full);
+        ptx::mbar_wait(p_full, (uint32_t)(j & 1));
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)      // dQ += dS K : K dimension = the 64 keys (K tile read MN-major, 16 key rows = 2048 bytes)
+          ptx::umma_bf16(tmem_base + 128u, sd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 128), idesc_a, (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::umma_commit(p_empty);
+        ptx::umma_commit(kv_empty(st));
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = p.scale * kLog2e;
+    uint8_t* srow = smem_raw + (sS - raw) + r * 128;
+    const int row = q0 + r;
+    const int64_t li = ((int64_t)b * p.heads + h) * p.Lp + (row < p.Lp ? row : p.Lp - 1);
+    const float lse_r = row < p.Lp ? p.lse_p[li] : INFINITY, delta_r = row < p.Lp ? p.delta_p[li] : 0.f;
+    for (int j = 0; j < nt; ++j) {
+      ptx::mbar_wait(s_full, (uint32_t)(j & 1));
+      ptx::tc_fence_after();
+      uint32_t sv[64], dv[64];
+      tmem_ld64(tl, sv);
+      tmem_ld64(tl + 64u, dv);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_empty);
+      float ds[64];
+      const bool tail = j * 64 + 64 > p.L;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float pr = ex2(fmaf(__uint_as_float(sv[i]), sl2, -lse_r));
+        if (tail && j * 64 + i >= p.L) pr = 0.f;
+        ds[i] = pr * (__uint_as_float(dv[i]) - delta_r);
+      }
+      ptx::mbar_wait(p_empty, (uint32_t)((j & 1) ^ 1));
+      st_row64(srow, r, ds);
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    uint32_t a[64];
+    tmem_ld64(tl + 128u, a);
+    if (row < p.L) {
+      float f[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(a[i]) * p.scale;
+      __nv_bfloat16* dst = p.dqkv + ((int64_t)b * p.L + row) * p.ldg + h * D;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *(uint4*)(dst + i * 8) = f32_to_bf16x8(f + i * 8);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace
 
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int heads, float scale, cudaStream_t stream) {
@@ -239,6 +590,50 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int h
   }
   dim3 grid((L + TQ - 1) / TQ, heads, b);
   attn_fwd_tc_kernel<<<grid, kThreads, smem, stream>>>(tm, p);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+size_t attention_bwd_tc_workspace(int b, int L, int heads) {
+  const int Lp = (L + 63) / 64 * 64;
+  return (size_t)2 * b * heads * Lp;
+}
+
+int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* ws, const void* dv_add, int dv_add_dtype,
+                     int64_t ld_dv_add, void* dqkv, int b, int L, int heads, float scale, cudaStream_t stream) {
+  const int E = heads * D;
+  const int Lp = (L + 63) / 64 * 64;
+  float* lse_p = ws;
+  float* delta_p = ws + (size_t)b * heads * Lp;
+  const int64_t rows = (int64_t)b * Lp;
+  int pgrid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
+  attn_prep_tc_kernel<<<pgrid, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, E, lse, lse_p, delta_p, b, L, Lp, heads);
+  SVL_LAUNCH_CHECK();
+  CUtensorMap tmQKV64, tmQKV128, tmDO64, tmDO128;
+  uint64_t dims[3] = {(uint64_t)3 * E, (uint64_t)L, (uint64_t)b};
+  uint64_t strides[2] = {(uint64_t)3 * E * 2, (uint64_t)L * 3 * E * 2};
+  uint64_t dimso[3] = {(uint64_t)E, (uint64_t)L, (uint64_t)b};
+  uint64_t strideso[2] = {(uint64_t)E * 2, (uint64_t)L * E * 2};
+  uint32_t box64[3] = {64u, 64u, 1u}, box128[3] = {64u, 128u, 1u};
+  if (int rc = tma_encode_bf16(&tmQKV64, qkv, 3, dims, strides, box64)) return rc;
+  if (int rc = tma_encode_bf16(&tmQKV128, qkv, 3, dims, strides, box128)) return rc;
+  if (int rc = tma_encode_bf16(&tmDO64, dout, 3, dimso, strideso, box64)) return rc;
+  if (int rc = tma_encode_bf16(&tmDO128, dout, 3, dimso, strideso, box128)) return rc;
+  BwdParams p;
+  p.lse_p = lse_p; p.delta_p = delta_p; p.dv_add = dv_add; p.dv_add_dtype = dv_add_dtype; p.ld_dv_add = ld_dv_add;
+  p.dqkv = (__nv_bfloat16*)dqkv; p.ldg = 3 * E; p.L = L; p.Lp = Lp; p.heads = heads; p.scale = scale;
+  const size_t smem_kv = 6 * (size_t)kTile + 1024 + 8 * 11 + 16, smem_q = 5 * (size_t)kTile + 8 * 11 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVL_CUDA(cudaFuncSetAttribute(attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+    SVL_CUDA(cudaFuncSetAttribute(attn_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    attr_set = true;
+  }
+  dim3 grid((L + 127) / 128, heads, b);
+  // the kv kernel keeps 128-row K/V tiles and streams 64-row Q/dO tiles, the q kernel the other way round
+  attn_bwd_kv_tc_kernel<<<grid, kThreads, smem_kv, stream>>>(tmQKV128, tmQKV64, tmDO64, p);
+  SVL_LAUNCH_CHECK();
+  attn_bwd_q_tc_kernel<<<grid, kThreads, smem_q, stream>>>(tmQKV128, tmQKV64, tmDO128, p);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

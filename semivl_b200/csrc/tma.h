@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace svl {
@@ -11,5 +12,8 @@ int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
                     const uint32_t* box);
 int num_sms();
 // tcgen05 flash attention (attention_tc.cu), bf16 throughput mode only
+size_t attention_bwd_tc_workspace(int b, int L, int heads);
+int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* ws, const void* dv_add, int dv_add_dtype,
+                     int64_t ld_dv_add, void* dqkv, int b, int L, int heads, float scale, cudaStream_t stream);
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int heads, float scale, cudaStream_t stream);
 }  // namespace svl

@@ -64,6 +64,8 @@ _lib.svl_check_device.restype = C.c_int
 _lib.svl_gemm.restype = C.c_int
 _lib.svl_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
 
+_lib.svl_attention_bwd_workspace.restype = C.c_size_t
+_lib.svl_attention_bwd_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
 _lib.svl_wgrad.restype = C.c_int
 _lib.svl_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
 

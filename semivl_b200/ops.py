@@ -256,7 +256,7 @@ def attention_fwd(qkv, b, seq, heads, precise, want_lse=True):
 def attention_bwd(qkv, out, dout, lse, b, seq, heads, precise, dv_add=None, dv_add_dtype=L.F32):
     E = heads * 64
     dqkv = new_act(b * seq, 3 * E, precise, qkv.device)
-    delta = torch.empty(b, heads, seq, device=qkv.device, dtype=torch.float32)
+    delta = torch.empty(L.lib().svl_attention_bwd_workspace(1 if precise else 0, b, seq, heads), device=qkv.device, dtype=torch.float32)
     L.call("svl_attention_bwd", qkv, out, dout, 1 if precise else 0, lse, delta, dv_add, dv_add_dtype,
            dv_add.shape[-1] if dv_add is not None else 0, dqkv, b, seq, heads, 0.125, n_launch=3)
     return dqkv

@@ -200,9 +200,9 @@ inline int gn_splits(int64_t maps, int hw, int C) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("SVL_GN_SPLITS"); forced = e ? atoi(e) : 0; }
   if (forced > 0) return forced;
-  // aim for >= 4 CTAs per SM in total, at least ~8 pixel iterations per thread
-  int64_t want = (148 * 4 + maps - 1) / maps;
-  int64_t cap = (int64_t)hw * (C / 8) / (kGnThreads * 8);
+  // many more CTAs than resident slots (no half-empty last wave), but at least ~16 pixel iterations per thread
+  int64_t want = (148 * 16 + maps - 1) / maps;
+  int64_t cap = (int64_t)hw * (C / 16) / (kGnThreads * 16);
   if (cap < 1) cap = 1;
   int64_t s = want < cap ? want : cap;
   return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));

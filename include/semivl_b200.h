@@ -52,7 +52,9 @@ int svl_check_device(void);
  * ---------------------------------------------------------------------------------------------- */
 #define SVL_MAX_TAPS 32
 
-typedef enum { SVL_ACT_NONE = 0, SVL_ACT_GELU = 1, SVL_ACT_RELU = 2 } svl_act;
+/* SVL_ACT_GELU_DSAVE (as `act`): out = gelu(z) and preact_out receives gelu'(z) instead of z, so that the data-gradient GEMM of the
+ * layer below only multiplies (dact_kind = SVL_ACT_SAVED: dact_src holds the derivative itself). */
+typedef enum { SVL_ACT_NONE = 0, SVL_ACT_GELU = 1, SVL_ACT_RELU = 2, SVL_ACT_GELU_DSAVE = 3, SVL_ACT_SAVED = 4 } svl_act;
 typedef enum { SVL_OUT_LINEAR = 0, SVL_OUT_CONVT2X2 = 1 } svl_out_mode;
 
 typedef struct {

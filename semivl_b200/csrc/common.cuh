@@ -245,6 +245,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
   erf_exp_fast(x * 0.70710678118654752f, er, ex);
   return 0.5f * x * (1.f + er);
 }
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& dg) {
+  float er, ex;
+  erf_exp_fast(x * 0.70710678118654752f, er, ex);
+  const float cdf = fmaf(0.5f, er, 0.5f);
+  g = x * cdf;
+  dg = fmaf(x * 0.3989422804014327f, ex, cdf);
+}
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float er, ex;
   erf_exp_fast(x * 0.70710678118654752f, er, ex);      // ex = exp(-x^2 / 2)

@@ -260,6 +260,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int y = (int)((grow % hw) / p.out_w), x = (int)(grow % p.out_w);
         ct_base = ((img * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.ldc;
       }
+      // Side inputs of the specialised epilogues (act' source, residual) do not depend on the accumulator: fetch them while the
+      // tile's MMAs are still running.  act' source: both 32-column chunks of this thread into registers (raw bf16);
+      // residual (fp32, 128 B per chunk): an L2 prefetch of the line.
+      uint4 sraw[2][4];
+      if (!GEN && DACT >= 1 && grow >= 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c0 = (cgrp + j * kEpiGroups) * 32;
+          if (c0 < p.block_n && n0 + c0 < p.n) {       // launcher: n % 32 == 0 for these variants, so a started chunk is whole
+            const uint4* src = (const uint4*)((const __nv_bfloat16*)p.dact_src + grow * p.ld_dact + n0 + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sraw[j][i] = __ldg(src + i);
+          }
+        }
+      }
+      if (!GEN && RES == SVL_F32 && grow >= 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c0 = (cgrp + j * kEpiGroups) * 32;
+          if (c0 < p.block_n && n0 + c0 < p.n)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const float*)p.residual + grow * p.ldres + n0 + c0));
+        }
+      }
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
       if (GEN)
@@ -287,7 +310,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) if (i < cnt) f[i] += __ldg(rb + i);
             }
-            if (p.preact_out) st8(p.preact_out, p.preact_dtype, grow * p.ld_preact + col, 0, cnt, f);
+            if (p.act == SVL_ACT_GELU_DSAVE) {
+              float dg[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { dg[i] = gelu_grad(f[i]); f[i] = gelu_exact(f[i]); }
+              st8(p.preact_out, p.preact_dtype, grow * p.ld_preact + col, 0, cnt, dg);
+            } else if (p.preact_out) st8(p.preact_out, p.preact_dtype, grow * p.ld_preact + col, 0, cnt, f);
             if (p.act == SVL_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = gelu_exact(f[i]);
@@ -301,6 +329,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (p.dact_kind == SVL_ACT_GELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] *= gelu_grad(s[i]);
+              } else if (p.dact_kind == SVL_ACT_SAVED) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= s[i];
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = s[i] > 0.f ? f[i] : 0.f;
@@ -334,21 +365,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (!GEN) {
         // specialised epilogue: 32-column chunks, one output row per thread, 32-byte vector accesses (full sectors);
         // bias / act / act' / residual fused in registers
-        for (int c0 = cgrp * 32; c0 < p.block_n; c0 += kEpiGroups * 32) {
-          if (n0 + c0 >= p.n) break;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                  // block_n <= 256: at most two chunks per warp
+          const int c0 = (cgrp + j * kEpiGroups) * 32;
+          if (c0 >= p.block_n || n0 + c0 >= p.n) break;
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
-          // side inputs (act' source / residual) do not depend on the accumulator: their global loads are issued before the TMEM wait
           float side[2][16];
-          if ((DACT == 1 || RES >= 0) && grow >= 0) {
+          if (RES >= 0 && grow >= 0) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int col = n0 + c0 + g * 16;
               const int cnt = min(16, p.n - col);
-              if (cnt > 0) {
-                if (DACT == 1) ld16(p.dact_src, SVL_BF16, grow * p.ld_dact + col, 0, cnt, side[g]);
-                else ld16(p.residual, RES, grow * p.ldres + col, 0, cnt, side[g]);
-              }
+              if (cnt > 0) ld16(p.residual, RES, grow * p.ldres + col, 0, cnt, side[g]);
+            }
+          }
+          if (DACT >= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t w = ((const uint32_t*)&sraw[j][0])[i];
+              side[i >> 3][(2 * i) & 15] = __uint_as_float(w << 16);
+              side[i >> 3][((2 * i) & 15) + 1] = __uint_as_float(w & 0xffff0000u);
             }
           }
           ptx::tmem_ld_wait();
@@ -383,7 +420,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 16; ++i) if (i < cnt) f[i] += __ldg(rb + i);
             }
-            if (PRE >= 0) st16(p.preact_out, PRE, grow * p.ld_preact + col, 0, cnt, f);
+            if (ACT == SVL_ACT_GELU_DSAVE) {                 // out = gelu(z), preact_out = gelu'(z): the backward epilogue is one multiply
+              float dg[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) gelu_and_grad_fast(f[i], f[i], dg[i]);
+              st16(p.preact_out, PRE, grow * p.ld_preact + col, 0, cnt, dg);
+            } else if (PRE >= 0) st16(p.preact_out, PRE, grow * p.ld_preact + col, 0, cnt, f);
             if (ACT == SVL_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = gelu_fast(f[i]);
@@ -394,6 +436,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (DACT == 1) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] *= gelu_grad_fast(side[g][i]);
+            } else if (DACT == 2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] *= side[g][i];
             }
             if (RES >= 0) {
 #pragma unroll
@@ -456,6 +501,8 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   if (d->out_mode == SVL_OUT_CONVT2X2)
     SVL_CHECK_ARG(d->n % 32 == 0 && d->out_h > 0 && d->out_w > 0 && d->m % ((int64_t)d->out_h * d->out_w) == 0,
                   "svl_gemm: CONVT2X2 needs n %% 32 == 0 and m a multiple of out_h*out_w");
+  SVL_CHECK_ARG(d->act != SVL_ACT_GELU_DSAVE || d->preact_out, "svl_gemm: SVL_ACT_GELU_DSAVE needs preact_out (it receives gelu')");
+  SVL_CHECK_ARG(d->act != SVL_ACT_SAVED && d->dact_kind != SVL_ACT_GELU_DSAVE, "svl_gemm: SVL_ACT_SAVED is a dact_kind, SVL_ACT_GELU_DSAVE an act");
   if (int rc = svl_check_device()) return rc;
 
   GemmParams p;
@@ -593,9 +640,13 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
              (!p.preact_out || p.preact_dtype == SVL_BF16)) {
     if (p.preact_out) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU, SVL_BF16, 0, -1, 0, false);
     else SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU, -1, 0, -1, 0, false);
-  } else if (plain && p.out_dtype == SVL_BF16 && p.dact_src && p.dact_kind == SVL_ACT_GELU && p.dact_dtype == SVL_BF16 && !p.preact_out &&
-             !p.residual && p.act == SVL_ACT_NONE) {
-    SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 1, -1, 0, false);
+  } else if (plain && p.out_dtype == SVL_BF16 && p.act == SVL_ACT_GELU_DSAVE && !p.dact_src && !p.residual && p.preact_dtype == SVL_BF16) {
+    SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU_DSAVE, SVL_BF16, 0, -1, 0, false);
+  } else if (plain && p.out_dtype == SVL_BF16 && p.dact_src && (p.dact_kind == SVL_ACT_GELU || p.dact_kind == SVL_ACT_SAVED) &&
+             p.dact_dtype == SVL_BF16 && !p.preact_out && !p.residual && p.act == SVL_ACT_NONE && p.n % 32 == 0 && p.ld_dact % 8 == 0 &&
+             ((uintptr_t)p.dact_src & 15) == 0) {
+    if (p.dact_kind == SVL_ACT_GELU) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 1, -1, 0, false);
+    else SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 2, -1, 0, false);
   } else if (no_extra && p.out_mode == SVL_OUT_CONVT2X2 && p.out_dtype == SVL_BF16 && !p.row_bias && !p.accumulate && (p.n / 4) % 16 == 0) {
     SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 1, false);
   } else if (no_extra && p.out_mode == SVL_OUT_LINEAR && p.out_dtype == SVL_BF16 && p.row_bias && !p.accumulate) {

@@ -115,6 +115,8 @@ class VitEngine:
         taps = self._tap_layers()
         feats_v = {}
         pre_dt = torch.float32 if pr else torch.bfloat16
+        # throughput mode saves gelu'(z) instead of z: the FFN data-gradient epilogue becomes a multiply
+        gelu_act = L.ACT_GELU if pr else L.ACT_GELU_DSAVE
         for i in range(c.layers):
             pre = f"layers.{i}."
             want_v = i in taps
@@ -138,7 +140,7 @@ class VitEngine:
                 y2, mu2, rs2 = ops.layernorm_fwd(x_mid, g2, be2, c.eps, precise=pr, save_stats=need_grad)
                 hpre = torch.empty(M, 4 * E, device=dev, dtype=pre_dt) if (need_grad and not last) else None
                 hact = ops.new_act(M, 4 * E, pr, dev)
-                ops.gemm(y2, w1, hact, n=4 * E, k=E, precise=pr, bias=b1, act=L.ACT_GELU, preact_out=hpre, out_dtype=ops.act_dtype(pr))
+                ops.gemm(y2, w1, hact, n=4 * E, k=E, precise=pr, bias=b1, act=gelu_act if hpre is not None else L.ACT_GELU, preact_out=hpre, out_dtype=ops.act_dtype(pr))
                 x = torch.empty(M, E, **f32)
                 ops.gemm(hact, w2, x, n=E, k=4 * E, precise=pr, bias=b2, residual=x_mid)
                 del hact, y2
@@ -151,7 +153,7 @@ class VitEngine:
                 yv, muv, rsv = ops.layernorm_fwd(v1, g2, be2, c.eps, precise=pr, save_stats=need_grad)
                 vpre = torch.empty(M, 4 * E, device=dev, dtype=pre_dt) if need_grad else None
                 hv = ops.new_act(M, 4 * E, pr, dev)
-                ops.gemm(yv, w1, hv, n=4 * E, k=E, precise=pr, bias=b1, act=L.ACT_GELU, preact_out=vpre, out_dtype=ops.act_dtype(pr))
+                ops.gemm(yv, w1, hv, n=4 * E, k=E, precise=pr, bias=b1, act=gelu_act if vpre is not None else L.ACT_GELU, preact_out=vpre, out_dtype=ops.act_dtype(pr))
                 v2 = torch.empty(M, E, **f32)
                 ops.gemm(hv, w2, v2, n=E, k=4 * E, precise=pr, bias=b2, residual=v1)
                 del hv, yv
@@ -202,6 +204,7 @@ class VitEngine:
         f32 = dict(device=dev, dtype=torch.float32)
         gdt = L.F32 if pr else L.BF16                       # storage of intermediate (non-operand) gradients
         gtorch = torch.float32 if pr else torch.bfloat16
+        gelu_dact = L.ACT_GELU if pr else L.ACT_SAVED
 
         def add_cls(g, C):
             out = torch.zeros(B, Lq, C, **f32)
@@ -244,7 +247,7 @@ class VitEngine:
             have_x = dx is not None and S["has_x"]
             if dv2 is not None:
                 dhv = ops.new_act(M, 4 * E, pr, dev)
-                ops.gemm(ops.to_act(dv2, pr), w2_t, dhv, n=4 * E, k=E, precise=pr, dact_src=S["vpre"], dact_kind=L.ACT_GELU,
+                ops.gemm(ops.to_act(dv2, pr), w2_t, dhv, n=4 * E, k=E, precise=pr, dact_src=S["vpre"], dact_kind=gelu_dact,
                          out_dtype=ops.act_dtype(pr))
                 dyv = torch.empty(M, E, device=dev, dtype=gtorch)
                 ops.gemm(dhv, w1_t, dyv, n=E, k=4 * E, precise=pr)
@@ -262,7 +265,7 @@ class VitEngine:
                 if dx_act is None:
                     dx_act = ops.to_act(dx, pr)
                 dh = ops.new_act(M, 4 * E, pr, dev)
-                ops.gemm(dx_act, w2_t, dh, n=4 * E, k=E, precise=pr, dact_src=S["hpre"], dact_kind=L.ACT_GELU, out_dtype=ops.act_dtype(pr))
+                ops.gemm(dx_act, w2_t, dh, n=4 * E, k=E, precise=pr, dact_src=S["hpre"], dact_kind=gelu_dact, out_dtype=ops.act_dtype(pr))
                 dy2 = torch.empty(M, E, device=dev, dtype=gtorch)
                 ops.gemm(dh, w1_t, dy2, n=E, k=4 * E, precise=pr)
                 del dh

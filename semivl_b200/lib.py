@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libsemivl_b200.so")
 
 F32, BF16, BF16X2 = 0, 1, 2
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_DSAVE, ACT_SAVED = 0, 1, 2, 3, 4
 OUT_LINEAR, OUT_CONVT2X2 = 0, 1
 MAX_TAPS = 32
 

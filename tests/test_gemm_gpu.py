@@ -85,6 +85,48 @@ def test_epilogue_gelu_residual_preact(ops):
     assert _rel(o2, zz * (_bf(y).float() > 0)) < 1e-4
 
 
+@pytest.mark.parametrize("m,n,k", [(700, 320, 256), (2100, 3072, 768), (130, 96, 64)])
+def test_ffn_epilogues_bf16(ops, m, n, k):
+    """The specialised throughput-mode epilogues of the transformer FFN: GELU forward saving z or gelu'(z), and the data-gradient
+    epilogue multiplying by gelu'(z) (recomputed from z, or read back as saved), plus the fp32 residual epilogue."""
+    from semivl_b200 import lib as L
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    a = _bf(torch.randn(m, k, device="cuda", generator=g))
+    w = _bf(torch.randn(n, k, device="cuda", generator=g) / k ** 0.5)
+    bias = torch.randn(n, device="cuda", generator=g)
+    z = a.float() @ w.float().t() + bias
+    zr = z.clone().requires_grad_(True)
+    F.gelu(zr).sum().backward()
+    out = torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+    pre = torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, n=n, k=k, bias=bias, act=L.ACT_GELU, preact_out=pre)
+    assert _rel(out, F.gelu(z)) < 6e-3 and _rel(pre, z) < 6e-3
+    out2 = torch.zeros_like(out)
+    dsave = torch.zeros_like(pre)
+    ops.gemm(a, w, out2, n=n, k=k, bias=bias, act=L.ACT_GELU_DSAVE, preact_out=dsave)
+    assert torch.equal(out2, out)
+    assert (dsave.float() - zr.grad).abs().max().item() < 6e-3
+    # backward: dY [m, n2] x W2^T -> [m, n], times gelu'
+    n2 = 128
+    dy = _bf(torch.randn(m, n2, device="cuda", generator=g))
+    w2t = _bf(torch.randn(n, n2, device="cuda", generator=g) / n2 ** 0.5)
+    lin = dy.float() @ w2t.float().t()
+    d1 = torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, w2t, d1, n=n, k=n2, dact_src=pre, dact_kind=L.ACT_GELU)
+    s = pre.float().requires_grad_(True)
+    F.gelu(s).sum().backward()
+    assert _rel(d1, lin * s.grad) < 6e-3
+    d2 = torch.zeros_like(d1)
+    ops.gemm(dy, w2t, d2, n=n, k=n2, dact_src=dsave, dact_kind=L.ACT_SAVED)
+    assert _rel(d2, lin * dsave.float()) < 6e-3
+    assert _rel(d2, lin * zr.grad) < 1.5e-2
+    # fp32 residual epilogue
+    res = torch.randn(m, n, device="cuda", generator=g)
+    o3 = torch.zeros(m, n, device="cuda")
+    ops.gemm(a, w, o3, n=n, k=k, bias=bias, residual=res)
+    assert _rel(o3, z + res) < 1e-4
+
+
 @pytest.mark.parametrize("nb,h,w,cin,cout,ks,dil", [(5, 12, 12, 64, 48, 3, 2), (7, 32, 32, 128, 128, 3, 6), (3, 64, 64, 128, 64, 3, 1),
                                                      (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
                                                      (2, 128, 128, 32, 1, 3, 1), (4, 8, 8, 256, 64, 1, 1)])

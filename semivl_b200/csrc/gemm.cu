@@ -23,6 +23,7 @@ constexpr int BK = 64;
 constexpr int kEpiGroups = 4;          // epilogue warps per TMEM lane quarter (each takes every kEpiGroups-th 32-column chunk)
 constexpr int kThreads = 64 + 128 * kEpiGroups;   // warp 0 TMA, warp 1 MMA, then 4 * kEpiGroups epilogue warps
 constexpr int kMaxStages = 8;
+constexpr int kMaxAcc = 8;          // TMEM accumulator ring: as many block_n-wide slots as fit in 512 columns, at most this
 constexpr int kSmemBudget = 200 * 1024;
 
 struct GemmParams {
@@ -34,7 +35,7 @@ struct GemmParams {
   int tiles_x, tiles_y;            // conv tiles per image row / column-of-tiles
   int num_m_tiles, num_n_tiles;
   int n, block_n, k_per_tap, num_taps;
-  int stages, tmem_cols;
+  int stages, tmem_cols, acc_stages;
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int tap_dy[SVL_MAX_TAPS], tap_dx[SVL_MAX_TAPS], tap_a_koff[SVL_MAX_TAPS], tap_b_row[SVL_MAX_TAPS], tap_b_col[SVL_MAX_TAPS];
   // epilogue
@@ -48,6 +49,8 @@ struct GemmParams {
   // A strip of (128 + span) pixels, read by each tap at its own row offset; all tap weights stay resident in shared memory
   int strip, ng;
   int g_dy[8], g_dxmin[8], g_ntaps[8], g_tap[8][4];
+  int g_nmma[4];                   // MMAs per strip group, and per MMA the A / B descriptor offsets (16-byte units)
+  uint32_t mma_aoff[4][16], mma_boff[4][16];
   uint32_t strip_bytes, b_tile_bytes;
 };
 
@@ -85,9 +88,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-  const uint32_t wbar = bar_base + 8u * (2 * kMaxStages + 4);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 5);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + s); };
+  const uint32_t wbar = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc + 1);
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,7 +104,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.acc_stages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
       ptx::mbar_init(tempty_bar(s), 4 * kEpiGroups);
     }
@@ -161,61 +164,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      if (p.strip) {
-        // The lone issuing thread pays every instruction's latency: all descriptor arithmetic is hoisted into registers
-        // (A descriptors relative to the stage base, B descriptors absolute: the weights are resident), loops fully unrolled.
-        const int nk = p.k_per_tap / 16;
-        const uint64_t tmpl = ptx::make_smem_desc(0, 16, 1024);
-        uint64_t aoff[4][4], bdesc[4][4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool on = g < p.ng && j < p.g_ntaps[g];
-            const int t = on ? p.g_tap[g][j] : 0;
-            aoff[g][j] = (uint64_t)(((uint32_t)(p.tap_dx[t] - (on ? p.g_dxmin[g] : p.tap_dx[t])) * 128u) >> 4);
-            bdesc[g][j] = tmpl + (uint64_t)((smem_b + t * p.b_tile_bytes) >> 4);
-          }
-        }
-        ptx::mbar_wait(wbar, 0);
+    // The whole warp runs the loop and one elected lane issues: every operand of tcgen05.mma (descriptors, TMEM address, instruction
+    // descriptor, accumulate flag) then stays in UNIFORM registers.  Issued from a divergent `lane == 0` branch the same code needs
+    // ~30 instructions per MMA (vector->uniform moves inside a waterfall loop) and small-N convolutions become bound by this one
+    // thread (profiles/r01_up2_conv_issue_bound.md).  The strip mode reads its per-tile MMA list (A offset inside the strip,
+    // B offset inside the resident weights) from a host-built table in the constant bank.
+    const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 0, 0);
+    const bool leader = ptx::elect_one();
+    const uint64_t tmpl = ptx::make_smem_desc(0, 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    if (p.strip) {
+      ptx::mbar_wait(wbar, 0);
+      ptx::tc_fence_after();
+      const uint32_t b_lo = smem_b >> 4;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+        uint32_t accum = 0;
+        for (int g = 0; g < p.ng; ++g) {
+          ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
-          uint32_t accum = 0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g < p.ng) {
-              ptx::mbar_wait(full_bar(stage), phase);
-              ptx::tc_fence_after();
-              const uint64_t abase = tmpl + (uint64_t)((smem_a + stage * p.a_stage_bytes) >> 4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (j < p.g_ntaps[g]) {
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    if (kk < nk) {
-                      ptx::umma_bf16(tmem_d, abase + aoff[g][j] + (uint64_t)(kk * 2), bdesc[g][j] + (uint64_t)(kk * 2), idesc, accum);
-                      accum = 1;
-                    }
-                  }
-                }
-              }
-              ptx::umma_commit(empty_bar(stage));
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          const uint32_t a_lo = (smem_a + stage * p.a_stage_bytes) >> 4;
+          const int nm = p.g_nmma[g];
+          if (leader) {
+            for (int i = 0; i < nm; ++i) {
+              ptx::umma_bf16(tmem_d, tmpl + (uint64_t)(a_lo + p.mma_aoff[g][i]), tmpl + (uint64_t)(b_lo + p.mma_boff[g][i]), idesc, accum);
+              accum = 1;
             }
+            ptx::umma_commit(empty_bar(stage));
           }
-          ptx::umma_commit(tfull_bar(as));
-          if (++as == 2) { as = 0; aphase ^= 1u; }
+          accum = 1;
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-      } else
+        if (leader) ptx::umma_commit(tfull_bar(as));
+        __syncwarp();
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+      }
+    } else {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
@@ -225,19 +215,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
-            const uint32_t sa = smem_a + stage * p.a_stage_bytes, sb = smem_b + stage * p.b_stage_bytes;
-            const uint64_t adesc = ptx::make_smem_desc(sa, 16, 1024), bdesc = ptx::make_smem_desc(sb, 16, 1024);
+            const uint64_t adesc = tmpl + (uint64_t)((smem_a + stage * p.a_stage_bytes) >> 4);
+            const uint64_t bdesc = tmpl + (uint64_t)((smem_b + stage * p.b_stage_bytes) >> 4);
             const int nk = min(BK, p.k_per_tap - kb * BK) / 16;
-            for (int kk = 0; kk < nk; ++kk) {
-              ptx::umma_bf16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, accum);
-              accum = 1;
+            if (leader) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < nk) ptx::umma_bf16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk == 0 ? accum : 1u);
+              }
+              ptx::umma_commit(empty_bar(stage));
             }
-            ptx::umma_commit(empty_bar(stage));
+            accum = 1;
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
-        ptx::umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (leader) ptx::umma_commit(tfull_bar(as));
+        __syncwarp();
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
@@ -462,7 +457,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
     }
   }
 
@@ -601,12 +596,25 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     p.stages = (int)((kSmemBudget - wbytes) / p.a_stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     smem_data = (size_t)p.stages * p.a_stage_bytes + wbytes;
+    for (int g = 0; g < p.ng; ++g) {
+      int nm = 0;
+      for (int j = 0; j < p.g_ntaps[g]; ++j) {
+        const int t = p.g_tap[g][j];
+        for (int kk = 0; kk < p.k_per_tap / 16; ++kk, ++nm) {
+          p.mma_aoff[g][nm] = ((uint32_t)(p.tap_dx[t] - p.g_dxmin[g]) * 128u + (uint32_t)kk * 32u) >> 4;
+          p.mma_boff[g][nm] = ((uint32_t)t * p.b_tile_bytes + (uint32_t)kk * 32u) >> 4;
+        }
+      }
+      p.g_nmma[g] = nm;
+    }
   } else {
     p.stages = (int)(kSmemBudget / (p.a_stage_bytes + p.b_stage_bytes));
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     smem_data = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes);
   }
-  p.tmem_cols = pow2ceil(2 * p.block_n < 32 ? 32 : 2 * p.block_n);
+  p.acc_stages = 512 / p.block_n < kMaxAcc ? 512 / p.block_n : kMaxAcc;
+  if (const char* e = getenv("SVL_ACC_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.acc_stages) p.acc_stages = v; }
+  p.tmem_cols = pow2ceil(p.acc_stages * p.block_n < 32 ? 32 : p.acc_stages * p.block_n);
 
   p.out = d->out; p.out_dtype = d->out_dtype; p.ldc = d->ldc; p.out_mode = d->out_mode; p.out_h = d->out_h; p.out_w = d->out_w;
   p.alpha = d->alpha; p.bias = d->bias; p.row_bias = d->row_bias; p.row_bias_div = d->row_bias_div > 0 ? d->row_bias_div : 1;
@@ -616,7 +624,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.ldres = d->ldres;
   p.accumulate = d->accumulate;
 
-  const size_t smem = 1024 + smem_data + 8 * (2 * kMaxStages + 5) + 16;
+  const size_t smem = 1024 + smem_data + 8 * (2 * kMaxStages + 2 * kMaxAcc + 2) + 16;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   const bool plain = !p.row_bias && !p.accumulate && p.out_mode == SVL_OUT_LINEAR;

@@ -98,24 +98,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_pv = ptx::make_idesc_bf16(128, 64, 0, 1);
-      const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
-      const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), pa = tmpl + (uint64_t)(sP >> 4);
-      ptx::mbar_wait(q_full, 0);
-      for (int j = 0; j < nt; ++j) {
-        const int st = j & 1, k = j >> 1;
-        ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
-        ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
-        ptx::tc_fence_after();
-        const uint64_t kd = tmpl + (uint64_t)((sK + st * kTile) >> 4), vb = tmpl + (uint64_t)((sV + st * kTile) >> 4);
+    // MMA issuer: the whole warp runs the loop, one elected lane issues, so the MMA operands stay in uniform registers
+    // (a divergent single-thread loop costs ~30 instructions per tcgen05.mma, see gemm.cu)
+    const bool leader = ptx::elect_one();
+    const uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_pv = ptx::make_idesc_bf16(128, 64, 0, 1);
+    const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
+    const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), pa = tmpl + (uint64_t)(sP >> 4);
+    ptx::mbar_wait(q_full, 0);
+    for (int j = 0; j < nt; ++j) {
+      const int st = j & 1, k = j >> 1;
+      ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
+      ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
+      ptx::tc_fence_after();
+      const uint64_t kd = tmpl + (uint64_t)((sK + st * kTile) >> 4), vb = tmpl + (uint64_t)((sV + st * kTile) >> 4);
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk > 0);
         ptx::umma_commit(s_full);
-        ptx::mbar_wait(p_full, (uint32_t)(j & 1));
-        ptx::mbar_wait(o_empty(st), (uint32_t)((k & 1) ^ 1));
-        ptx::tc_fence_after();
+      }
+      __syncwarp();
+      ptx::mbar_wait(p_full, (uint32_t)(j & 1));
+      ptx::mbar_wait(o_empty(st), (uint32_t)((k & 1) ^ 1));
+      ptx::tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
           // A: P k-block s/4 (16 KB apart), 32 bytes per 16 keys inside the swizzled row; B: V rows (keys) are the K dimension, 16 rows = 2048 bytes
@@ -125,6 +131,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         ptx::umma_commit(o_full(st));
         ptx::umma_commit(kv_empty(st));
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -328,25 +335,29 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);       // scores: both operands K-major (d contiguous)
-      const uint32_t idesc_a = ptx::make_idesc_bf16(128, 64, 0, 1);       // accumulates: B = Q / dO tile read MN-major
-      const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
-      const uint64_t kd = tmpl + (uint64_t)(sK >> 4), vd = tmpl + (uint64_t)(sV >> 4), pd = tmpl + (uint64_t)(sP >> 4), sd = tmpl + (uint64_t)(sS >> 4);
-      ptx::mbar_wait(kv_full, 0);
-      for (int j = 0; j < nt; ++j) {
-        const int st = j & 1, k = j >> 1;
-        ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));
-        ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
-        ptx::tc_fence_after();
-        const uint64_t qd = tmpl + (uint64_t)((sQ + st * kHalf) >> 4), gd = tmpl + (uint64_t)((sG + st * kHalf) >> 4);
+    const bool leader = ptx::elect_one();                                 // warp-uniform issue loop (see the forward kernel)
+    const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);       // scores: both operands K-major (d contiguous)
+    const uint32_t idesc_a = ptx::make_idesc_bf16(128, 64, 0, 1);       // accumulates: B = Q / dO tile read MN-major
+    const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
+    const uint64_t kd = tmpl + (uint64_t)(sK >> 4), vd = tmpl + (uint64_t)(sV >> 4), pd = tmpl + (uint64_t)(sP >> 4), sd = tmpl + (uint64_t)(sS >> 4);
+    ptx::mbar_wait(kv_full, 0);
+    for (int j = 0; j < nt; ++j) {
+      const int st = j & 1, k = j >> 1;
+      ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));
+      ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
+      ptx::tc_fence_after();
+      const uint64_t qd = tmpl + (uint64_t)((sQ + st * kHalf) >> 4), gd = tmpl + (uint64_t)((sG + st * kHalf) >> 4);
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base, kd + (uint64_t)(kk * 2), qd + (uint64_t)(kk * 2), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base + 64u, vd + (uint64_t)(kk * 2), gd + (uint64_t)(kk * 2), idesc_s, kk > 0);
         ptx::umma_commit(s_full);
-        ptx::mbar_wait(p_full, (uint32_t)(j & 1));
-        ptx::tc_fence_after();
+      }
+      __syncwarp();
+      ptx::mbar_wait(p_full, (uint32_t)(j & 1));
+      ptx::tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)      // K = 64 queries: A 32 bytes per 16 queries inside the row, B 16 query rows = 2048 bytes
           ptx::umma_bf16(tmem_base + 128u, pd + (uint64_t)(kk * 2), gd + (uint64_t)(kk * 128), idesc_a, (j > 0 || kk > 0) ? 1u : 0u);
@@ -356,8 +367,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         ptx::umma_commit(p_empty);
         ptx::umma_commit(q_empty(st));
       }
-      ptx::umma_commit(acc_full);
+      __syncwarp();
     }
+    if (leader) ptx::umma_commit(acc_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -491,33 +504,39 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t idesc_a = ptx::make_idesc_bf16(128, 64, 0, 1);
-      const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
-      const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), gd = tmpl + (uint64_t)(sG >> 4), sd = tmpl + (uint64_t)(sS >> 4);
-      ptx::mbar_wait(q_full, 0);
-      for (int j = 0; j < nt; ++j) {
-        const int st = j & 1, k = j >> 1;
-        ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
-        ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
-        ptx::tc_fence_after();
-        const uint64_t kd = tmpl + (uint64_t)((sK + st * kHalf) >> 4), vd = tmpl + (uint64_t)((sV + st * kHalf) >> 4);
+    const bool leader = ptx::elect_one();                                 // warp-uniform issue loop (see the forward kernel)
+    const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc_a = ptx::make_idesc_bf16(128, 64, 0, 1);
+    const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
+    const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), gd = tmpl + (uint64_t)(sG >> 4), sd = tmpl + (uint64_t)(sS >> 4);
+    ptx::mbar_wait(q_full, 0);
+    for (int j = 0; j < nt; ++j) {
+      const int st = j & 1, k = j >> 1;
+      ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
+      ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
+      ptx::tc_fence_after();
+      const uint64_t kd = tmpl + (uint64_t)((sK + st * kHalf) >> 4), vd = tmpl + (uint64_t)((sV + st * kHalf) >> 4);
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base + 64u, gd + (uint64_t)(kk * 2), vd + (uint64_t)(kk * 2), idesc_s, kk > 0);
         ptx::umma_commit(s_full);
-        ptx::mbar_wait(p_full, (uint32_t)(j & 1));
-        ptx::tc_fence_after();
+      }
+      __syncwarp();
+      ptx::mbar_wait(p_full, (uint32_t)(j & 1));
+      ptx::tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)      // dQ += dS K : K dimension = the 64 keys (K tile read MN-major, 16 key rows = 2048 bytes)
           ptx::umma_bf16(tmem_base + 128u, sd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 128), idesc_a, (j > 0 || kk > 0) ? 1u : 0u);
         ptx::umma_commit(p_empty);
         ptx::umma_commit(kv_empty(st));
       }
-      ptx::umma_commit(acc_full);
+      __syncwarp();
     }
+    if (leader) ptx::umma_commit(acc_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;

@@ -126,29 +126,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t accum = 0;
-        for (int t = tap0; t < tap1; ++t) {
-          for (int64_t kb = kb0; kb < kb1; ++kb) {
-            ptx::mbar_wait(full_bar(stage), phase);
-            ptx::tc_fence_after();
-            const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
-            const uint64_t adesc = ptx::make_smem_desc(sa, kBoxBytes, 1024), bdesc = ptx::make_smem_desc(sb, kBoxBytes, 1024);
+      // whole warp in the loop, one elected lane issues: the MMA operands stay in uniform registers (see gemm.cu)
+      const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
+      const bool leader = ptx::elect_one();
+      const uint64_t tmpl = ptx::make_smem_desc(0, kBoxBytes, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accum = 0;
+      for (int t = tap0; t < tap1; ++t) {
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = tmpl + (uint64_t)((smem_a + stage * a_stage) >> 4), bdesc = tmpl + (uint64_t)((smem_b + stage * b_stage) >> 4);
+          if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < KB / 16; ++kk) {
-              // 16 K-rows = 2048 bytes further into every chunk
-              ptx::umma_bf16(tmem_base, adesc + (uint64_t)(kk * 128), bdesc + (uint64_t)(kk * 128), idesc, accum);
-              accum = 1;
-            }
+            for (int kk = 0; kk < KB / 16; ++kk)   // 16 K-rows = 2048 bytes further into every chunk
+              ptx::umma_bf16(tmem_base, adesc + (uint64_t)(kk * 128), bdesc + (uint64_t)(kk * 128), idesc, kk > 0 ? 1u : accum);
             ptx::umma_commit(empty_bar(stage));
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          accum = 1;
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar);
       }
+      if (leader) ptx::umma_commit(tfull_bar);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       const int i = m_tile * BM + q * 32 + lane;       // output row (dy channel)
@@ -207,6 +209,7 @@ struct StripParams {
   int stages, tmem_cols, bo_mode;
   float* dw; int64_t ld_dw, slot_stride;
   float alpha;
+  uint32_t mma_boff[8][kMaxGroupTaps * (KB / 16)], mma_dcol[8][kMaxGroupTaps * (KB / 16)];   // per group: B offset (16-byte units) / TMEM column of each MMA
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -283,47 +286,42 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
-        // The issuing thread is alone: every integer instruction in this loop is exposed latency.  All descriptor arithmetic is
-        // hoisted: per (tap, K step) a descriptor relative to the stage base, per stage one 64-bit add.
-        uint64_t bdesc0[kMaxGroupTaps][KB / 16], adesc0[KB / 16];
+      // whole warp in the loop, one elected lane issues: the MMA operands stay in uniform registers (see gemm.cu).
+      // B descriptors: per (tap, K step) an offset inside the strip (constant bank, host-built) added to the stage base.
+      const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
+      const bool leader = ptx::elect_one();
+      const uint64_t tmpl_b = ptx::make_smem_desc(0, p.strip_stride, 1024);
+      const uint64_t tmpl_a = ptx::make_smem_desc(0, kBoxBytes, 1024);
+      const int nmma = ntaps * (KB / 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accum = 0;
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
+        uint64_t adesc[KB / 16];
 #pragma unroll
-        for (int ti = 0; ti < kMaxGroupTaps; ++ti) {
-          const int shift = ti < ntaps ? p.g_dx[grp][ti] - p.g_dxmin[grp] : 0;
-#pragma unroll
-          for (int kk = 0; kk < KB / 16; ++kk) {
-            const int prow = kk * 16;
-            const int srow = (prow / p.bw) * p.strip_w + (prow % p.bw) + shift;
-            bdesc0[ti][kk] = ptx::make_smem_desc((uint32_t)srow * 128u, p.strip_stride, 1024);
-          }
+        for (int kk = 0; kk < KB / 16; ++kk) {
+          // the zero chunk (a_chunks == 1) is shared by all K steps: its offset must not advance with kk
+          adesc[kk] = p.a_chunks == 2 ? tmpl_a + (uint64_t)((sa + kk * 2048) >> 4) : ptx::make_smem_desc(sa + kk * 2048, zero_buf - sa - kk * 2048, 1024);
         }
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t accum = 0;
-        for (int64_t kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
-          const uint32_t a_lbo = p.a_chunks == 2 ? kBoxBytes : (zero_buf - sa);
+        const uint64_t bbase = tmpl_b + (uint64_t)(sb >> 4);
+        if (leader) {
+          for (int i = 0; i < nmma; i += KB / 16) {
+            const uint32_t td = tmem_base + p.mma_dcol[grp][i];
 #pragma unroll
-          for (int kk = 0; kk < KB / 16; ++kk)   // the zero chunk (a_chunks == 1) is shared by all K steps: its offset must not advance with kk
-            adesc0[kk] = ptx::make_smem_desc(sa + kk * 2048, p.a_chunks == 2 ? a_lbo : a_lbo - kk * 2048, 1024);
-          const uint64_t sb16 = (uint64_t)(sb >> 4);
-#pragma unroll
-          for (int ti = 0; ti < kMaxGroupTaps; ++ti) {
-            if (ti < ntaps) {
-#pragma unroll
-              for (int kk = 0; kk < KB / 16; ++kk)
-                ptx::umma_bf16(tmem_base + (uint32_t)(ti * p.block_n), adesc0[kk], bdesc0[ti][kk] + sb16, idesc, kk > 0 ? 1u : accum);
-            }
+            for (int kk = 0; kk < KB / 16; ++kk)
+              ptx::umma_bf16(td, adesc[kk], bbase + (uint64_t)p.mma_boff[grp][i + kk], idesc, kk > 0 ? 1u : accum);
           }
-          accum = 1;
           ptx::umma_commit(empty_bar(stage));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar);
+        accum = 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (leader) ptx::umma_commit(tfull_bar);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       const int i = m_tile * BM + q * 32 + lane;
@@ -363,6 +361,24 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+}
+
+// Split-K factor: one CTA per SM is resident, so the kernel runs in ceil(tiles * s / SMs) rounds of (K / s) each.  Pick the s (at most
+// ~3 rounds, at least 8 K blocks per CTA) that minimises rounds / s: a grid of 2 * SMs + 1 CTAs costs three rounds, not two.
+int pick_splits(int64_t tiles, int64_t num_kblocks) {
+  const int64_t sms = num_sms();
+  int64_t cap = num_kblocks / 8 > 0 ? num_kblocks / 8 : 1;
+  int64_t smax = (3 * sms + tiles - 1) / tiles;
+  if (smax > cap) smax = cap;
+  if (smax < 1) smax = 1;
+  int64_t best = 1;
+  double best_cost = 1e30;
+  for (int64_t s = 1; s <= smax; ++s) {
+    const int64_t rounds = (tiles * s + sms - 1) / sms;
+    const double cost = (double)rounds / (double)s + 1e-4 * (double)s;      // tie-break towards fewer partial sums
+    if (cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return (int)best;
 }
 
 // Returns 1 when the strip kernel was launched, 0 when the problem does not qualify, < 0 on error.
@@ -419,6 +435,14 @@ int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) 
   p.strip_stride = ((uint32_t)p.strip_rows * 128u + 1023u) & ~1023u;
   p.a_chunks = d->m <= 64 ? 1u : 2u;
   p.bo_mode = mode;
+  for (int g = 0; g < p.ngroups; ++g)
+    for (int ti = 0; ti < p.g_ntaps[g]; ++ti)
+      for (int kk = 0; kk < KB / 16; ++kk) {
+        const int prow = kk * 16;                  // 16 K-rows (pixels) per MMA; a K block may span several image rows of the strip
+        const int srow = (prow / p.bw) * p.strip_w + (prow % p.bw) + (p.g_dx[g][ti] - p.g_dxmin[g]);
+        p.mma_boff[g][ti * (KB / 16) + kk] = ((uint32_t)srow * 128u) >> 4;
+        p.mma_dcol[g][ti * (KB / 16) + kk] = (uint32_t)(ti * block_n);
+      }
   p.dw = d->dw; p.ld_dw = d->ld_dw; p.slot_stride = d->slot_stride;
   p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
   const uint32_t stage_bytes = p.a_chunks * kBoxBytes + (uint32_t)(block_n / 64) * p.strip_stride;
@@ -442,12 +466,7 @@ int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) 
   }
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * p.ngroups;
   int splits = d->splits;
-  if (splits <= 0) {
-    int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles;
-    int64_t cap = p.num_kblocks / 8 > 0 ? p.num_kblocks / 8 : 1;
-    splits = (int)(want < cap ? want : cap);
-    if (splits < 1) splits = 1;
-  }
+  if (splits <= 0) splits = pick_splits(tiles, p.num_kblocks);
   if (splits > p.num_kblocks) splits = (int)p.num_kblocks;
   p.splits = splits;
   const size_t smem = 1024 + (size_t)p.stages * stage_bytes + kBoxBytes + 8 * (2 * kMaxStages + 2) + 16;
@@ -548,13 +567,7 @@ extern "C" int svl_wgrad(const svl_wgrad_desc* d, void* stream) {
 
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * p.num_slots;
   int splits = d->splits;
-  if (splits <= 0) {
-    // fill ~2 waves of the machine, but keep at least 8 K blocks per CTA
-    int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles;
-    int64_t cap = p.num_kblocks / 8 > 0 ? p.num_kblocks / 8 : 1;
-    splits = (int)(want < cap ? want : cap);
-    if (splits < 1) splits = 1;
-  }
+  if (splits <= 0) splits = pick_splits(tiles, p.num_kblocks);
   if (splits > p.num_kblocks) splits = (int)p.num_kblocks;
   p.splits = splits;
 

@@ -54,18 +54,25 @@ struct GemmParams {
   uint32_t strip_bytes, b_tile_bytes;
 };
 
+// Position of tile row r inside a conv tile box (tile-invariant: computed once per thread, the divisions are not repeated per tile)
+struct RowInBox { int ix, iy, in; };
+__device__ __forceinline__ RowInBox row_in_box(const GemmParams& p, int r) {
+  RowInBox b = {0, 0, 0};
+  if (p.a_conv) { b.ix = r % p.bw; b.iy = (r / p.bw) % p.bh; b.in = r / (p.bw * p.bh); }
+  return b;
+}
 // global row index of tile row r, or -1 when the row is padding
-__device__ __forceinline__ int64_t tile_row_to_global(const GemmParams& p, int m_tile, int r) {
+__device__ __forceinline__ int64_t tile_row_to_global(const GemmParams& p, int m_tile, int r, const RowInBox& b) {
   if (!p.a_conv) {
     int64_t g = (int64_t)m_tile * BM + r;
     return g < p.m ? g : -1;
   }
-  int tx = m_tile % p.tiles_x;
-  int ty = (m_tile / p.tiles_x) % p.tiles_y;
-  int tn = m_tile / (p.tiles_x * p.tiles_y);
-  int ix = r % p.bw, iy = (r / p.bw) % p.bh, in = r / (p.bw * p.bh);
-  int x = tx * p.bw + ix, y = ty * p.bh + iy, img = tn * p.bn + in;
-  if (in >= p.bn || x >= p.w || y >= p.h || img >= p.nb) return -1;
+  const int t2 = m_tile / p.tiles_x;
+  const int tx = m_tile - t2 * p.tiles_x;
+  const int tn = t2 / p.tiles_y;
+  const int ty = t2 - tn * p.tiles_y;
+  int x = tx * p.bw + b.ix, y = ty * p.bh + b.iy, img = tn * p.bn + b.in;
+  if (b.in >= p.bn || x >= p.w || y >= p.h || img >= p.nb) return -1;
   return ((int64_t)img * p.h + y) * p.w + x;
 }
 
@@ -106,7 +113,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < p.acc_stages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 4 * kEpiGroups);
+      ptx::mbar_init(tempty_bar(s), 4 * (p.block_n < kEpiGroups * 32 ? (p.block_n + 31) / 32 : kEpiGroups));
     }
     ptx::mbar_init(wbar, 1);
     ptx::fence_barrier_init();
@@ -244,10 +251,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int cq = p.out_mode == SVL_OUT_CONVT2X2 ? p.n / 4 : 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const RowInBox rib = row_in_box(p, r);
+    // column groups without a 32-column chunk of this block_n (narrow conv outputs) take no part: the accumulator-free barrier counts
+    // only the active groups
+    const bool active = cgrp * 32 < p.block_n;
+    for (int tile = active ? blockIdx.x : num_tiles; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
       const int n0 = n_tile * p.block_n;
-      const int64_t grow = tile_row_to_global(p, m_tile, r);
+      const int64_t grow = tile_row_to_global(p, m_tile, r, rib);
       int64_t ct_base = 0;                  // CONVT2X2: element offset of output pixel (2y, 2x), channel 0
       if (cq && grow >= 0) {
         int64_t hw = (int64_t)p.out_h * p.out_w;

@@ -103,16 +103,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        // K-block -> box origin: one division at the start, then counters (a 64-bit division per K block made this lone thread,
+        // not the tensor pipe, the bound of the narrow-channel convolutions)
+        const int tx0 = p.conv ? (int)(kb0 % p.tiles_x) : 0;
+        const int ty0 = p.conv ? (int)((kb0 / p.tiles_x) % p.tiles_y) : 0;
+        const int tn0 = p.conv ? (int)(kb0 / ((int64_t)p.tiles_x * p.tiles_y)) : 0;
         for (int t = tap0; t < tap1; ++t) {
+          int tx = tx0, ty = ty0, tn = tn0;
           for (int64_t kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
             ptx::mbar_arrive_expect_tx(full_bar(stage), p.k_tx_bytes * (2 + nchunks_b));
             const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
             const int ca = p.tap_dy_koff[t] + m_tile * BM, cb = p.tap_x_koff[t] + n_tile * p.block_n;
             if (p.conv) {
-              const int cx = (int)(kb % p.tiles_x) * p.bw;
-              const int cy = (int)((kb / p.tiles_x) % p.tiles_y) * p.bh;
-              const int cn = (int)(kb / ((int64_t)p.tiles_x * p.tiles_y)) * p.bn;
+              const int cx = tx * p.bw, cy = ty * p.bh, cn = tn * p.bn;
+              if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++tn; } }
               for (int c = 0; c < 2; ++c) ptx::tma_load_4d(sa + c * kBoxBytes, &tmDY, full_bar(stage), ca + c * 64, cx, cy, cn);
               for (int c = 0; c < nchunks_b; ++c)
                 ptx::tma_load_4d(sb + c * kBoxBytes, &tmX, full_bar(stage), cb + c * 64, cx + p.tap_dx[t], cy + p.tap_dy[t], cn);
@@ -272,13 +277,13 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         uint32_t phase = 0;
         const uint32_t tx = p.a_chunks * kBoxBytes + (uint32_t)nchunks_b * (uint32_t)p.strip_rows * 128u;
         const int ca = p.dy_koff + m_tile * BM, cb = p.x_koff + n_tile * p.block_n;
+        int tix = (int)(kb0 % p.tiles_x), tiy = (int)((kb0 / p.tiles_x) % p.tiles_y), tin = (int)(kb0 / ((int64_t)p.tiles_x * p.tiles_y));
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           ptx::mbar_arrive_expect_tx(full_bar(stage), tx);
           const uint32_t sa = smem_a + stage * a_stage, sb = smem_b + stage * b_stage;
-          const int cx = (int)(kb % p.tiles_x) * p.bw;
-          const int cy = (int)((kb / p.tiles_x) % p.tiles_y) * p.bh;
-          const int cn = (int)(kb / ((int64_t)p.tiles_x * p.tiles_y)) * p.bn;
+          const int cx = tix * p.bw, cy = tiy * p.bh, cn = tin * p.bn;      // counters instead of a 64-bit division per K block
+          if (++tix == p.tiles_x) { tix = 0; if (++tiy == p.tiles_y) { tiy = 0; ++tin; } }
           for (uint32_t c = 0; c < p.a_chunks; ++c) ptx::tma_load_4d(sa + c * kBoxBytes, &tmDY, full_bar(stage), ca + (int)c * 64, cx, cy, cn);
           for (int c = 0; c < nchunks_b; ++c)
             ptx::tma_load_4d(sb + c * p.strip_stride, &tmX, full_bar(stage), cb + c * 64, cx + p.g_dxmin[grp], cy + p.g_dy[grp], cn);

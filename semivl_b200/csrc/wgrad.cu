@@ -212,6 +212,7 @@ struct StripParams {
   int strip_w, strip_rows;
   uint32_t strip_stride, a_chunks;
   int stages, tmem_cols, bo_mode;
+  int npack, dxstep, g_nmma[8];      // npack: the taps of a group are 64-column chunks of ONE MMA (B chunk stride = dxstep pixels)
   float* dw; int64_t ld_dw, slot_stride;
   float alpha;
   uint32_t mma_boff[8][kMaxGroupTaps * (KB / 16)], mma_dcol[8][kMaxGroupTaps * (KB / 16)];   // per group: B offset (16-byte units) / TMEM column of each MMA
@@ -293,11 +294,14 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
     } else if (warp == 1) {
       // whole warp in the loop, one elected lane issues: the MMA operands stay in uniform registers (see gemm.cu).
       // B descriptors: per (tap, K step) an offset inside the strip (constant bank, host-built) added to the stage base.
-      const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 1, 1);
+      // Tap packing (npack): the dx taps of the group are equally spaced, so tap t of the strip is the SAME strip read `t * dxstep`
+      // K-rows (pixels) further.  An MN-major B operand is a sequence of 64-column chunks `LBO` bytes apart: with LBO = dxstep * 128
+      // bytes chunk t IS tap t, and one MMA of N = 64 * ntaps accumulates all taps of the filter row (A is read once, not per tap).
+      const uint32_t idesc = ptx::make_idesc_bf16(BM, p.npack ? 64 * ntaps : p.block_n, 1, 1);
       const bool leader = ptx::elect_one();
-      const uint64_t tmpl_b = ptx::make_smem_desc(0, p.strip_stride, 1024);
+      const uint64_t tmpl_b = ptx::make_smem_desc(0, p.npack ? (uint32_t)p.dxstep * 128u : p.strip_stride, 1024);
       const uint64_t tmpl_a = ptx::make_smem_desc(0, kBoxBytes, 1024);
-      const int nmma = ntaps * (KB / 16);
+      const int nmma = p.g_nmma[grp];
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accum = 0;
@@ -338,7 +342,8 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           if (n0 + c0 >= p.n) break;
           uint32_t v[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ti * p.block_n + c0), v);
+          const int tcol = p.npack ? ((c0 >> 6) * ntaps + ti) * 64 + (c0 & 63) : ti * p.block_n + c0;
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, v);
           ptx::tmem_ld_wait();
           if (i >= p.m) continue;
 #pragma unroll
@@ -426,7 +431,17 @@ int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) 
     for (int k = 0; k < p.g_ntaps[g]; ++k) span = span > p.g_dx[g][k] - p.g_dxmin[g] ? span : p.g_dx[g][k] - p.g_dxmin[g];
     max_taps = max_taps > p.g_ntaps[g] ? max_taps : p.g_ntaps[g];
   }
-  if (max_taps * block_n > 512 || p.bw + span > 256) return 0;
+  // tap packing needs every group to hold the same number of taps, ascending and equally spaced
+  p.npack = max_taps >= 2 && (block_n / 64 > 0 ? block_n / 64 : 1) * max_taps * 64 <= 512 && block_n % 64 == 0 ? 1 : 0;
+  p.dxstep = p.g_ntaps[0] >= 2 ? p.g_dx[0][1] - p.g_dx[0][0] : 1;
+  for (int g = 0; g < p.ngroups && p.npack; ++g) {
+    if (p.g_ntaps[g] != max_taps) p.npack = 0;
+    for (int k = 0; k < p.g_ntaps[g] && p.npack; ++k)
+      if (p.g_dx[g][k] != p.g_dxmin[g] + k * p.dxstep) p.npack = 0;
+  }
+  if (p.dxstep < 1 || p.dxstep * 128 >= (1 << 18)) p.npack = 0;
+  if (const char* e = getenv("SVL_WGRAD_PACK")) if (atoi(e) == 0) p.npack = 0;
+  if ((!p.npack && max_taps * block_n > 512) || p.bw + span > 256) return 0;
   p.nb = d->nb; p.h = d->h; p.w = d->w;
   p.tiles_x = (d->w + p.bw - 1) / p.bw;
   p.tiles_y = (d->h + p.bh - 1) / p.bh;
@@ -440,21 +455,25 @@ int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) 
   p.strip_stride = ((uint32_t)p.strip_rows * 128u + 1023u) & ~1023u;
   p.a_chunks = d->m <= 64 ? 1u : 2u;
   p.bo_mode = mode;
-  for (int g = 0; g < p.ngroups; ++g)
-    for (int ti = 0; ti < p.g_ntaps[g]; ++ti)
+  for (int g = 0; g < p.ngroups; ++g) {
+    const int outer = p.npack ? block_n / 64 : p.g_ntaps[g];      // packed: one MMA group per 64-channel chunk of x; else one per tap
+    for (int o = 0; o < outer; ++o)
       for (int kk = 0; kk < KB / 16; ++kk) {
         const int prow = kk * 16;                  // 16 K-rows (pixels) per MMA; a K block may span several image rows of the strip
-        const int srow = (prow / p.bw) * p.strip_w + (prow % p.bw) + (p.g_dx[g][ti] - p.g_dxmin[g]);
-        p.mma_boff[g][ti * (KB / 16) + kk] = ((uint32_t)srow * 128u) >> 4;
-        p.mma_dcol[g][ti * (KB / 16) + kk] = (uint32_t)(ti * block_n);
+        const int shift = p.npack ? 0 : p.g_dx[g][o] - p.g_dxmin[g];
+        const int srow = (prow / p.bw) * p.strip_w + (prow % p.bw) + shift;
+        p.mma_boff[g][o * (KB / 16) + kk] = ((uint32_t)srow * 128u + (p.npack ? (uint32_t)o * p.strip_stride : 0u)) >> 4;
+        p.mma_dcol[g][o * (KB / 16) + kk] = (uint32_t)(p.npack ? o * p.g_ntaps[g] * 64 : o * block_n);
       }
+    p.g_nmma[g] = outer * (KB / 16);
+  }
   p.dw = d->dw; p.ld_dw = d->ld_dw; p.slot_stride = d->slot_stride;
   p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
   const uint32_t stage_bytes = p.a_chunks * kBoxBytes + (uint32_t)(block_n / 64) * p.strip_stride;
   p.stages = (int)((kSmemBudget - kBoxBytes) / stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return 0;
-  p.tmem_cols = pow2ceil(max_taps * block_n < 32 ? 32 : max_taps * block_n);
+  p.tmem_cols = p.npack ? pow2ceil((block_n / 64) * max_taps * 64) : pow2ceil(max_taps * block_n < 32 ? 32 : max_taps * block_n);
 
   const int64_t dy_cols = d->dy_cols > 0 ? d->dy_cols : d->ld_dy;
   const int64_t x_cols = d->x_cols > 0 ? d->x_cols : d->ld_x;

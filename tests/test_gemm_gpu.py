@@ -187,7 +187,8 @@ def test_wgrad_linear(ops, rows, m, n, precise):
 
 @pytest.mark.parametrize("nb,h,w,cin,cout,ks,dil", [(5, 12, 12, 64, 48, 3, 2), (7, 32, 32, 128, 128, 3, 6), (3, 64, 64, 128, 64, 3, 1),
                                                      (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
-                                                     (4, 8, 8, 256, 64, 1, 1)])
+                                                     (4, 8, 8, 256, 64, 1, 1), (2, 128, 128, 64, 32, 3, 1), (3, 64, 64, 96, 64, 3, 1),
+                                                     (2, 32, 32, 256, 128, 3, 1)])
 @pytest.mark.parametrize("precise", [False, True])
 def test_wgrad_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
     g = torch.Generator(device="cuda").manual_seed(nb * h + cin + cout)

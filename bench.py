@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--nclass", type=int, default=NCLASS)
     ap.add_argument("--precise", action="store_true", help="split-bf16 parity mode instead of the bf16 throughput mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the ~690 kernels of the step eagerly instead of replaying the captured CUDA graph (N=1)")
     ap.add_argument("--cpu-crop", type=int, default=CROP)
     return ap.parse_args()
 
@@ -171,9 +172,13 @@ def main():
     host = synth_batch(torch, b, args.crop, args.nclass, 1234 + rank, "cuda", semivl)
     resident = {k: v.to(dev) for k, v in host.items()}
 
+    use_graph = world == 1 and not semivl and not args.no_graph and args.crop % 16 == 0
+
     def step(batch):
         if semivl:
             return tr.semivl_step(batch)[0]
+        if use_graph and ops.PROFILE is None:         # the instrumented steps (events around each contraction) run eagerly
+            return tr.graphed_supervised_step(batch["img_x"], batch["mask_x"])
         return tr.supervised_step(batch["img_x"], batch["mask_x"])
 
     def barrier():
@@ -198,36 +203,65 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (L.launches - l0) // args.steps
-    # ---- end-to-end region: host (pinned) buffers, H2D inside, loss read back every step
+    # ---- end-to-end region: host (pinned) buffers; every step's inputs cross PCIe inside the timed region and the loss is read
+    # back every step.  The copies are double-buffered on a copy stream (what a pinned-memory data loader does): the H2D of step
+    # i+1 runs under the kernels of step i, each step waits for its own inputs.
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    stage = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    stages = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])              # the step that last read this staging buffer has finished
+            for k, v in host.items():
+                stages[i % 2][k].copy_(v, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
     barrier()
+    for ev in consumed:
+        ev.record()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        for k, v in host.items():
-            stage[k].copy_(v, non_blocking=True)
-        lv = float(step(stage).item())
+    upload(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            upload(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        out = step(stages[i % 2])
+        consumed[i % 2].record()
+        lv = float(out.item())
     f1.record()
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3) / args.steps
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-    # ---- instrumented step: CUDA events around every tensor-core contraction launch (roofline of the dominant kernel)
+    # ---- instrumented steps: CUDA events (on the launching stream) around every tensor-core contraction launch
     ops.PROFILE = []
-    step(resident)
+    n_inst = 2
+    for _ in range(n_inst):
+        step(resident)
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(bv) for a, bv, _, _ in ops.PROFILE)
-    gemm_flops = sum(f for _, _, f, _ in ops.PROFILE)
-    n_gemm = len(ops.PROFILE)
+    prof = [(a.elapsed_time(bv), f, lab) for a, bv, f, lab in ops.PROFILE]
+    ops.PROFILE = None
+    gemm_ms = sum(t_ for t_, _, _ in prof) / n_inst
+    gemm_flops = sum(f for _, f, _ in prof) / n_inst
+    n_gemm = len(prof) // n_inst
+    by_shape = {}
+    for t_, f, lab in prof:
+        e = by_shape.setdefault(lab, [0, 0.0, 0.0])
+        e[0] += 1
+        e[1] += t_
+        e[2] += f
+    dom_label, dom = max(by_shape.items(), key=lambda kv: kv[1][1])         # the launch shape with the largest share of the step
+    dom_n, dom_ms, dom_fl = dom[0] / n_inst, dom[1] / n_inst, dom[2] / n_inst
     if os.environ.get("SVL_PROFILE_DUMP") and rank == 0:
         with open(os.environ["SVL_PROFILE_DUMP"], "w") as fh:
-            for a, bv, f, lab in ops.PROFILE:
-                t_ms = a.elapsed_time(bv)
+            for t_ms, f, lab in prof[:n_gemm]:
                 fh.write(f"{t_ms * 1e3:10.1f} us {f / t_ms / 1e9 if t_ms > 0 else 0:8.1f} TF/s  {lab}\n")
-    ops.PROFILE = None
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -243,6 +277,12 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    dom_tf = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = {}
+    try:        # DRAM bytes per launch of the dominant shape, from the committed `ncu --set full` capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dom_label, {})
+    except Exception:
+        pass
     unit_gf = GF_PER_UNIT_SEMIVL if semivl else GF_PER_IMG_SUPERVISED
     step_tf = unit_gf * b / 1e3
     value = world * b / (ms / 1e3)
@@ -252,17 +292,23 @@ def main():
         "data": "synthetic",
         "config": {"workload": (f"VOC {args.nclass}-class synthetic {args.crop}x{args.crop} ViT-B/16+VLG head, "
                                 + ("full SemiVL consistency step" if semivl else "supervised step fwd+bwd+AdamW")),
-                   "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
+                   "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}",
+                   "launch": "one CUDA-graph replay per step" if use_graph else "eager kernel launches", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
                    "weights": "random init (reference init_weights)", "loss": float(loss.item())},
         "e2e": {"value": world * b / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "last_loss": lv},
         "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None,
-        "roofline": {"bound": "tensor", "kernel": "gemm_kernel/wgrad_kernel (tcgen05 contraction engine)", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "launches": n_gemm,
-                     "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / ms if ms else None,
-                     "measured_on": "one instrumented step after the timed region (CUDA events around every contraction launch)",
+        "roofline": {"bound": "tensor", "kernel": f"gemm_kernel [{dom_label}] (persistent TMA + tcgen05 GEMM, csrc/gemm.cu)",
+                     "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf if peak_tf else None,
+                     "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                     "algorithmic_flops_per_launch": dom_fl / dom_n, "algorithmic_bytes_per_launch": traffic.get("algorithmic_bytes_per_launch"),
+                     "avg_launch_us": 1e3 * dom_ms / dom_n, "launches_per_step": dom_n, "share_of_step": dom_ms / ms if ms else None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                     "measured_on": f"{n_inst} instrumented steps after the timed region (CUDA events on the launching stream around every contraction launch)",
+                     "engine": {"what": "all gemm_kernel / wgrad_kernel / wgrad_strip_kernel launches of the step", "launches": n_gemm,
+                                "achieved": achieved_tf, "frac": achieved_tf / peak_tf if peak_tf else None, "ms_per_step": gemm_ms,
+                                "share_of_step": gemm_ms / ms if ms else None},
                      "whole_step_algorithmic_tflops": step_tf / (ms / 1e3), "whole_step_frac": step_tf / (ms / 1e3) / peak_tf},
     }
     if not args.no_cpu_baseline and world == 1:

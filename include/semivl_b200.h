@@ -242,10 +242,26 @@ int svl_reciprocal(const float* count, float* out, float numer, float floor_, vo
 int svl_cutmix_weights(const int64_t* lab_a, const int64_t* lab_b, const float* conf_a, const float* conf_b, const int64_t* ign_a,
                        const int64_t* ign_b, const float* box, int64_t* lab_out, float* w_out, int64_t* ign_out, float* valid_count,
                        int64_t n, float thresh, void* stream);
+/* Confidence modes 'pixelratio' / 'pixelavg' of confidence_weighted_loss (utils/train_utils.py:40-46), no host sync:
+ * svl_conf_stats: per image b of the CutMixed (conf, ignore) maps, stats[3b..3b+2] += {#valid, #(conf >= thresh & valid), sum(conf * valid)}
+ *                 (box == NULL: the first pair unmixed);
+ * svl_conf_coef : mode 0 pixelwise  coef = numer / sum_b #valid_b
+ *                 mode 1 pixelratio coef = numer / sum_b #valid_b and row_w[b] = #high_b / #valid_b
+ *                 mode 2 pixelavg   coef = numer * sum_b(sumconf_b / #valid_b) / sum_b #valid_b;
+ * svl_fill_rows : w[b, :] = row_w[b] (per-image weight as the per-pixel weight map svl_upsample_ce takes). */
+int svl_conf_stats(const float* conf_a, const float* conf_b, const int64_t* ign_a, const int64_t* ign_b, const float* box, float* stats,
+                   int B, int64_t hw, float thresh, void* stream);
+int svl_conf_coef(const float* stats, int B, int mode, float numer, float* coef, float* row_w, void* stream);
+int svl_fill_rows(float* w, const float* row_w, int B, int64_t hw, void* stream);
 int svl_cutmix_img(const float* a, const float* b, const float* box, float* out, int B, int C, int64_t hw, void* stream);
 /* torch.optim.AdamW single-tensor update on a flat buffer (semivl.py:326-328; experiments.py:246-255); g is scaled by gscale first */
 int svl_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
               int step, float gscale, void* stream);
+
+/* svl_adamw with the per-step scalars in DEVICE memory: hyper = {lr of class 0, lr of class 1, 1 - beta1^t, sqrt(1 - beta2^t)};
+ * lets a captured CUDA graph of the whole training step be replayed under the poly LR schedule (semivl.py:338-345). */
+int svl_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int lr_index, float beta1, float beta2,
+                  float eps, float wd, float gscale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -101,7 +101,7 @@ def forward_fixture(name, crop, b, seed, nclass=21):
     print(name, "loss", loss.item(), "ngrads", len(out["grad_names"]))
 
 
-def step_fixture(name, crop, b, seed, nclass=21):
+def step_fixture(name, crop, b, seed, nclass=21, hp_over=None):
     """semivl.py:224-323 driven on the reference model with injected dropout2d masks."""
     m, mc, sd = build(crop, nclass)
     import model.builder as ref_builder
@@ -111,6 +111,7 @@ def step_fixture(name, crop, b, seed, nclass=21):
     drop_masks = [(torch.rand(2 * b, c, 1, 1, generator=g) >= 0.5).float() for c in (768, 768, 512)]
     hp = dict(conf_thresh=1.0 / nclass + 2e-3, conf_mode="pixelwise", mcc_conf_thresh=1.0 / nclass + 1e-3,
               mcc_loss_reduce="mean_all", mcc_lambda=0.07)
+    hp.update(hp_over or {})
     cfgd = dict(conf_mode=hp["conf_mode"], conf_thresh=hp["conf_thresh"])
 
     calls = {"i": 0}
@@ -153,9 +154,17 @@ def step_fixture(name, crop, b, seed, nclass=21):
             loss_s1 = confidence_weighted_loss(cu(pred_s1, mm1), cm1, im1, cfgd)
             loss_s2 = confidence_weighted_loss(cu(pred_s2, mm2), cm2, im2, cfgd)
             loss_fp = confidence_weighted_loss(cu(pred_w_fp, mask_w), conf_w, bt["ignore_mask"], cfgd)
-            l_mc1 = cmc(pred_s1, mc1).sum() / im1.numel()
-            l_mc2 = cmc(pred_s2, mc2).sum() / im2.numel()
-            l_mcf = cmc(pred_w_fp, mclip).sum() / bt["ignore_mask"].numel()
+
+            def compute_mc_loss(pred, mask, ign):            # semivl.py:52-58 (module-level there, bound to __main__ globals)
+                if hp["mcc_loss_reduce"] == "mean":
+                    return torch.nn.CrossEntropyLoss(ignore_index=255)(pred, mask)
+                l_mc = cmc(pred, mask)
+                if hp["mcc_loss_reduce"] == "mean_valid":
+                    return l_mc.sum() / (ign != 255).sum()
+                return l_mc.sum() / ign.numel()
+            l_mc1 = compute_mc_loss(pred_s1, mc1, im1)
+            l_mc2 = compute_mc_loss(pred_s2, mc2, im2)
+            l_mcf = compute_mc_loss(pred_w_fp, mclip, bt["ignore_mask"])
             lam = hp["mcc_lambda"]
             loss = (loss_x + loss_s1 * 0.25 + loss_s2 * 0.25 + loss_fp * 0.5) / 2.0
             loss = loss + l_mc1 * 0.25 * lam + l_mc2 * 0.25 * lam + l_mcf * 0.5 * lam
@@ -184,6 +193,9 @@ def main():
     forward_fixture("fwd_c224_b1", 224, 1, seed=13)        # BASELINE config 1
     step_fixture("step_c64_b1", 64, 1, seed=21)            # full SemiVL iteration (semivl.py:224-323)
     step_fixture("step_c96_b2", 96, 2, seed=22)
+    # Cityscapes-style loss modes (experiments.py:451 conf_mode='pixelavg'; train_utils.py:40-46; semivl.py:52-58)
+    step_fixture("step_c64_b2_pixelavg_mv", 64, 2, seed=23, hp_over=dict(conf_mode="pixelavg", mcc_loss_reduce="mean_valid"))
+    step_fixture("step_c64_b2_pixelratio_mean", 64, 2, seed=24, hp_over=dict(conf_mode="pixelratio", mcc_loss_reduce="mean"))
 
 
 if __name__ == "__main__":

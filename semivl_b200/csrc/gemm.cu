@@ -5,6 +5,9 @@
 //   warps 2..9  : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global); warp w owns TMEM lane
 //                 quarter w % 4 and every other 32-column chunk
 //
+// Tile order: N fastest.  The CTAs that run concurrently then cover (#SMs / n_tiles) row blocks x all column blocks, so each A row
+// block is fetched from HBM once and served to its other column blocks by L2 (with M fastest the K = 3072 FFN GEMMs streamed the
+// 100 MB A operand once per column block: 350 MB of DRAM reads per launch instead of 155 MB, profiles/r01_ncu_targets.md).
 // Accumulators are double-buffered in TMEM (2 x block_n columns) so the epilogue of tile i overlaps the main
 // loop of tile i+1.  Tile = 128 output rows x block_n columns, K step 64 (one 128-byte swizzle row).
 // In conv mode the 128 rows of a tile are a (bn images x bh rows x bw columns) box of an NHWC tensor, fetched with a
@@ -146,7 +149,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;      // N fastest: see tile order note at the top
         const int n0 = n_tile * p.block_n;
         int cx = 0, cy = 0, cn = 0;
         if (p.a_conv) {
@@ -256,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // only the active groups
     const bool active = cgrp * 32 < p.block_n;
     for (int tile = active ? blockIdx.x : num_tiles; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;      // N fastest: see tile order note at the top
       const int n0 = n_tile * p.block_n;
       const int64_t grow = tile_row_to_global(p, m_tile, r, rib);
       int64_t ct_base = 0;                  // CONVT2X2: element offset of output pixel (2y, 2x), channel 0

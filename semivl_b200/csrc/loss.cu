@@ -274,6 +274,53 @@ __global__ void cutmix_weights_kernel(const int64_t* __restrict__ lab_a, const i
   c = block_sum(c, red);
   if (threadIdx.x == 0 && valid_count && c != 0.f) atomicAdd(valid_count, c);
 }
+// Per-image statistics of the (CutMixed) confidence map / ignore mask for the 'pixelratio' and 'pixelavg' modes of
+// utils/train_utils.py:40-46:  stats[b] = { #valid, #(conf >= thresh & valid), sum(conf * valid) },  valid = (ign != 255).
+// grid = (chunks, B); one atomicAdd triple per CTA.
+__global__ void conf_stats_kernel(const float* __restrict__ conf_a, const float* __restrict__ conf_b, const int64_t* __restrict__ ign_a,
+                                  const int64_t* __restrict__ ign_b, const float* __restrict__ box, float* __restrict__ stats, int64_t hw,
+                                  float thresh) {
+  __shared__ float red[32];
+  const int64_t base = (int64_t)blockIdx.y * hw;
+  float nv = 0.f, nh = 0.f, sc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool m = box != nullptr && box[base + i] == 1.f;
+    const float cf = m ? conf_b[base + i] : conf_a[base + i];
+    const bool valid = (m ? ign_b[base + i] : ign_a[base + i]) != 255;
+    nv += valid;
+    nh += (valid && cf >= thresh);
+    sc += valid ? cf : 0.f;
+  }
+  nv = block_sum(nv, red);
+  __syncthreads();
+  nh = block_sum(nh, red);
+  __syncthreads();
+  sc = block_sum(sc, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + 3 * blockIdx.y + 0, nv);
+    atomicAdd(stats + 3 * blockIdx.y + 1, nh);
+    atomicAdd(stats + 3 * blockIdx.y + 2, sc);
+  }
+}
+// Loss coefficient (device scalar) and per-image weights from the statistics above (one thread; B is the per-GPU batch):
+//   mode 0 pixelwise : coef = numer / sum_b nvalid_b                                     (row_w untouched)
+//   mode 1 pixelratio: coef = numer / sum_b nvalid_b, row_w[b] = nhigh_b / nvalid_b
+//   mode 2 pixelavg  : coef = numer * sum_b (sumconf_b / nvalid_b) / sum_b nvalid_b      (train_utils.py:43-46: loss.sum() * avg_conf)
+__global__ void conf_coef_kernel(const float* __restrict__ stats, int B, int mode, float numer, float* __restrict__ coef,
+                                 float* __restrict__ row_w) {
+  float nv = 0.f, avg = 0.f;
+  for (int b = 0; b < B; ++b) {
+    nv += stats[3 * b];
+    avg += stats[3 * b + 2] / stats[3 * b];
+    if (mode == 1 && row_w) row_w[b] = stats[3 * b + 1] / stats[3 * b];
+  }
+  coef[0] = mode == 2 ? numer * avg / nv : numer / nv;
+}
+// w[b, :] = row_w[b]  (the per-image 'pixelratio' weight as a per-pixel weight map of the fused CE kernel)
+__global__ void fill_rows_kernel(float* __restrict__ w, const float* __restrict__ row_w, int B, int64_t hw) {
+  const int64_t total = (int64_t)B * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) w[i] = row_w[i / hw];
+}
 // img = box ? img_b : img_a  per pixel, all channels (utils/train_utils.py:19-21), out of place
 __global__ void cutmix_img_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ box, float* __restrict__ out,
                                   int B, int C, int64_t hw) {
@@ -384,6 +431,27 @@ extern "C" int svl_cutmix_weights(const int64_t* lab_a, const int64_t* lab_b, co
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
+extern "C" int svl_conf_stats(const float* conf_a, const float* conf_b, const int64_t* ign_a, const int64_t* ign_b, const float* box,
+                              float* stats, int B, int64_t hw, float thresh, void* stream) {
+  SVL_CHECK_ARG(conf_a && ign_a && stats && B > 0 && hw > 0, "svl_conf_stats: bad arguments");
+  SVL_CHECK_ARG(box == nullptr || (conf_b && ign_b), "svl_conf_stats: a CutMix box needs the second (conf, ignore) pair");
+  const int chunks = (int)((hw + 256 * 8 - 1) / (256 * 8));
+  conf_stats_kernel<<<dim3(chunks < 64 ? chunks : 64, B), 256, 0, ST>>>(conf_a, conf_b, ign_a, ign_b, box, stats, hw, thresh);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_conf_coef(const float* stats, int B, int mode, float numer, float* coef, float* row_w, void* stream) {
+  SVL_CHECK_ARG(stats && coef && B > 0 && mode >= 0 && mode <= 2, "svl_conf_coef: bad arguments");
+  conf_coef_kernel<<<1, 1, 0, ST>>>(stats, B, mode, numer, coef, row_w);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_fill_rows(float* w, const float* row_w, int B, int64_t hw, void* stream) {
+  SVL_CHECK_ARG(w && row_w && B > 0 && hw > 0, "svl_fill_rows: bad arguments");
+  fill_rows_kernel<<<ew_grid((int64_t)B * hw), 256, 0, ST>>>(w, row_w, B, hw);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
 extern "C" int svl_cutmix_img(const float* a, const float* b, const float* box, float* out, int B, int C, int64_t hw, void* stream) {
   SVL_CHECK_ARG(a && b && box && out, "svl_cutmix_img: null pointer");
   cutmix_img_kernel<<<ew_grid((int64_t)B * C * hw), 256, 0, ST>>>(a, b, box, out, B, C, hw);
@@ -391,6 +459,31 @@ extern "C" int svl_cutmix_img(const float* a, const float* b, const float* box, 
   return SVL_OK;
 }
 
+// Same update with the per-step scalars read from device memory (hyper = {lr class 0, lr class 1, 1 - beta1^t, sqrt(1 - beta2^t)}), so
+// that a captured CUDA graph of the training step can be replayed with a new learning rate / step count.
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                 const float* __restrict__ hyper, int lr_index, float beta1, float beta2, float eps, float wd, float gscale) {
+  const float lr = hyper[lr_index], bc1 = hyper[2], bc2_sqrt = hyper[3];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gr = g[i] * gscale;
+    float pv = p[i] * (1.f - lr * wd);
+    const float mv = beta1 * m[i] + (1.f - beta1) * gr;
+    const float vv = beta2 * v[i] + (1.f - beta2) * gr * gr;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= (lr / bc1) * (mv / denom);
+    p[i] = pv;
+  }
+}
+extern "C" int svl_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int lr_index, float beta1,
+                             float beta2, float eps, float wd, float gscale, void* stream) {
+  SVL_CHECK_ARG(p && g && m && v && hyper && (lr_index == 0 || lr_index == 1), "svl_adamw_dev: bad arguments");
+  if (n == 0) return SVL_OK;
+  adamw_dev_kernel<<<ew_grid(n), 256, 0, ST>>>(p, g, m, v, n, hyper, lr_index, beta1, beta2, eps, wd, gscale == 0.f ? 1.f : gscale);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
 extern "C" int svl_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
                          int step, float gscale, void* stream) {
   SVL_CHECK_ARG(p && g && m && v && step >= 1, "svl_adamw: bad arguments");

@@ -191,7 +191,7 @@ class VitEngine:
         return feats, glob, ctx
 
     # ------------------------------------------------------------------ backward
-    def backward(self, ctx, dfeats, p, grads):
+    def backward(self, ctx, dfeats, p, grads, on_layer_done=None):
         """dfeats: list (same order as forward's feats) of f32 [B,h,w,C] contiguous or None.
         `grads` maps parameter name -> f32 gradient tensor (same shape as the parameter), accumulated in place."""
         c, pr = self.cfg, self.precise
@@ -292,6 +292,8 @@ class VitEngine:
                 dx, dx_act = ops.layernorm_bwd(dy1, gdt, S["x_in"], p[pre + "ln1.weight"], S["mu1"], S["rs1"], dres1=dx, dres2=dv1,
                                                act_precise=pr)
             # else: nothing reaches this layer (cannot happen with the reference's tap configuration)
+            if on_layer_done is not None:
+                on_layer_done(i)                         # layer i's weight gradients are final: the trainer may start exchanging them
 
         if dx is not None:
             dx0, _ = ops.layernorm_bwd(dx, L.F32, ctx["x0"], p["ln0.weight"], ctx["mu0"], ctx["rs0"])

@@ -104,8 +104,12 @@ _PROTOS = {
     "svl_count_valid": [_P, _L, _I, _P, _P],
     "svl_reciprocal": [_P, _P, _F, _F, _P],
     "svl_cutmix_weights": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _P],
+    "svl_conf_stats": [_P, _P, _P, _P, _P, _P, _I, _L, _F, _P],
+    "svl_conf_coef": [_P, _I, _I, _F, _P, _P, _P],
+    "svl_fill_rows": [_P, _P, _I, _L, _P],
     "svl_cutmix_img": [_P, _P, _P, _P, _I, _I, _L, _P],
     "svl_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "svl_adamw_dev": [_P, _P, _P, _P, _L, _P, _I, _F, _F, _F, _F, _F, _P],
     "svl_attention_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P],
     "svl_attention_bwd": [_P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _I, _I, _I, _F, _P],
 }

@@ -4,7 +4,7 @@ semivl.py:326-328 / experiments.py:246-255 and the data-parallel gradient all-re
 
 All trainable tensors (backbone attn.* + pos_embed, every decode-head tensor) live in ONE flat fp32
 buffer; gradients, Adam moments likewise, so the optimizer is two kernel launches (one per learning-rate class) and the
-data-parallel exchange is one NCCL all-reduce."""
+data-parallel exchange is a handful of NCCL all-reduces of contiguous slices, issued as the slices become final (GradExchange)."""
 import ctypes as C
 
 import torch
@@ -14,11 +14,58 @@ from . import lib as L
 from . import ops
 
 
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def allreduce_sum_(flat):
-    """Data-parallel gradient exchange: ONE all-reduce of the flat gradient buffer (NCCL on GPUs, gloo in the CPU tests)."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    """Data-parallel gradient exchange of a (slice of the) flat gradient buffer (NCCL on GPUs, gloo in the CPU tests)."""
+    if _world() > 1:
         dist.all_reduce(flat)
     return flat
+
+
+class GradExchange:
+    """Bucketed data-parallel gradient exchange over the flat gradient buffer, overlapped with the rest of the backward pass.
+
+    The reference wraps the model in DDP (semivl.py:139-140), whose reducer all-reduces gradient buckets while autograd is
+    still running.  Here the backward pass is a hand-scheduled kernel sequence, so the schedule is explicit: `reduce(lo, hi)`
+    is called as soon as the slice [lo, hi) of the flat buffer is final (the head after `head.backward`, groups of encoder
+    layers from the last one down); it makes a side stream wait for the kernels issued so far and launches the NCCL
+    all-reduce there, so the transfer over NVLink runs under the remaining backward kernels.  `finish()` reduces whatever was
+    not covered and makes the compute stream wait for the side stream before AdamW.  Sums only: the 1/world mean is folded
+    into the AdamW kernel's `gscale`."""
+
+    def __init__(self, flat):
+        self.flat, self.done = flat, []
+        self.comm = torch.cuda.Stream(device=flat.device) if flat.is_cuda and _world() > 1 else None
+
+    def begin(self):
+        self.done = []
+
+    def reduce(self, lo, hi):
+        if _world() == 1 or hi <= lo:
+            return
+        assert all(hi <= a or lo >= b for a, b in self.done), "gradient slice exchanged twice"
+        self.done.append((lo, hi))
+        if self.comm is None:
+            allreduce_sum_(self.flat[lo:hi])
+            return
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            allreduce_sum_(self.flat[lo:hi])
+
+    def finish(self):
+        pos = 0
+        for a, b in sorted(self.done) + [(self.flat.numel(), self.flat.numel())]:
+            self.reduce(pos, a)
+            pos = b
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        self.done = []
+
+
+CONF_MODES = {"pixelwise": 0, "pixelratio": 1, "pixelavg": 2}
 
 
 class OptimCfg:
@@ -35,8 +82,8 @@ class Trainer:
         self.hp = dict(conf_thresh=0.95, conf_mode="pixelwise", mcc_conf_thresh=0.9, mcc_loss_reduce="mean_all", mcc_lambda=0.1)
         if hp:
             self.hp.update(hp)
-        assert self.hp["conf_mode"] == "pixelwise" and self.hp["mcc_loss_reduce"] == "mean_all", \
-            "the fused loss path implements conf_mode='pixelwise' and mcc_loss_reduce='mean_all' (VOC/COCO/ADE experiments)"
+        assert self.hp["conf_mode"] in CONF_MODES, self.hp["conf_mode"]                       # utils/train_utils.py:36-48
+        assert self.hp["mcc_loss_reduce"] in ("mean", "mean_valid", "mean_all"), self.hp["mcc_loss_reduce"]   # semivl.py:113
         self.iters = 0
         bb = [(n, p) for n, p in model.backbone.named_parameters() if p.requires_grad]
         hd = [(n, p) for n, p in model.decode_head.named_parameters() if p.requires_grad]
@@ -60,7 +107,25 @@ class Trainer:
         self.vit, self.head = model.backbone.engine, model.decode_head.engine
         self.vit.cache.volatile = set(self.g_bb)
         self.head.cache.volatile = set(self.g_hd)
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = _world()
+        self._capturing, self._graph, self._graph_key, self._hyper = False, None, None, None
+        self.exchange = GradExchange(self.g_flat)
+        # exchange schedule of the encoder gradients: layers are contiguous and ascending in the flat buffer, the backward pass
+        # runs from the last layer down -> one bucket per `bucket_layers` layers, cut at the first parameter of a layer
+        self.layer_lo, self.bucket_layers = {}, 3
+        off, self._layers_end, order, tail = 0, 0, [], False
+        for name, p in bb:
+            if name.startswith("layers."):
+                assert not tail, f"{name}: the encoder layers must be contiguous in the flat buffer"
+                li = int(name.split(".")[1])
+                self.layer_lo.setdefault(li, off)
+                order.append(li)
+                self._layers_end = off + p.numel()
+            else:
+                tail = bool(order)
+            off += p.numel()
+        assert order == sorted(order), "encoder layers must be laid out in ascending order in the flat buffer"
+        self._bucket_hi = self._layers_end
         self._f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
@@ -70,22 +135,81 @@ class Trainer:
     def _ph(self):
         return {n: p.data for n, p in self.model.decode_head.named_parameters()}
 
-    def lr_now(self):
-        """poly schedule applied after each step (semivl.py:338-345)"""
-        return self.opt.lr * (1.0 - self.iters / self.opt.total_iters) ** self.opt.power if self.iters > 0 else self.opt.lr
+    def lr_at(self, it):
+        """Base learning rate used BY optimizer step number `it` (1-based).  semivl.py:338-345 rewrites the rate after each
+        optimizer.step() from the 0-based iteration index of the step just taken: step 1 and step 2 run at the initial rate, step
+        `it` at lr * (1 - (it - 2) / total) ** 0.9."""
+        o = self.opt
+        return o.lr * (1.0 - max(it - 2, 0) / o.total_iters) ** o.power
+
+    def _head_grads_final(self):
+        self.exchange.reduce(self.n_bb, self.n_bb + self.n_hd)
+
+    def _layer_grads_final(self, i):
+        """called by the encoder backward after layer i's weight gradients are complete (layers run 11 -> 0)"""
+        if i in self.layer_lo and i > 0 and i % self.bucket_layers == 0:
+            self.exchange.reduce(self.layer_lo[i], self._bucket_hi)
+            self._bucket_hi = self.layer_lo[i]
+
+    def _step_scalars(self, it):
+        """(lr of the backbone class, lr of the head class, 1 - beta1^t, sqrt(1 - beta2^t)) of optimizer step number `it` (1-based)."""
+        o = self.opt
+        base = self.lr_at(it)
+        return base * o.bb_mult, base * o.head_mult, 1.0 - o.betas[0] ** it, (1.0 - o.betas[1] ** it) ** 0.5
 
     def optimizer_step(self):
-        allreduce_sum_(self.g_flat)                                   # NCCL sum over ranks; the mean is folded into gscale below
+        self.exchange.finish()                                        # sum over ranks; the mean is folded into gscale below
+        self._bucket_hi = self._layers_end
+        o, gs, nb = self.opt, 1.0 / self.world, self.n_bb
+        if self._capturing:
+            # inside a CUDA-graph capture: per-step scalars come from device memory (self._hyper), host counters move at replay time
+            for lo, k, idx in ((0, nb, 0), (nb, self.n_hd, 1)):
+                L.call("svl_adamw_dev", self.p_flat[lo:], self.g_flat[lo:], self.m_flat[lo:], self.v_flat[lo:], k, self._hyper, idx, o.betas[0],
+                       o.betas[1], o.eps, o.wd, gs)
+            return
         self.iters += 1
-        lr, o = self.lr_now() if self.iters > 1 else self.opt.lr, self.opt
-        gs = 1.0 / self.world
-        nb = self.n_bb
+        lr = self.lr_at(self.iters)
         L.call("svl_adamw", self.p_flat, self.g_flat, self.m_flat, self.v_flat, nb, lr * o.bb_mult, o.betas[0], o.betas[1], o.eps, o.wd,
                self.iters, gs)
         L.call("svl_adamw", self.p_flat[nb:], self.g_flat[nb:], self.m_flat[nb:], self.v_flat[nb:], self.n_hd, lr * o.head_mult, o.betas[0],
                o.betas[1], o.eps, o.wd, self.iters, gs)
         self.vit.cache.bump()
         self.head.cache.bump()
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the supervised step
+    def graphed_supervised_step(self, img, mask):
+        """`supervised_step(img, mask)` as ONE CUDA-graph launch (~690 kernel launches and their host-side descriptor set-up
+        collapse into a replay).  Captured on first use for the given input shapes; inputs are copied into the graph's static
+        buffers, the per-step AdamW scalars (LR schedule, bias corrections) into a device vector.  Single-GPU only: with more
+        ranks the eager step overlaps the NCCL exchange with the backward pass instead."""
+        assert self.world == 1, "graph replay is the single-GPU path; multi-GPU steps run eagerly with the overlapped exchange"
+        key = (tuple(img.shape), tuple(mask.shape))
+        if self._graph is None or self._graph_key != key:
+            assert img.shape[-1] % 16 == 0 and img.shape[-2] % 16 == 0, "crops that need the pos-embed resize run eagerly"
+            self._g_img, self._g_mask = img.clone(), mask.clone()
+            self._hyper = torch.zeros(4, device=img.device)
+            self.supervised_step(self._g_img, self._g_mask, update=False)        # eager pass: frozen-weight operand cache, lazy attributes
+            self.vit.cache.bump()                                                 # trainable-weight casts must be part of the graph
+            self.head.cache.bump()
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            self._capturing, l0 = True, L.launches
+            try:
+                with torch.cuda.graph(self._graph):
+                    self._g_loss = self.supervised_step(self._g_img, self._g_mask, update=True)
+            finally:
+                self._capturing = False
+            self._graph_key, self._graph_launches = key, L.launches - l0      # svl kernels recorded into the graph
+            L.launches = l0
+        self._g_img.copy_(img, non_blocking=True)
+        self._g_mask.copy_(mask, non_blocking=True)
+        self._hyper.copy_(torch.tensor(self._step_scalars(self.iters + 1), dtype=torch.float32))
+        self._graph.replay()
+        L.launches += self._graph_launches
+        self.iters += 1
+        self.vit.cache.bump()                       # the cached operand copies now belong to the graph: eager calls must re-cast
+        self.head.cache.bump()
+        return self._g_loss
 
     @staticmethod
     def _ptr_array(items):
@@ -105,6 +229,7 @@ class Trainer:
         H, W = img.shape[-2:]
         text = m._text(img.device)
         self.g_flat.zero_()
+        self.exchange.begin()
         pb, ph = self._pb(), self._ph()
         feats, _, vctx = self.vit.forward(m.renormalize_img_for_clip(img), pb, need_grad=True, want_global=False)
         low, hctx = self.head.forward(feats, text, ph, need_grad=True)
@@ -116,7 +241,9 @@ class Trainer:
         self._ce(low, d_low, R, N, hl, wl, H, W, [(mask, None, coef)], loss)
         dfe = self.head.backward(hctx, d_low, ph, self.g_hd)
         del hctx
-        self.vit.backward(vctx, dfe, pb, self.g_bb)
+        if update:
+            self._head_grads_final()
+        self.vit.backward(vctx, dfe, pb, self.g_bb, on_layer_done=self._layer_grads_final if update else None)
         del vctx
         if update:
             self.optimizer_step()
@@ -134,7 +261,11 @@ class Trainer:
         text = m._text(dev)
         pb, ph = self._pb(), self._ph()
         lam = hp["mcc_lambda"]
+        if isinstance(lam, (list, tuple)):                               # linear schedule of the MaskCLIP lambda (semivl.py:312-316)
+            prog = self.iters / self.opt.total_iters
+            lam = lam[0] * (1 - prog) + lam[1] * prog
         self.g_flat.zero_()
+        self.exchange.begin()
         img_s1 = torch.empty_like(batch["img_s1"])
         img_s2 = torch.empty_like(batch["img_s2"])
         L.call("svl_cutmix_img", batch["img_s1"], batch["img_s1_other"], batch["mix1"], img_s1, b, 3, H * W)
@@ -167,48 +298,71 @@ class Trainer:
         conf_w = torch.empty(b, H, W, device=dev)
         lab_w = torch.empty(b, H, W, device=dev, dtype=torch.int64)
         L.call("svl_softmax_max", low[b:2 * b], conf_w, lab_w, b, N, hl, wl, H, W, 1.0, 0.0)
-        # ---- targets (cutmix of pseudo-labels, confidences, ignore masks; confidence weights)
+        # ---- targets (cutmix of pseudo-labels, confidences, ignore masks; confidence weights per cfg['conf_mode'])
         npx = float(b * H * W)
-        tgt = {}
-        for key, box in (("s1", batch["mix1"]), ("s2", batch["mix2"])):
-            lab = torch.empty_like(lab_w)
-            wgt = torch.empty_like(conf_w)
-            cnt = self._f(1)
-            L.call("svl_cutmix_weights", lab_w, lab_o, conf_w, conf_o, batch["ignore_mask"], batch["ignore_mask_other"], box, lab, wgt, None,
-                   cnt, lab.numel(), hp["conf_thresh"])
-            mcl = None
-            if lam != 0:
-                mcl = torch.empty_like(lab_w)
-                L.call("svl_cutmix_weights", mclip, mclip_o, None, None, None, None, box, mcl, None, None, None, mcl.numel(), 0.0)
-            tgt[key] = (lab, wgt, cnt, mcl)
-        w_fp = torch.empty_like(conf_w)
-        cnt_fp = self._f(1)
-        L.call("svl_cutmix_weights", lab_w, lab_w, conf_w, conf_w, batch["ignore_mask"], batch["ignore_mask"], None, None, w_fp, None, cnt_fp,
-               lab_w.numel(), hp["conf_thresh"])
-        cnt_x = self._f(1)
-        L.call("svl_count_valid", batch["mask_x"], batch["mask_x"].numel(), 255, cnt_x)
-
+        mode = CONF_MODES[hp["conf_mode"]]
         def coef(count, numer):
             out = self._f(1)
             L.call("svl_reciprocal", count, out, numer, 1.0)
             return out
-        losses = self._f(7)               # x, s1, s2, fp, mc_s1, mc_s2, mc_fp  (each already multiplied by its weight in the total)
-        d_low = torch.zeros_like(low)
+
+        def conf_target(lab_b, conf_b, ign_b, box, numer, want_lab):
+            """(labels, per-pixel weights | None, device coefficient, #valid of the mixed ignore mask) of one consistency loss:
+            confidence_weighted_loss(CE(pred, cutmix(mask_w, lab_b)), cutmix(conf_w, conf_b), cutmix(ignore, ign_b)) * numer."""
+            lab = torch.empty_like(lab_w) if want_lab else None
+            wgt = torch.empty_like(conf_w) if mode == 0 else None
+            cnt = self._f(1)
+            L.call("svl_cutmix_weights", lab_w, lab_b, conf_w, conf_b, batch["ignore_mask"], ign_b, box, lab, wgt, None, cnt, lab_w.numel(),
+                   hp["conf_thresh"])
+            if mode == 0:
+                return lab, wgt, coef(cnt, numer), cnt
+            stats, cf = self._f(b, 3), self._f(1)
+            row_w = self._f(b) if mode == 1 else None
+            L.call("svl_conf_stats", conf_w, conf_b, batch["ignore_mask"], ign_b, box, stats, b, H * W, hp["conf_thresh"])
+            L.call("svl_conf_coef", stats, b, mode, numer, cf, row_w)
+            if mode == 1:
+                wgt = torch.empty_like(conf_w)
+                L.call("svl_fill_rows", wgt, row_w, b, H * W)
+            return lab, wgt, cf, cnt
+
+        def mc_coef(mcl, cnt_ign, k):
+            """device coefficient of one MaskCLIP consistency term: lambda * k / denominator(mcc_loss_reduce) (semivl.py:52-58)."""
+            red = hp["mcc_loss_reduce"]
+            if red == "mean_all":
+                return one * (lam * k / npx)
+            if red == "mean_valid":
+                return coef(cnt_ign, lam * k)
+            c = self._f(1)                                                  # 'mean': CrossEntropyLoss(ignore_index=255) mean over labels != 255
+            L.call("svl_count_valid", mcl, mcl.numel(), 255, c)
+            return coef(c, lam * k)
+
         one = torch.ones(1, device=dev)
+        tgt = {}
+        for key, box in (("s1", batch["mix1"]), ("s2", batch["mix2"])):
+            lab, wgt, cf, cnt = conf_target(lab_o, conf_o, batch["ignore_mask_other"], box, 0.125, True)
+            mcl = None
+            if lam != 0:
+                mcl = torch.empty_like(lab_w)
+                L.call("svl_cutmix_weights", mclip, mclip_o, None, None, None, None, box, mcl, None, None, None, mcl.numel(), 0.0)
+            tgt[key] = (lab, wgt, cf, cnt, mcl)
+        _, w_fp, cf_fp, cnt_fp = conf_target(lab_w, conf_w, batch["ignore_mask"], None, 0.25, False)
+        cnt_x = self._f(1)
+        L.call("svl_count_valid", batch["mask_x"], batch["mask_x"].numel(), 255, cnt_x)
+        d_low = torch.zeros_like(low)
         rows = lambda t, i: t[i * b:(i + 1) * b]
         lx = self._f(3)
         self._ce(rows(low, 0), rows(d_low, 0), b, N, hl, wl, H, W, [(batch["mask_x"], None, coef(cnt_x, 0.5))], lx)
         lfp = self._f(3)
-        t_fp = [(lab_w, w_fp, coef(cnt_fp, 0.25))]
+        t_fp = [(lab_w, w_fp, cf_fp)]
         if lam != 0:
-            t_fp.append((mclip, None, one * (lam * 0.5 / npx)))
+            t_fp.append((mclip, None, mc_coef(mclip, cnt_fp, 0.5)))
         self._ce(rows(low, 2), rows(d_low, 2), b, N, hl, wl, H, W, t_fp, lfp)
         ls = {}
         for i, key in ((3, "s1"), (4, "s2")):
-            lab, wgt, cnt, mcl = tgt[key]
-            t = [(lab, wgt, coef(cnt, 0.125))]
+            lab, wgt, cf, cnt, mcl = tgt[key]
+            t = [(lab, wgt, cf)]
             if lam != 0:
-                t.append((mcl, None, one * (lam * 0.25 / npx)))
+                t.append((mcl, None, mc_coef(mcl, cnt, 0.25)))
             ls[key] = self._f(3)
             self._ce(rows(low, i), rows(d_low, i), b, N, hl, wl, H, W, t, ls[key])
         total = lx[0] + lfp[0] + lfp[1] + ls["s1"][0] + ls["s1"][1] + ls["s2"][0] + ls["s2"][1]
@@ -218,6 +372,8 @@ class Trainer:
         # ---- backward
         dhf = self.head.backward(hctx, d_low, ph, self.g_hd)
         del hctx
+        if update:
+            self._head_grads_final()
         dfe = []
         for d, k in zip(dhf, dm):
             g = torch.empty(4 * b, *d.shape[1:], device=dev, dtype=torch.float32)
@@ -226,7 +382,7 @@ class Trainer:
             g[2 * b:] = d[3 * b:]
             dfe.append(g)
         del dhf
-        self.vit.backward(vctx, dfe, pb, self.g_bb)
+        self.vit.backward(vctx, dfe, pb, self.g_bb, on_layer_done=self._layer_grads_final if update else None)
         del vctx
         if update:
             self.optimizer_step()

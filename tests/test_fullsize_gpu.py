@@ -1,0 +1,117 @@
+"""Parity at BASELINE.json's full sizes (crop, class count and text table of configs 2-5) against the CPU oracle, run on the
+GPU box's host cores at batch 1-2 so that it finishes in seconds, plus size-independent properties of the data-parallel
+path at the full per-GPU batch of config 2 (the path shards per image: an image's logits do not depend on its batch).
+
+Tolerances: precise mode (split-bf16 x3) 1e-3 of the logit range = the north-star bound (measured ~3e-5);
+bf16 throughput mode 4e-2 of the logit range (measured ~1e-2; the reference's own CPU bf16 autocast gives 1.3e-2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+# (BASELINE config, dataset key, text table, classes, crop)
+CONFIGS = {
+    "cfg2_voc_512": ("pascal", "voc12_wbg_single.npy", 21, 512),
+    "cfg3_cityscapes_801": ("cityscapes", "cityscapes_single.npy", 19, 801),     # 801 -> corner pad to 816, pos-embed 32^2 -> 51^2 bicubic
+    "cfg4_ade_512": ("ade", "ade_single.npy", 150, 512),
+    "cfg5_coco_641": ("coco", "coco_single.npy", 81, 641),                       # 641 -> 656, pos-embed 32^2 -> 41^2
+}
+
+
+def _cfg(dataset, nclass, crop, precise):
+    return dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=nclass, crop_size=crop, dataset=dataset,
+                text_embedding_variant='single', mcc_text='single', pl_text='single', clip_encoder=None, disable_dropout=True, fp_rate=0.5,
+                model_args=dict(pretrained=None), precise=precise)
+
+
+def _build(dataset, nclass, crop, precise):
+    from oracle import semivl_oracle as O
+    from semivl_b200.model import build_model
+    mc = O.ModelCfg(img_size=crop, num_classes=nclass)
+    sd = O.fixture_state_dict(O.param_shapes(mc, with_clip_encoder=False), seed=0)
+    m = build_model(_cfg(dataset, nclass, crop, precise))
+    m.load_state_dict(sd)
+    return m.cuda(), mc, sd
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_size_logits_match_oracle(text_dir, name):
+    from oracle import semivl_oracle as O
+    dataset, table, nclass, crop = CONFIGS[name]
+    torch.set_num_threads(os.cpu_count() or 1)
+    text = torch.from_numpy(np.load(os.path.join(text_dir, table)))
+    img = torch.randn(1, 3, crop, crop, generator=torch.Generator().manual_seed(5))
+    ref = None
+    for precise, tol in ((True, 1e-3), (False, 4e-2)):
+        m, mc, sd = _build(dataset, nclass, crop, precise)
+        if ref is None:
+            with torch.no_grad():
+                ref = O.model_forward(img, sd, text, mc)
+        with torch.no_grad():
+            out = m(img.cuda()).float().cpu()
+        assert out.shape == ref.shape == (1, nclass, crop, crop)
+        err = (out - ref).abs().max().item() / ref.abs().max().item()
+        print(name, "precise" if precise else "bf16", "logit error / range", err)
+        assert err < tol, (name, precise, err)
+        if precise:
+            # argmax masks: bit-exact wherever the reference's top-1/top-2 margin exceeds twice the measured logit error
+            top2 = ref.topk(2, dim=1).values
+            decidable = (top2[:, 0] - top2[:, 1]) > 2 * (out - ref).abs().max()
+            assert (out.argmax(1) == ref.argmax(1))[decidable].all()
+            assert (out.argmax(1) == ref.argmax(1)).float().mean() > 0.999
+        del m
+        torch.cuda.empty_cache()
+
+
+def test_config2_step_at_full_resolution_matches_oracle(text_dir):
+    """Supervised step of BASELINE config 2 at 512x512 / N=21 (batch 2 so that the oracle's backward takes seconds):
+    loss and every gradient norm against the oracle, precise mode."""
+    from oracle import semivl_oracle as O
+    from semivl_b200.train import OptimCfg, Trainer
+    torch.set_num_threads(os.cpu_count() or 1)
+    m, mc, sd = _build("pascal", 21, 512, True)
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(2, 3, 512, 512, generator=g)
+    mask = torch.randint(0, 21, (2, 512, 512), generator=g)
+    mask[:, :100, :130] = 255
+    text = torch.from_numpy(np.load(os.path.join(text_dir, "voc12_wbg_single.npy")))
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss_ref = O.supervised_step_loss(img, mask, p, text, mc)
+    loss_ref.backward()
+    tr = Trainer(m, OptimCfg())
+    loss = tr.supervised_step(img.cuda(), mask.cuda(), update=False)
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * loss_ref.item()
+    for prefix, gd in (("backbone.", tr.g_bb), ("decode_head.", tr.g_hd)):
+        for k, gv in gd.items():
+            nr = p[prefix + k].grad.double().norm().item()
+            if nr > 1e-7:
+                assert abs(gv.double().norm().item() - nr) <= 3e-2 * nr, (k, gv.norm().item(), nr)
+
+
+def test_config2_full_batch_is_per_image(text_dir):
+    """Size-independent property at the full per-GPU batch of config 2 (16 x 512x512): the path shards per image, so images 5..6 of
+    the batch of 16 get the logits they get as a batch of 2 (same kernels, same per-row reduction order); the loss of the full
+    batch is the valid-pixel-weighted mean of the two half-batch losses."""
+    from semivl_b200.train import OptimCfg, Trainer
+    m, mc, sd = _build("pascal", 21, 512, False)
+    g = torch.Generator().manual_seed(17)
+    img = torch.randn(16, 3, 512, 512, generator=g).cuda()
+    mask = torch.randint(0, 21, (16, 512, 512), generator=g)
+    mask[:8, :200, :] = 255
+    mask = mask.cuda()
+    with torch.no_grad():
+        full = m.forward_lowres(img)
+        part = m.forward_lowres(img[5:7].contiguous())
+    scale = full.float().abs().max().item()
+    assert (full[5:7].float() - part.float()).abs().max().item() <= 1e-6 * scale
+    tr = Trainer(m, OptimCfg())
+    l_all = tr.supervised_step(img, mask, update=False).item()
+    l_a = tr.supervised_step(img[:8].contiguous(), mask[:8].contiguous(), update=False).item()
+    l_b = tr.supervised_step(img[8:].contiguous(), mask[8:].contiguous(), update=False).item()
+    na, nb = (mask[:8] != 255).sum().item(), (mask[8:] != 255).sum().item()
+    assert abs(l_all - (l_a * na + l_b * nb) / (na + nb)) < 1e-5 * abs(l_all)

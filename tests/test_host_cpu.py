@@ -8,6 +8,7 @@ import subprocess
 import sys
 
 import pytest
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -112,3 +113,53 @@ def test_gradient_exchange_gloo_world2(built):
         p.join(timeout=60)
     want = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
     assert torch.allclose(res[0], want) and torch.allclose(res[1], want)
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semivl_b200.train import GradExchange
+    flat = torch.randn(1000, generator=torch.Generator().manual_seed(100 + rank))
+    ex = GradExchange(flat)
+    ex.begin()
+    ex.reduce(900, 1000)          # "head" slice first, then encoder buckets from the last layers down, like Trainer does
+    ex.reduce(600, 900)
+    ex.reduce(250, 600)
+    ex.finish()                   # the uncovered prefix [0, 250)
+    q.put((rank, flat))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_exchange_gloo_world2(built):
+    """GradExchange: slices exchanged as they become final + finish() of the remainder == one all-reduce of the whole buffer."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    want = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    assert torch.allclose(res[0], want) and torch.allclose(res[1], want)
+
+
+def test_poly_lr_schedule_matches_reference_order(built):
+    """semivl.py:338-345 rewrites the rate AFTER optimizer.step() from the 0-based index of the iteration just run, so optimizer
+    step `it` (1-based) runs at poly_lr(it - 2) (and steps 1, 2 at the initial rate)."""
+    from oracle import semivl_oracle as O
+    from semivl_b200.train import OptimCfg, Trainer
+    tr = Trainer.__new__(Trainer)
+    tr.opt = OptimCfg(lr=1e-4, total_iters=50)
+    lr, seen = 1e-4, []
+    for i in range(10):                     # the reference loop: step with the current rate, then rewrite it from index i
+        seen.append(lr)
+        lr = O.poly_lr(1e-4, i, 50)
+    assert np.allclose([tr.lr_at(it) for it in range(1, 11)], seen, rtol=1e-12)
+    a, b_, bc1, bc2s = tr._step_scalars(3)
+    assert np.isclose(a, seen[2] * 0.01) and np.isclose(b_, seen[2] * 10.0)
+    assert np.isclose(bc1, 1 - 0.9 ** 3) and np.isclose(bc2s, (1 - 0.999 ** 3) ** 0.5)

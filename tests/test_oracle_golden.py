@@ -65,7 +65,7 @@ def test_forward_backward_matches_reference(golden_dir, text_dir, name):
         assert (mcl.numpy().astype(np.uint8) == g[key]).mean() > 0.999
 
 
-@pytest.mark.parametrize("name", ["step_c64_b1", "step_c96_b2"])
+@pytest.mark.parametrize("name", ["step_c64_b1", "step_c96_b2", "step_c64_b2_pixelavg_mv", "step_c64_b2_pixelratio_mean"])
 def test_semivl_iteration_matches_reference(golden_dir, text_dir, name):
     g = _load(golden_dir, name)
     mc = O.ModelCfg(img_size=int(g["crop"]), num_classes=int(g["nclass"]))

@@ -5,9 +5,11 @@
 //   warps 2..9  : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global); warp w owns TMEM lane
 //                 quarter w % 4 and every other 32-column chunk
 //
-// Tile order: N fastest.  The CTAs that run concurrently then cover (#SMs / n_tiles) row blocks x all column blocks, so each A row
-// block is fetched from HBM once and served to its other column blocks by L2 (with M fastest the K = 3072 FFN GEMMs streamed the
-// 100 MB A operand once per column block: 350 MB of DRAM reads per launch instead of 155 MB, profiles/r01_ncu_targets.md).
+// Tile order: M fastest (all concurrent CTAs share one B tile) unless the A operand is too large to stay in L2 between column
+// blocks; then N fastest: the concurrent CTAs cover (#SMs / n_tiles) row blocks x all column blocks, so each A row block comes from
+// HBM once and L2 serves its other column blocks (with M fastest the K = 3072 FFN GEMMs streamed the 100 MB A operand once per
+// column block: 350 MB of DRAM reads per launch instead of 155 MB, profiles/r01_ncu_targets.md; measured -9..-14 % on those
+// launches, while the L2-resident QKV / FFN1 shapes lost 6-9 % with N fastest and keep M fastest).
 // Accumulators are double-buffered in TMEM (2 x block_n columns) so the epilogue of tile i overlaps the main
 // loop of tile i+1.  Tile = 128 output rows x block_n columns, K step 64 (one 128-byte swizzle row).
 // In conv mode the 128 rows of a tile are a (bn images x bh rows x bw columns) box of an NHWC tensor, fetched with a
@@ -37,6 +39,7 @@ struct GemmParams {
   int bw, bh, bn;                  // conv tile box
   int tiles_x, tiles_y;            // conv tiles per image row / column-of-tiles
   int num_m_tiles, num_n_tiles;
+  int n_fastest;                   // tile order (see the note at the top)
   int n, block_n, k_per_tap, num_taps;
   int stages, tmem_cols, acc_stages;
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes;
@@ -149,7 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;      // N fastest: see tile order note at the top
+        const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / p.num_m_tiles, m_tile = p.n_fastest ? tile / p.num_n_tiles : tile % p.num_m_tiles;
         const int n0 = n_tile * p.block_n;
         int cx = 0, cy = 0, cn = 0;
         if (p.a_conv) {
@@ -259,7 +262,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // only the active groups
     const bool active = cgrp * 32 < p.block_n;
     for (int tile = active ? blockIdx.x : num_tiles; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;      // N fastest: see tile order note at the top
+      const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / p.num_m_tiles, m_tile = p.n_fastest ? tile / p.num_n_tiles : tile % p.num_m_tiles;
       const int n0 = n_tile * p.block_n;
       const int64_t grow = tile_row_to_global(p, m_tile, r, rib);
       int64_t ct_base = 0;                  // CONVT2X2: element offset of output pixel (2y, 2x), channel 0
@@ -528,6 +531,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.block_n = d->block_n > 0 ? d->block_n : auto_block_n(d->n);
   SVL_CHECK_ARG(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "svl_gemm: block_n=%d invalid", p.block_n);
   p.num_n_tiles = (d->n + p.block_n - 1) / p.block_n;
+  p.n_fastest = p.num_n_tiles > 1 && !d->a_conv && (int64_t)d->m * d->k_per_tap * d->num_taps * 2 > (48ll << 20);
   const int64_t a_cols = d->a_cols > 0 ? d->a_cols : d->lda;
 
   CUtensorMap tmA, tmB;

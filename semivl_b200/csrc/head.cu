@@ -196,6 +196,226 @@ gn_bwd_apply_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------- all-bf16 GroupNorm fast paths
+// Every large GroupNorm of the throughput mode reads a bf16 conv output and writes a bf16 operand.  The generic kernels above
+// go through ld8/st8 (run-time dtype + alignment dispatch around every access), which keeps ptxas from batching the loads:
+// they ran at 1.2 - 3.6 TB/s (profiles/r01_ncu_targets.md).  Here a thread owns ONE 8-channel vector (16 bytes) of U pixels and
+// issues all its 16-byte loads back to back (streaming, no L1 allocation) before it uses any of them; the map is a grid
+// dimension, so there is no per-element division and the statistics of the block are loaded once.
+__device__ __forceinline__ uint4 ld_stream16(const __nv_bfloat16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void ldg8f(const float* p, float* f) {
+  const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)p + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ sum, float* __restrict__ sq, int hw, int C, int G,
+                     int splits) {
+  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, ppi = kGnThreads / vpp;
+  if (threadIdx.x < kMaxGroups) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
+  __syncthreads();
+  int p0, p1;
+  gn_range(hw, splits, split, p0, p1);
+  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / (C / G);
+  const __nv_bfloat16* xb = x + (int64_t)map * hw * ldx + c8;
+  float pa = 0.f, pb = 0.f;
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 4 * ppi) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = pix + u * ppi;
+      v[u] = ld_stream16(xb + (int64_t)(q < p1 ? q : pix) * ldx);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (pix + u * ppi < p1) {
+        float f[8];
+        bf16x8_to_f32(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { pa += f[i]; pb += f[i] * f[i]; }
+      }
+    }
+  }
+  atomicAdd(&s_sum[g], pa);
+  atomicAdd(&s_sq[g], pb);
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(sum + (int64_t)map * G + threadIdx.x, s_sum[threadIdx.x]);
+    atomicAdd(sq + (int64_t)map * G + threadIdx.x, s_sq[threadIdx.x]);
+  }
+}
+
+// grid = (ceil(hw * vpp / (256 * U)), maps); item = (pixel of the map, 8-channel vector); vshift = log2(vpp)
+constexpr int kGnApplyU = 4;
+__global__ void __launch_bounds__(256)
+gn_apply_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ out, int64_t ldo, const __nv_bfloat16* __restrict__ res, int64_t ldres,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int hw, int C, int G, int vshift) {
+  constexpr int U = kGnApplyU;
+  const int vpp = 1 << vshift, v = threadIdx.x & (vpp - 1), c8 = v * 8, g = c8 / (C / G);
+  const int map = blockIdx.y, items = hw << vshift;
+  const int base = blockIdx.x * (256 * U) + threadIdx.x;
+  if (base >= items) return;
+  const int64_t pix0 = (int64_t)map * hw;
+  int pix[U];
+  uint4 xv[U], rv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int idx = base + u * 256;
+    pix[u] = (idx < items ? idx : base) >> vshift;
+    xv[u] = ld_stream16(x + (pix0 + pix[u]) * ldx + c8);
+  }
+  if (res) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) rv[u] = ld_stream16(res + (pix0 + pix[u]) * ldres + c8);
+  }
+  float ga[8], be[8];
+  ldg8f(gamma + c8, ga);
+  ldg8f(beta + c8, be);
+  const float mu = __ldg(mean + (int64_t)map * G + g), rs = __ldg(rstd + (int64_t)map * G + g);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (base + u * 256 < items) {
+      float f[8];
+      bf16x8_to_f32(xv[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf((f[i] - mu) * rs * ga[i] + be[i], 0.f);       // same expression as the backward's ReLU mask
+      if (res) {
+        float r[8];
+        bf16x8_to_f32(rv[u], r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += r[i];
+      }
+      *(uint4*)(out + (pix0 + pix[u]) * ldo + c8) = f32_to_bf16x8(f);
+    }
+  }
+}
+
+// backward statistics: thread = (pixel slot, 8-channel vector), two pixels (x, dy: four 16-byte loads) in flight; the 18 per-thread
+// partials (dgamma[8], dbeta[8], s1, s2) are reduced through a padded shared-memory table instead of same-address atomics.
+__global__ void __launch_bounds__(kGnThreads, 3)
+gn_bwd_stats_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int hw,
+                         int C, int G, int splits) {
+  __shared__ float part[18][kGnThreads + 1];
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, ppi = kGnThreads / vpp, cpg = C / G;
+  int p0, p1;
+  gn_range(hw, splits, split, p0, p1);
+  const int v = threadIdx.x % vpp, c8 = v * 8, g = c8 / cpg;
+  float ga[8], be[8];
+  ldg8f(gamma + c8, ga);
+  ldg8f(beta + c8, be);
+  const float mu = mean[(int64_t)map * G + g], rs = rstd[(int64_t)map * G + g];
+  const __nv_bfloat16* xb = x + (int64_t)map * hw * ldx + c8;
+  const __nv_bfloat16* yb = dy + (int64_t)map * hw * lddy + c8;
+  float s1 = 0.f, s2 = 0.f, dg[8], db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 2 * ppi) {
+    const bool ok1 = pix + ppi < p1;
+    const int q1 = ok1 ? pix + ppi : pix;
+    const uint4 a0 = ld_stream16(xb + (int64_t)pix * ldx), b0 = ld_stream16(yb + (int64_t)pix * lddy);
+    const uint4 a1 = ld_stream16(xb + (int64_t)q1 * ldx), b1 = ld_stream16(yb + (int64_t)q1 * lddy);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 || ok1) {
+        float xv[8], d[8];
+        bf16x8_to_f32(u == 0 ? a0 : a1, xv);
+        bf16x8_to_f32(u == 0 ? b0 : b1, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[i] - mu) * rs;
+          const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
+          dg[i] += dd * xh;
+          db[i] += dd;
+          const float gg = dd * ga[i];
+          s1 += gg;
+          s2 += gg * xh;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { part[i][threadIdx.x] = dg[i]; part[8 + i][threadIdx.x] = db[i]; }
+  part[16][threadIdx.x] = s1;
+  part[17][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.x < C && dgamma) {                       // channel c = (vector c / 8, lane c % 8): sum over the pixel slots
+    const int cv = threadIdx.x / 8, ci = threadIdx.x % 8;
+    float a = 0.f, b = 0.f;
+    for (int ps = 0; ps < ppi; ++ps) { a += part[ci][ps * vpp + cv]; b += part[8 + ci][ps * vpp + cv]; }
+    atomicAdd(dgamma + threadIdx.x, a);
+    atomicAdd(dbeta + threadIdx.x, b);
+  }
+  if (threadIdx.x >= kGnThreads - G) {                   // one (late) thread per group: sum over its vectors and the pixel slots
+    const int gg = kGnThreads - 1 - threadIdx.x, v0 = gg * cpg / 8, v1 = (gg + 1) * cpg / 8;
+    float a = 0.f, b = 0.f;
+    for (int ps = 0; ps < ppi; ++ps)
+      for (int vv = v0; vv < v1; ++vv) { a += part[16][ps * vpp + vv]; b += part[17][ps * vpp + vv]; }
+    atomicAdd(ws + ((int64_t)map * G + gg) * 2, a);
+    atomicAdd(ws + ((int64_t)map * G + gg) * 2 + 1, b);
+  }
+}
+
+constexpr int kGnBwdApplyU = 2;
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, const float* __restrict__ ws, __nv_bfloat16* __restrict__ dx, int64_t lddx, int hw,
+                         int C, int G, int vshift) {
+  constexpr int U = kGnBwdApplyU;
+  const int vpp = 1 << vshift, v = threadIdx.x & (vpp - 1), c8 = v * 8, g = c8 / (C / G);
+  const int map = blockIdx.y, items = hw << vshift;
+  const int base = blockIdx.x * (256 * U) + threadIdx.x;
+  if (base >= items) return;
+  const int64_t pix0 = (int64_t)map * hw;
+  int pix[U];
+  uint4 xv[U], dv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int idx = base + u * 256;
+    pix[u] = (idx < items ? idx : base) >> vshift;
+    xv[u] = ld_stream16(x + (pix0 + pix[u]) * ldx + c8);
+    dv[u] = ld_stream16(dy + (pix0 + pix[u]) * lddy + c8);
+  }
+  float ga[8], be[8];
+  ldg8f(gamma + c8, ga);
+  ldg8f(beta + c8, be);
+  const float n = (float)hw * (float)(C / G);
+  const float mu = __ldg(mean + (int64_t)map * G + g), rs = __ldg(rstd + (int64_t)map * G + g);
+  const float m1 = __ldg(ws + ((int64_t)map * G + g) * 2) / n, m2 = __ldg(ws + ((int64_t)map * G + g) * 2 + 1) / n;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (base + u * 256 < items) {
+      float xf[8], d[8];
+      bf16x8_to_f32(xv[u], xf);
+      bf16x8_to_f32(dv[u], d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (xf[i] - mu) * rs;
+        const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
+        d[i] = rs * (dd * ga[i] - m1 - xh * m2);
+      }
+      *(uint4*)(dx + (pix0 + pix[u]) * lddx + c8) = f32_to_bf16x8(d);
+    }
+  }
+}
+
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+inline int log2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
+}
+
 inline int gn_splits(int64_t maps, int hw, int C) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("SVL_GN_SPLITS"); forced = e ? atoi(e) : 0; }
@@ -615,6 +835,175 @@ conv_out1_wgrad_kernel(const float* __restrict__ dout, const void* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- output conv, all-bf16 fast paths (C = 32)
+// The generic kernels above are instruction-bound, not HBM-bound (0.9 TB/s on 352 MB: one scalar shared-memory weight read per FMA,
+// 2-byte x loads, run-time dtype dispatch).  Here: 16-byte loads issued in batches, weights as float4 broadcasts (forward) or
+// resident in registers (backward: a thread owns one 8-channel vector for all its pixels).
+constexpr int kO1C = 32;
+__global__ void __launch_bounds__(256)
+conv_out1_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const float* __restrict__ wgt, const float* __restrict__ bias,
+                          float* __restrict__ out, int h, int w, int tiles_x, int tiles_y) {
+  __shared__ float4 s_w4[9 * kO1C / 4];
+  __shared__ float s_z[9 * kO1HW];
+  for (int i = threadIdx.x; i < 9 * kO1C / 4; i += blockDim.x) s_w4[i] = __ldg((const float4*)wgt + i);
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
+  const int64_t map = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = tx * kO1TW - 1, y0 = ty * kO1TH - 1;
+  // the (at most two) halo pixels of this thread: all eight 16-byte loads are issued before the first FMA
+  uint4 v[2][4];
+  bool ok[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int i = threadIdx.x + u * 256;
+    const int yy = y0 + i / (kO1TW + 2), xx = x0 + i % (kO1TW + 2);
+    ok[u] = i < kO1HW && yy >= 0 && yy < h && xx >= 0 && xx < w;
+    const __nv_bfloat16* px = x + ((map * h + (ok[u] ? yy : 0)) * w + (ok[u] ? xx : 0)) * ld;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[u][q] = ld_stream16(px + q * 8);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int i = threadIdx.x + u * 256;
+    if (i < kO1HW) {
+      float z[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) z[t] = 0.f;
+      if (ok[u]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          bf16x8_to_f32(v[u][q], f);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float4 wa = s_w4[t * (kO1C / 4) + q * 2], wb = s_w4[t * (kO1C / 4) + q * 2 + 1];
+            z[t] += f[0] * wa.x + f[1] * wa.y + f[2] * wa.z + f[3] * wa.w + f[4] * wb.x + f[5] * wb.y + f[6] * wb.z + f[7] * wb.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) s_z[t * kO1HW + i] = z[t];
+    }
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kO1TW, lx = threadIdx.x % kO1TW;
+  const int yy = ty * kO1TH + ly, xx = tx * kO1TW + lx;
+  if (yy < h && xx < w) {
+    float s = __ldg(bias);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s += s_z[t * kO1HW + (ly + t / 3) * (kO1TW + 2) + lx + t % 3];
+    out[(map * h + yy) * w + xx] = s;
+  }
+}
+
+// The nine dout values that reach pixel (yy, xx) through the taps: d[t] = dout[yy - (t/3 - 1), xx - (t%3 - 1)] (0 outside the map)
+__device__ __forceinline__ void out1_neighbours(const float* __restrict__ dmap, int yy, int xx, int h, int w, float* d) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int y2 = yy - (t / 3 - 1), x2 = xx - (t % 3 - 1);
+    d[t] = (y2 >= 0 && y2 < h && x2 >= 0 && x2 < w) ? __ldg(dmap + y2 * w + x2) : 0.f;
+  }
+}
+// dx[map, y, x, c] = sum_t w[t, c] * d_t(y, x).  grid = (chunks of 256 * U items, maps); item = (pixel, 8-channel vector);
+// the 72 weights of the thread's vector live in registers.
+__global__ void __launch_bounds__(256)
+conv_out1_dgrad_bf16_kernel(const float* __restrict__ dout, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ dx, int64_t ld, int h, int w) {
+  constexpr int U = 4, VPP = kO1C / 8;
+  const int v = threadIdx.x % VPP, c8 = v * 8;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) ldg8f(wgt + t * kO1C + c8, wr[t]);
+  const int64_t map = blockIdx.y;
+  const float* dmap = dout + map * h * w;
+  const int items = h * w * VPP;
+#pragma unroll 1
+  for (int u = 0; u < U; ++u) {
+    const int idx = blockIdx.x * (256 * U) + u * 256 + threadIdx.x;
+    if (idx >= items) break;
+    const int pix = idx / VPP, yy = pix / w, xx = pix - yy * w;
+    float d[9], f[8];
+    out1_neighbours(dmap, yy, xx, h, w, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += d[t] * wr[t][i];
+    }
+    *(uint4*)(dx + (map * h * w + pix) * ld + c8) = f32_to_bf16x8(f);
+  }
+}
+// dw[t, c] += sum_q x[q, c] * d_t(q);  dbias += sum dout.  Persistent CTAs over (map, chunk) units; a thread keeps the 9 x 8
+// accumulators of its channel vector in registers across all its units, then warp shuffles + shared memory + one atomic per
+// (tap, channel) per CTA.
+__global__ void __launch_bounds__(256, 2)
+conv_out1_wgrad_bf16_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ dw,
+                            float* __restrict__ dbias, int h, int w, int chunks, int64_t units) {
+  constexpr int VPP = kO1C / 8, PPC = 256 / VPP * 2;       // pixels per chunk: two items per thread
+  __shared__ float red[8][9 * kO1C + 1];
+  const int v = threadIdx.x % VPP, c8 = v * 8, slot = threadIdx.x / VPP;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  }
+  float sb = 0.f;
+  const int hw = h * w;
+  for (int64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int64_t map = unit / chunks;
+    const int p0 = (int)(unit % chunks) * PPC + slot, p1 = p0 + 256 / VPP;
+    const float* dmap = dout + map * hw;
+    const bool ok0 = p0 < hw, ok1 = p1 < hw;
+    const uint4 xa = ld_stream16(x + (map * hw + (ok0 ? p0 : 0)) * ld + c8), xb = ld_stream16(x + (map * hw + (ok1 ? p1 : 0)) * ld + c8);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 0 ? ok0 : ok1) {
+        const int pix = u == 0 ? p0 : p1, yy = pix / w, xx = pix - yy * w;
+        float d[9], f[8];
+        out1_neighbours(dmap, yy, xx, h, w, d);
+        bf16x8_to_f32(u == 0 ? xa : xb, f);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[t][i] += d[t] * f[i];
+        }
+        if (v == 0) sb += d[4];
+      }
+    }
+  }
+  // lanes of a warp with the same channel vector: lane % VPP == v  ->  butterfly over the pixel-slot bits
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = acc[t][i];
+#pragma unroll
+      for (int o = VPP; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[t][i] = a;
+    }
+  }
+#pragma unroll
+  for (int o = VPP; o < 32; o <<= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < VPP) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][t * kO1C + c8 + i] = acc[t][i];
+    }
+    if (lane == 0) red[warp][9 * kO1C] = sb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * kO1C + 1; i += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += red[k][i];
+    if (a != 0.f) atomicAdd(i < 9 * kO1C ? dw + i : dbias, a);
+  }
+}
+
 }  // namespace
 }  // namespace svl
 
@@ -632,13 +1021,27 @@ extern "C" int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const fl
   SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_fwd: grid too large");
   SVL_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * maps * G, ST));
   SVL_CUDA(cudaMemsetAsync(rstd, 0, sizeof(float) * maps * G, ST));
-  gn_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, mean, rstd, hw, C, G, splits);
+  // all-bf16 fast path (every large GroupNorm of the throughput mode); anything else takes the generic kernels
+  const int vshift = log2_exact(C / 8);
+  const bool fast = x_dtype == SVL_BF16 && out_dtype == SVL_BF16 && (!res || res_dtype == SVL_BF16) && al16(x) && al16(out) && al16(res) &&
+                    ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldres % 8 == 0) && vshift >= 0 && maps <= 65535 && C / G == 16 &&
+                    (int64_t)hw * (C / 8) < (1ll << 30);
+  if (fast)
+    gn_stats_bf16_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>((const __nv_bfloat16*)x, ldx, mean, rstd, hw, C, G, splits);
+  else
+    gn_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, mean, rstd, hw, C, G, splits);
   SVL_LAUNCH_CHECK();
   gn_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(mean, rstd, maps * G, (float)hw * (C / G), eps);
   SVL_LAUNCH_CHECK();
   SVL_CHECK_ARG(C / G == 16, "svl_gn_relu_fwd: the apply kernel is specialised for 16 channels per group");
-  gn_apply_kernel<<<ew_grid(maps * hw * G, 256), 256, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean, rstd, maps,
-                                                              hw, C, G);
+  if (fast) {
+    const dim3 grid((unsigned)cdiv((int64_t)hw * (C / 8), 256 * kGnApplyU), (unsigned)maps);
+    gn_apply_bf16_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)x, ldx, gamma, beta, (__nv_bfloat16*)out, ldo, (const __nv_bfloat16*)res, ldres,
+                                              mean, rstd, hw, C, G, vshift);
+  } else {
+    gn_apply_kernel<<<ew_grid(maps * hw * G, 256), 256, 0, ST>>>(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, res, res_dtype, ldres, mean, rstd,
+                                                                maps, hw, C, G);
+  }
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
@@ -654,6 +1057,19 @@ extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const
   const int splits = gn_splits(maps, hw, C);
   SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_bwd: grid too large");
   SVL_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * maps * G * 2, ST));
+  const int vshift = log2_exact(C / 8);
+  const bool fast = dy_dtype == SVL_BF16 && x_dtype == SVL_BF16 && dx_dtype == SVL_BF16 && al16(dy) && al16(x) && al16(dx) && lddy % 8 == 0 &&
+                    ldx % 8 == 0 && lddx % 8 == 0 && vshift >= 0 && maps <= 65535 && (int64_t)hw * (C / 8) < (1ll << 30);
+  if (fast) {
+    gn_bwd_stats_bf16_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, gamma,
+                                                                              beta, mean, rstd, ws, dgamma, dbeta, hw, C, G, splits);
+    SVL_LAUNCH_CHECK();
+    const dim3 grid((unsigned)cdiv((int64_t)hw * (C / 8), 256 * kGnBwdApplyU), (unsigned)maps);
+    gn_bwd_apply_bf16_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, gamma, beta, mean, rstd, ws,
+                                                  (__nv_bfloat16*)dx, lddx, hw, C, G, vshift);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   gn_bwd_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dgamma,
                                                                        dbeta, hw, C, G, splits);
   SVL_LAUNCH_CHECK();
@@ -753,13 +1169,28 @@ extern "C" int svl_conv_out1_fwd(const void* x, int dtype, int64_t ld, const flo
   const int tiles_x = (w + kO1TW - 1) / kO1TW, tiles_y = (h + kO1TH - 1) / kO1TH;
   const size_t smem = (size_t)(9 * C + 9 * kO1HW) * sizeof(float);
   SVL_CHECK_ARG(maps * tiles_x * tiles_y < (1ll << 31), "svl_conv_out1_fwd: grid too large");
-  conv_out1_fwd_kernel<<<(unsigned)(maps * tiles_x * tiles_y), 256, smem, ST>>>(x, dtype, ld, wgt, bias, out, h, w, C, tiles_x, tiles_y);
+  if (dtype == SVL_BF16 && C == kO1C && ld % 8 == 0 && al16(x) && al16(wgt))
+    conv_out1_fwd_bf16_kernel<<<(unsigned)(maps * tiles_x * tiles_y), 256, 0, ST>>>((const __nv_bfloat16*)x, ld, wgt, bias, out, h, w, tiles_x, tiles_y);
+  else
+    conv_out1_fwd_kernel<<<(unsigned)(maps * tiles_x * tiles_y), 256, smem, ST>>>(x, dtype, ld, wgt, bias, out, h, w, C, tiles_x, tiles_y);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
 extern "C" int svl_conv_out1_bwd(const float* dout, const void* x, int x_dtype, int64_t ldx, const float* wgt, void* dx, int dx_dtype, int64_t lddx,
                                  float* dw, float* dbias, int64_t maps, int h, int w, int C, void* stream) {
   SVL_CHECK_ARG(dout && x && wgt && dx && dw && dbias && C % 8 == 0 && 9 * C <= 1024, "svl_conv_out1_bwd: bad arguments");
+  if (x_dtype == SVL_BF16 && dx_dtype == SVL_BF16 && C == kO1C && ldx % 8 == 0 && lddx % 8 == 0 && al16(x) && al16(dx) && al16(wgt) && maps <= 65535 &&
+      (int64_t)h * w * (C / 8) < (1ll << 30)) {
+    const dim3 grid((unsigned)cdiv((int64_t)h * w * (kO1C / 8), 256 * 4), (unsigned)maps);
+    conv_out1_dgrad_bf16_kernel<<<grid, 256, 0, ST>>>(dout, wgt, (__nv_bfloat16*)dx, lddx, h, w);
+    SVL_LAUNCH_CHECK();
+    const int ppc = 256 / (kO1C / 8) * 2, chunks = (h * w + ppc - 1) / ppc;
+    const int64_t units = maps * chunks;
+    conv_out1_wgrad_bf16_kernel<<<(unsigned)(units < 148 * 2 ? units : 148 * 2), 256, 0, ST>>>(dout, (const __nv_bfloat16*)x, ldx, dw, dbias, h, w, chunks,
+                                                                                          units);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   conv_out1_dgrad_kernel<<<ew_grid(maps * h * w * (C / 8)), 256, 9 * C * sizeof(float), ST>>>(dout, wgt, dx, dx_dtype, lddx, maps, h, w, C);
   SVL_LAUNCH_CHECK();
   const int tiles_x = (w + kO1TW - 1) / kO1TW, tiles_y = (h + kO1TH - 1) / kO1TH;

@@ -163,8 +163,13 @@ upsample_ce_kernel(const __grid_constant__ CeParams p) {
   for (int t = 0; t < kMaxTargets; ++t) coef[t] = t < p.num_targets ? __ldg(p.coef[t]) : 0.f;
   float lsum[kMaxTargets] = {0.f, 0.f, 0.f};
 
-  for (int k = threadIdx.x; k < TILE * TILE; k += blockDim.x) {
-    const int Y = Y0 + k / TILE, X = X0 + k % TILE;
+  // Pixel order inside the tile: the 32 lanes of a warp take the SAME sub-position of 32 DIFFERENT 4x4 pixel cells (cell = tid % 64,
+  // row of the cell = tid / 64, column = iteration), so at the usual 4x upsampling every lane of a gradient atomic below hits its own
+  // low-res entry; with row-major lanes four neighbours shared each entry and the shared-memory atomics serialised 4-way.
+  static_assert(TILE == 32, "the cell mapping below covers a 32 x 32 tile with 256 threads x 4 iterations");
+  for (int it = 0; it < 4; ++it) {
+    const int cell = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    const int Y = Y0 + (cell >> 3) * 4 + sub, X = X0 + (cell & 7) * 4 + it;
     if (Y >= p.H || X >= p.W) continue;
     int y0, y1, x0, x1;
     float wy, wx;

@@ -235,6 +235,87 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, co
   }
 }
 
+// Lean variant for the common case (no weight gradients -- the encoder's LayerNorms are frozen, vlm.py:80-88 -- dy in f32 or bf16,
+// bf16 / f32 / no operand copy): the generic kernel above keeps xhat, g, the residual and gamma of the whole row in registers
+// (128 regs, 13 warps per SM, 86 % of issue slots without an eligible warp, 2.7 TB/s: profiles/r01_ncu_targets.md).  Here a warp
+// keeps only the raw x, dy and residual vectors, recomputes xhat after the reduction, reads gamma from shared memory and runs a
+// persistent grid-stride loop over rows, so ~24 warps per SM each have their whole row (and residual) in flight.
+template <int NV, bool DY_BF16>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+layernorm_bwd_lean_kernel(const void* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres1,
+                          const float* __restrict__ dres2, float* __restrict__ dx, void* __restrict__ dx_act, int act_dtype, int64_t ld_act,
+                          int64_t rows) {
+  constexpr int c = NV * 128;
+  __shared__ float4 sgm[NV * 32];
+  for (int i = threadIdx.x; i < NV * 32; i += blockDim.x) sgm[i] = __ldg((const float4*)gamma + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    float4 xv[NV];
+    uint2 db[DY_BF16 ? NV : 1];
+    float4 df[DY_BF16 ? 1 : NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      xv[i] = *(const float4*)(x + row * ldx + col);
+      if (DY_BF16) db[i] = *(const uint2*)((const __nv_bfloat16*)dy + row * lddy + col);
+      else df[i] = *(const float4*)((const float*)dy + row * lddy + col);
+    }
+    // the residual gradients are only needed after the reduction: pull their lines into L2 now (no registers), load them at use
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (dres1) asm volatile("prefetch.global.L2 [%0];" ::"l"(dres1 + row * (int64_t)c + (i * 32 + lane) * 4));
+      if (dres2) asm volatile("prefetch.global.L2 [%0];" ::"l"(dres2 + row * (int64_t)c + (i * 32 + lane) * 4));
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 gm = sgm[i * 32 + lane];
+      float d[4];
+      if (DY_BF16) {
+        const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&db[i].x), b = __bfloat1622float2(*(const __nv_bfloat162*)&db[i].y);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+      } else {
+        d[0] = df[i].x; d[1] = df[i].y; d[2] = df[i].z; d[3] = df[i].w;
+      }
+      const float g0 = d[0] * gm.x, g1 = d[1] * gm.y, g2 = d[2] * gm.z, g3 = d[3] * gm.w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += g0 * ((xv[i].x - mu) * rs) + g1 * ((xv[i].y - mu) * rs) + g2 * ((xv[i].z - mu) * rs) + g3 * ((xv[i].w - mu) * rs);
+    }
+    s1 = warp_sum(s1) * (1.f / c);
+    s2 = warp_sum(s2) * (1.f / c);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 gm = sgm[i * 32 + lane];
+      float d[4];
+      if (DY_BF16) {
+        const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&db[i].x), b = __bfloat1622float2(*(const __nv_bfloat162*)&db[i].y);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+      } else {
+        d[0] = df[i].x; d[1] = df[i].y; d[2] = df[i].z; d[3] = df[i].w;
+      }
+      float o[4];
+      o[0] = rs * (d[0] * gm.x - s1 - (xv[i].x - mu) * rs * s2);
+      o[1] = rs * (d[1] * gm.y - s1 - (xv[i].y - mu) * rs * s2);
+      o[2] = rs * (d[2] * gm.z - s1 - (xv[i].z - mu) * rs * s2);
+      o[3] = rs * (d[3] * gm.w - s1 - (xv[i].w - mu) * rs * s2);
+      if (dres1) {
+        const float4 u = *(const float4*)(dres1 + row * (int64_t)c + col);
+        o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
+      }
+      if (dres2) {
+        const float4 u = *(const float4*)(dres2 + row * (int64_t)c + col);
+        o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
+      }
+      if (dx) *(float4*)(dx + row * (int64_t)c + col) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dx_act) store4_act(dx_act, act_dtype, row * ld_act + col, ld_act / 2, o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- L2 normalisation
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 l2norm_fwd_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, void* __restrict__ y_act, int act_dtype, int64_t ld_act,
@@ -324,6 +405,57 @@ colsum_kernel(const void* __restrict__ x, int x_dtype, int64_t ld, int64_t rows,
   }
 }
 
+// Streaming variant (16-byte-aligned rows of bf16 / f32, cols % 8 == 0): the thread block is shaped to the matrix -- vt column
+// lanes (8 columns each) x 256 / vt row lanes, so a 32-column gradient still uses all 256 threads -- and every thread keeps four
+// rows (64-128 bytes) in flight.  The generic kernel above had 1 load in flight and idled 7/8 of the block on narrow matrices.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+colsum_stream_kernel(const void* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out, int vt_shift) {
+  __shared__ float red[256 * 8 + 256];           // [nrl][vt * 8 + 1], nrl * vt = 256, nrl <= 256
+  const int vt = 1 << vt_shift, cl = threadIdx.x & (vt - 1), rl = threadIdx.x >> vt_shift, nrl = 256 >> vt_shift;
+  const int col = (blockIdx.x * vt + cl) * 8;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (col < cols) {
+    const int64_t stride = (int64_t)gridDim.y * nrl;
+    for (int64_t r = (int64_t)blockIdx.y * nrl + rl; r < rows; r += 4 * stride) {
+      float f[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t rr = r + u * stride < rows ? r + u * stride : r;
+        if (BF16) {
+          const uint4 v = __ldg((const uint4*)((const __nv_bfloat16*)x + rr * ld + col));
+          bf16x8_to_f32(v, f[u]);
+        } else {
+          const float4 a = __ldg((const float4*)((const float*)x + rr * ld + col)), b = __ldg((const float4*)((const float*)x + rr * ld + col) + 1);
+          f[u][0] = a.x; f[u][1] = a.y; f[u][2] = a.z; f[u][3] = a.w; f[u][4] = b.x; f[u][5] = b.y; f[u][6] = b.z; f[u][7] = b.w;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * stride < rows) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += f[u][i];
+        }
+      }
+    }
+  }
+  // red[rl][cl * 8 + i], row pitch vt * 8 + 1
+  const int pitch = vt * 8 + 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl * pitch + cl * 8 + i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < vt * 8) {
+    const int c = blockIdx.x * vt * 8 + threadIdx.x;
+    if (c < cols) {
+      float v = 0.f;
+      for (int j = 0; j < nrl; ++j) v += red[j * pitch + threadIdx.x];
+      atomicAdd(out + c, v);
+    }
+  }
+}
+
 // out[i] (+)= sum_b x[b, i]
 __global__ void batch_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int b, int64_t inner, int accumulate) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < inner; i += (int64_t)gridDim.x * blockDim.x) {
@@ -387,6 +519,17 @@ extern "C" int svl_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, con
   if (dgamma && grid > 296) grid = 296;     // fewer, longer-lived blocks: cheaper dgamma/dbeta reduction
   SVL_CHECK_ARG(c == 768 || c == 256, "svl_layernorm_bwd: rows of %d elements are not instantiated (768: ViT, 256: class attention)", c);
   SVL_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "svl_layernorm_bwd: dgamma and dbeta go together");
+  if (!dgamma && c == 768 && (dy_dtype == SVL_F32 || dy_dtype == SVL_BF16) && lddy % 4 == 0 && ldx % 4 == 0 && ld_act % 4 == 0) {
+    const int lean_grid = (int)(cdiv(rows, kWarpsPerBlock) < 148 * 3 ? cdiv(rows, kWarpsPerBlock) : 148 * 3);     // persistent: 3 CTAs per SM
+    if (dy_dtype == SVL_BF16)
+      layernorm_bwd_lean_kernel<6, true><<<lean_grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, dres1, dres2, dx,
+                                                                                                   dx_act, act_dtype, ld_act, rows);
+    else
+      layernorm_bwd_lean_kernel<6, false><<<lean_grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, gamma, mean, rstd, dres1, dres2, dx,
+                                                                                                    dx_act, act_dtype, ld_act, rows);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
 #define SVL_LN_BWD(NV, WG)                                                                                                                       \
   layernorm_bwd_kernel<NV, WG><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dy, dy_dtype, lddy, x, ldx, gamma, mean, rstd, dres1, dres2, \
                                                                                         dx, dx_act, act_dtype, ld_act, dgamma, dbeta, rows)
@@ -429,6 +572,21 @@ extern "C" int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t 
 extern "C" int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
   SVL_CHECK_ARG(x && out, "svl_colsum: null pointer");
   if (rows == 0 || cols == 0) return SVL_OK;
+  if ((x_dtype == SVL_F32 || x_dtype == SVL_BF16) && cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+    int vt_shift = 0;
+    while ((1 << vt_shift) < cols / 8 && vt_shift < 5) ++vt_shift;            // column lanes per block: next power of two of cols / 8, <= 32
+    const int vt = 1 << vt_shift, nrl = 256 >> vt_shift;
+    const int xt = (int)cdiv(cols / 8, vt);
+    int64_t ysplit = cdiv(rows, (int64_t)nrl * 8);                            // >= 8 rows per thread
+    const int64_t cap = (148 * 8 + xt - 1) / xt;
+    if (ysplit > cap) ysplit = cap;
+    if (ysplit < 1) ysplit = 1;
+    dim3 grid(xt, (unsigned)ysplit);
+    if (x_dtype == SVL_BF16) colsum_stream_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, out, vt_shift);
+    else colsum_stream_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, out, vt_shift);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   const int xt = (cols + 255) / 256;
   int64_t ysplit = cdiv(rows, 8 * 16);
   const int64_t cap = (148 * 8 + xt - 1) / xt;

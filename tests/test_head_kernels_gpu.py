@@ -144,3 +144,28 @@ def test_map_sum_bcast(L):
     y = x.clone()
     L.call("svl_map_bcast_add", y, out, L.F32, C, maps, hw, C, 2.0)
     assert _rel(y, x + 2 * out[:, None]) < 1e-6
+
+
+@pytest.mark.parametrize("maps,h,w", [(3, 20, 24), (2, 128, 128), (5, 9, 70)])
+def test_conv_out1_bf16_fast_path(L, maps, h, w):
+    """the all-bf16 kernels of the 32 -> 1 output conv (ragged tiles, full-size maps) against F.conv2d on the bf16-rounded input"""
+    C = 32
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xb = torch.randn(maps, h, w, C, device="cuda", generator=g).to(torch.bfloat16)
+    x = xb.float()
+    wt = torch.randn(1, C, 3, 3, device="cuda", generator=g)
+    bias = torch.randn(1, device="cuda", generator=g)
+    dout = torch.randn(maps, h, w, device="cuda", generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = F.conv2d(xr.permute(0, 3, 1, 2), wr, br, padding=1)[:, 0]
+    ref.backward(dout)
+    wk = wt[0].permute(1, 2, 0).reshape(-1).contiguous()
+    out = torch.empty(maps, h, w, device="cuda")
+    L.call("svl_conv_out1_fwd", xb, L.BF16, C, wk, bias, out, maps, h, w, C)
+    assert _rel(out, ref) < 1e-5
+    dx = torch.empty(maps, h, w, C, device="cuda", dtype=torch.bfloat16)
+    dw, dbias = torch.zeros(9 * C, device="cuda"), torch.zeros(1, device="cuda")
+    L.call("svl_conv_out1_bwd", dout, xb, L.BF16, C, wk, dx, L.BF16, C, dw, dbias, maps, h, w, C)
+    assert _rel(dx, xr.grad) < 5e-3                         # bf16 output rounding
+    assert _rel(dw.view(3, 3, C).permute(2, 0, 1)[None], wr.grad) < 1e-4
+    assert _rel(dbias, br.grad) < 1e-4

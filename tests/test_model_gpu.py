@@ -148,25 +148,29 @@ def test_semivl_step_matches_reference_golden(golden_dir, name):
 
 def test_graph_replay_matches_eager_steps(text_dir):
     """`graphed_supervised_step` (one CUDA-graph launch per step, AdamW scalars from device memory) against the eager kernel
-    sequence over 4 optimizer steps with changing inputs: same losses, same parameters (up to the order of the fp32 atomics)."""
+    sequence over 4 optimizer steps with changing inputs.  The fp32 atomics of the statistics / weight-gradient reductions make
+    two EAGER runs differ too (and the random-init head amplifies it), so the bound is calibrated on an eager-vs-eager pair:
+    graph-vs-eager must sit within 3x that noise floor (precise mode, where the floor is small)."""
     from semivl_b200.train import OptimCfg, Trainer
     crop, b = 64, 2
     g = torch.Generator().manual_seed(5)
     imgs = [torch.randn(b, 3, crop, crop, generator=g).cuda() for _ in range(4)]
     masks = [torch.randint(0, 21, (b, crop, crop), generator=g).cuda() for _ in range(4)]
     runs = []
-    for graphed in (False, True):
-        m, mc, sd = _build(crop, False)
+    for graphed in (False, False, True):
+        m, mc, sd = _build(crop, True)
         tr = Trainer(m, OptimCfg(lr=1e-4, total_iters=10))
         losses = []
         for img, mask in zip(imgs, masks):
             out = tr.graphed_supervised_step(img, mask) if graphed else tr.supervised_step(img, mask)
             losses.append(out.item())
         assert tr.iters == 4
-        runs.append((losses, tr.p_flat.clone(), tr.m_flat.clone()))
-    (l0, p0, m0), (l1, p1, m1) = runs
-    print("eager", l0, "graph", l1)
-    assert np.allclose(l0, l1, rtol=2e-3)
-    # AdamW's first steps move every weight by ~lr regardless of |g|: compare the moments (linear in g) and bound the parameter drift
-    assert (m0 - m1).norm().item() <= 5e-2 * m0.norm().item()
-    assert (p0 - p1).abs().max().item() <= 4 * 1e-3 * 4            # <= steps * head lr (1e-4 * 10) * a few
+        runs.append((losses, tr.p_flat.clone(), tr.m_flat.clone(), tr.v_flat.clone()))
+    (l0, p0, m0, v0), (l1, p1, m1, v1), (l2, p2, m2, v2) = runs
+    rel = lambda a, b_: ((a - b_).norm() / a.norm()).item()
+    floor_m, floor_v, floor_p = rel(m0, m1), rel(v0, v1), (p0 - p1).abs().max().item()
+    print("eager", l0, "graph", l2, "noise floor m/v/p", floor_m, floor_v, floor_p, "graph m/v/p", rel(m0, m2), rel(v0, v2), (p0 - p2).abs().max().item())
+    assert np.allclose(l0, l2, rtol=1e-4)
+    assert rel(m0, m2) <= max(3 * floor_m, 1e-3)
+    assert rel(v0, v2) <= max(3 * floor_v, 1e-3)
+    assert (p0 - p2).abs().max().item() <= max(3 * floor_p, 1e-5)

@@ -74,6 +74,30 @@ def test_layernorm(ops, rows, c):
     xr.grad = None
     F.layer_norm(xr, (c,), gamma, beta, 1e-6).backward(dy.to(torch.bfloat16).float())
     assert _rel(dx2, xr.grad) < 2e-5
+    # the encoder's common call (lean kernel for c = 768): bf16 / f32 dy, two residual gradients, bf16 operand copy, no weight grads
+    r2 = torch.randn(rows, c, device="cuda", generator=g)
+    for dyv, dt in ((dy.to(torch.bfloat16), L.BF16), (dy, L.F32)):
+        dx3, dxa3 = ops.layernorm_bwd(dyv, dt, x, gamma, mean, rstd, dres1=r1, dres2=r2, act_precise=False)
+        xr.grad = None
+        F.layer_norm(xr, (c,), gamma, beta, 1e-6).backward(dyv.float())
+        assert _rel(dx3, xr.grad + r1 + r2) < 2e-5
+        assert _rel(dxa3, xr.grad + r1 + r2) < 5e-3
+    _, dxa4 = ops.layernorm_bwd(dy, L.F32, x, gamma, mean, rstd, dres1=r1, want_dx=False, act_precise=False)
+    xr.grad = None
+    F.layer_norm(xr, (c,), gamma, beta, 1e-6).backward(dy)
+    assert _rel(dxa4, xr.grad + r1) < 5e-3
+
+
+@pytest.mark.parametrize("rows,cols,ld", [(16400, 2304, 2304), (5000, 32, 32), (3001, 48, 128), (777, 768, 768), (9, 8, 8), (2000, 200, 200)])
+def test_colsum_shapes(ops, rows, cols, ld):
+    """bias gradients: wide token matrices, 32-column conv gradients (all 256 threads busy), strided views, ragged row counts"""
+    from semivl_b200 import lib as L
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(rows, ld, device="cuda", generator=g)
+    for t, dt, tol in ((x, L.F32, 1e-5), (x.to(torch.bfloat16), L.BF16, 1e-5)):
+        out = torch.full((cols,), 2.0, device="cuda")
+        ops.colsum(t, dt, rows, cols, out, ld=ld)
+        assert _rel(out, 2.0 + t[:, :cols].float().sum(0)) < tol
 
 
 def test_l2norm_cast_colsum(ops):

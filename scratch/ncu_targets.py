@@ -43,6 +43,14 @@ m_, r_ = ops.gn_relu_fwd(xm, L.BF16, ga, be, ym, L.BF16, maps, hw, C, G)
 dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
 targets["gn_fwd_336x128x128x32"] = lambda: ops.gn_relu_fwd(xm, L.BF16, ga, be, ym, L.BF16, maps, hw, C, G)
 targets["gn_bwd_336x128x128x32"] = lambda: ops.gn_relu_bwd(dm, L.BF16, xm, L.BF16, ga, be, m_, r_, ym, L.BF16, dg, db, maps, hw, C, G)
+u2 = bf(maps * hw, C); low = torch.empty(16, 21, 128, 128, device=dev); wk = torch.randn(9 * C, device=dev); ob = torch.zeros(1, device=dev)
+dlow = torch.randn(16, 21, 128, 128, device=dev); du2 = torch.empty_like(u2); dw9 = torch.zeros(9 * C, device=dev); dbo = torch.zeros(1, device=dev)
+targets["conv_out1_fwd"] = lambda: L.call("svl_conv_out1_fwd", u2, L.BF16, C, wk, ob, low, maps, 128, 128, C)
+targets["conv_out1_bwd"] = lambda: L.call("svl_conv_out1_bwd", dlow, u2, L.BF16, C, wk, du2, L.BF16, C, dw9, dbo, maps, 128, 128, C, n_launch=2)
+import ctypes as Cc
+lab = torch.randint(0, 21, (16, 512, 512), device=dev); coef = torch.full((1,), 1e-6, device=dev); lossb = torch.zeros(3, device=dev); dl2 = torch.zeros_like(low)
+arr = lambda t: (Cc.c_void_p * 3)(t.data_ptr() if t is not None else None, None, None)
+targets["upsample_ce"] = lambda: L.call("svl_upsample_ce", low, dl2, 16, 21, 128, 128, 512, 512, 1, arr(lab), arr(None), arr(coef), lossb, 1.0, 255)
 sel = sys.argv[1:] or list(targets)
 for name in sel:
     fn = targets[name]

@@ -105,6 +105,7 @@ class MaskClipVisionTransformer(nn.Module):
         assert drop_rate == 0.0 and attn_drop_rate == 0.0 and drop_path_rate == 0.0, "dropout inside the encoder is not supported"
         assert embed_dims == num_heads * 64, "attention kernels are specialised for head_dim 64"
         assert interpolate_mode == 'bicubic'
+        self.interpolate_mode = interpolate_mode
         for k, v in unsupported.items():
             assert not v, f"unsupported backbone option {k}={v}"
         self.img_size, self.patch_size, self.pretrained, self.norm_eval = img_size, patch_size, pretrained, norm_eval
@@ -129,17 +130,27 @@ class MaskClipVisionTransformer(nn.Module):
         self._last_want_global = True
 
     def init_weights(self):
-        """Random-init branch of the reference (maskclip_vit.py:413-429): trunc-normal(0.02) for pos/cls and Linear weights."""
+        """maskclip_vit.py:378-429.  `pretrained` (a converted CLIP checkpoint, see semivl_b200/convert_clip_weights.py): strip the
+        'backbone.' prefix, resize the position table to this model's token grid (bicubic, cls entry kept), give the CLIP projection
+        its 1x1-conv shape (or drop it when the model does not return the CLIP embedding), load non-strictly -- the reference's
+        Pretrained branch.  Otherwise the random-init branch: trunc-normal(0.02) for pos/cls and Linear weights."""
         if isinstance(self.pretrained, str):
             sd = torch.load(self.pretrained, map_location='cpu')
             sd = sd.get('state_dict', sd)
-            if sd['pos_embed'].shape != self.pos_embed.shape:          # maskclip_vit.py:395-408
+            sd = {k.replace('backbone.', ''): v for k, v in sd.items()}
+            if 'pos_embed' in sd and sd['pos_embed'].shape != self.pos_embed.shape:          # maskclip_vit.py:395-408
                 g = int(round((sd['pos_embed'].shape[1] - 1) ** 0.5))
                 hw = (self.img_size[0] // self.patch_size, self.img_size[1] // self.patch_size)
                 grid = sd['pos_embed'][:, 1:].reshape(1, g, g, -1).permute(0, 3, 1, 2)
-                grid = torch.nn.functional.interpolate(grid, size=hw, mode='bicubic', align_corners=False)
+                grid = torch.nn.functional.interpolate(grid, size=hw, mode=self.interpolate_mode, align_corners=False)
                 sd['pos_embed'] = torch.cat((sd['pos_embed'][:, :1], grid.flatten(2).transpose(1, 2)), dim=1)
-            self.load_state_dict(sd, strict=False)
+            if 'proj.weight' in sd:
+                own = dict(self.named_parameters()).get('proj.weight')
+                if own is None:
+                    sd.pop('proj.weight')
+                elif sd['proj.weight'].dim() == 2 and own.dim() == 4:
+                    sd['proj.weight'] = sd['proj.weight'][:, :, None, None]
+            self.load_report = self.load_state_dict(sd, strict=False)
             return
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
         nn.init.trunc_normal_(self.cls_token, std=0.02)

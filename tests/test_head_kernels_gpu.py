@@ -90,6 +90,12 @@ def test_pool_unpool_tokens(L, B, N, h, w):
     dtok = torch.empty_like(tk)
     L.call("svl_unpool_bwd", dout, L.F32, C, dtok, C + Ct, B, N, h, w, C, hp, wp)
     assert _rel(dtok, tk.grad) < 1e-5
+    # bf16 gradient input (vectorised kernel): exact on the bf16-rounded values
+    dtok_b = torch.full_like(tk, 7.0)
+    L.call("svl_unpool_bwd", dout.to(torch.bfloat16), L.BF16, C, dtok_b, C + Ct, B, N, h, w, C, hp, wp)
+    tk.grad = None
+    (xr + F.interpolate(t2, size=(h, w), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)).backward(dout.to(torch.bfloat16).float())
+    assert _rel(dtok_b, tk.grad) < 1e-5
     # pool backward
     dtk = torch.randn(B * hp * wp * N, C + Ct, device="cuda", generator=g)
     xr2 = x.clone().requires_grad_(True)

@@ -163,3 +163,49 @@ def test_poly_lr_schedule_matches_reference_order(built):
     a, b_, bc1, bc2s = tr._step_scalars(3)
     assert np.isclose(a, seen[2] * 0.01) and np.isclose(b_, seen[2] * 10.0)
     assert np.isclose(bc1, 1 - 0.9 ** 3) and np.isclose(bc2s, (1 - 0.999 ** 3) ** 0.5)
+
+
+def test_clip_checkpoint_conversion_and_pretrained_load(built, tmp_path):
+    """third_party/maskclip/convert_clip_weights.py:27-64 + maskclip_vit.py:378-410: an OpenAI-CLIP-named visual state dict is renamed,
+    saved, and loaded by `pretrained=` into a model with a DIFFERENT token grid (position table resized on load, cls entry kept)."""
+    from oracle import semivl_oracle as O
+    from semivl_b200.convert_clip_weights import clip_visual_to_mmseg, rename_visual_key
+    from semivl_b200.model.maskclip_vit import MaskClipVisionTransformer
+    assert rename_visual_key("transformer.resblocks.7.attn.in_proj_weight") == "layers.7.attn.attn.in_proj_weight"
+    assert rename_visual_key("transformer.resblocks.0.mlp.c_fc.bias") == "layers.0.ffn.layers.0.0.bias"
+    assert rename_visual_key("transformer.resblocks.11.mlp.c_proj.weight") == "layers.11.ffn.layers.1.weight"
+    assert rename_visual_key("transformer.resblocks.3.ln_2.weight") == "layers.3.ln2.weight"
+    assert rename_visual_key("ln_pre.bias") == "ln0.bias" and rename_visual_key("ln_post.weight") == "ln1.weight"
+    E, layers, g0 = 64, 2, 14                                # a small tower with CLIP's structure: 224 / 16 = 14 x 14 positions
+    gen = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=gen).half()     # CLIP checkpoints are fp16
+    clip = {"visual.class_embedding": r(E), "visual.positional_embedding": r(g0 * g0 + 1, E), "visual.conv1.weight": r(E, 3, 16, 16),
+            "visual.ln_pre.weight": r(E), "visual.ln_pre.bias": r(E), "visual.ln_post.weight": r(E), "visual.ln_post.bias": r(E),
+            "visual.proj": r(E, 512), "logit_scale": r(1), "token_embedding.weight": r(10, 8)}
+    for i in range(layers):
+        pre = f"visual.transformer.resblocks.{i}."
+        clip.update({pre + "attn.in_proj_weight": r(3 * E, E), pre + "attn.in_proj_bias": r(3 * E), pre + "attn.out_proj.weight": r(E, E),
+                     pre + "attn.out_proj.bias": r(E), pre + "ln_1.weight": r(E), pre + "ln_1.bias": r(E), pre + "ln_2.weight": r(E),
+                     pre + "ln_2.bias": r(E), pre + "mlp.c_fc.weight": r(4 * E, E), pre + "mlp.c_fc.bias": r(4 * E),
+                     pre + "mlp.c_proj.weight": r(E, 4 * E), pre + "mlp.c_proj.bias": r(E)})
+    conv = clip_visual_to_mmseg(clip, backbone_prefix=True)
+    assert all(v.dtype == torch.float32 for v in conv["state_dict"].values())
+    path = str(tmp_path / "clip2mmseg.pth")
+    torch.save(conv, path)
+    kw = dict(patch_size=16, patch_bias=False, in_channels=3, embed_dims=E, num_layers=layers, num_heads=1, mlp_ratio=4, out_indices=(0, layers),
+              qkv_bias=True, with_cls_token=True, output_cls_token=False, norm_cfg=dict(type='LN', eps=1e-6), act_cfg=dict(type='GELU'),
+              patch_norm=False, pre_norm=True, final_norm=True, return_clip_embed=True, return_qkv=True, interpolate_mode='bicubic', num_fcs=2)
+    try:
+        m = MaskClipVisionTransformer(img_size=(96, 96), pretrained=path, **kw)
+    except (AssertionError, TypeError, ValueError) as e:         # the engine is specialised for CLIP ViT-B/16 widths
+        pytest.skip(f"small tower not constructible: {e}")
+    m.init_weights()
+    rep = m.load_report
+    assert not rep.unexpected_keys, rep.unexpected_keys
+    assert not rep.missing_keys, rep.missing_keys
+    sd = m.state_dict()
+    assert torch.equal(sd["layers.1.ffn.layers.0.0.weight"], clip["visual.transformer.resblocks.1.mlp.c_fc.weight"].float())
+    assert torch.equal(sd["cls_token"], clip["visual.class_embedding"].float()[None, None])
+    assert sd["proj.weight"].shape == (512, E, 1, 1) and torch.equal(sd["proj.weight"][:, :, 0, 0], clip["visual.proj"].float().t())
+    want = O.resize_pos_embed(clip["visual.positional_embedding"].float()[None], (6, 6), (g0, g0))
+    assert sd["pos_embed"].shape == (1, 37, E) and torch.allclose(sd["pos_embed"], want, atol=1e-6)

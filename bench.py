@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--crop", type=int, default=CROP)
     ap.add_argument("--nclass", type=int, default=NCLASS)
     ap.add_argument("--precise", action="store_true", help="split-bf16 parity mode instead of the bf16 throughput mode")
+    ap.add_argument("--graph-multi", action="store_true", help="N > 1: capture the step (NCCL exchange included) in a CUDA graph as well")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~690 kernels of the step eagerly instead of replaying the captured CUDA graph (N=1)")
     ap.add_argument("--cpu-crop", type=int, default=CROP)
@@ -172,7 +173,7 @@ def main():
     host = synth_batch(torch, b, args.crop, args.nclass, 1234 + rank, "cuda", semivl)
     resident = {k: v.to(dev) for k, v in host.items()}
 
-    use_graph = world == 1 and not semivl and not args.no_graph and args.crop % 16 == 0
+    use_graph = not semivl and not args.no_graph and args.crop % 16 == 0 and (world == 1 or args.graph_multi)
 
     def step(batch):
         if semivl:
@@ -267,8 +268,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown(world, tr)
         return
     peaks = {}
     try:
@@ -319,9 +319,24 @@ def main():
                                               f"{args.cpu_crop}x{args.cpu_crop}, N={args.nclass}: 14 timed steps after 2 warm-up ({cms:.0f} ms/step)"}
         except Exception as e:      # the baseline must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    teardown(world, tr)
+
+
+def teardown(world, tr):
+    """Release the captured graph before the communicator; a watchdog ends the process if the NCCL teardown stalls (seen once with a
+    live captured graph at N=2) -- the result line is already on stdout by then."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    killer = threading.Timer(20.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    tr._graph = None
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    killer.cancel()
 
 
 if __name__ == "__main__":

@@ -258,6 +258,20 @@ int svl_cutmix_img(const float* a, const float* b, const float* box, float* out,
 int svl_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
               int step, float gscale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation (third_party/unimatch/supervised.py:40-164): sliding-window stitching, arg-max, mIoU histograms.
+ * ---------------------------------------------------------------------------------------------- */
+/* dst[b, :, y1+y, x1+x] += f(src[b, :, sy+y, sx+x]) for y < ch, x < cw; f = softmax over the N classes (softmax != 0) or identity;
+ * count[b, y1+y, x1+x] += 1 when count != NULL.  dst [B,N,H,W], src [B,N,h,w], count [B,H,W], all f32
+ * (padded / plain sliding window: supervised.py:58-59,113-114; ZegCLIP window: supervised.py:88-92). */
+int svl_window_accumulate(float* dst, const float* src, float* count, int B, int N, int H, int W, int h, int w, int y1, int x1, int sy, int sx,
+                          int ch, int cw, int softmax, void* stream);
+int svl_divide_count(float* x, const float* count, int B, int N, int64_t plane, void* stream);                  /* x[b,n,p] /= count[b,p] */
+int svl_argmax_classes(const float* x, int64_t* out, int B, int N, int64_t plane, void* stream);              /* first maximal class */
+/* intersectionAndUnion (third_party/unimatch/util/utils.py:91-103): counts int64 [3][K] += {#(pred==target==k), #(pred==k), #(target==k)}
+ * with pred forced to ignore_index where target == ignore_index; bit-exact integer histograms */
+int svl_intersection_union(const int64_t* pred, const int64_t* target, int64_t n, int K, int ignore_index, int64_t* counts, void* stream);
+
 /* svl_adamw with the per-step scalars in DEVICE memory: hyper = {lr of class 0, lr of class 1, 1 - beta1^t, sqrt(1 - beta2^t)};
  * lets a captured CUDA graph of the whole training step be replayed under the poly LR schedule (semivl.py:338-345). */
 int svl_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int lr_index, float beta1, float beta2,

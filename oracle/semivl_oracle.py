@@ -434,3 +434,61 @@ def fixture_state_dict(shapes, seed=0, gain=1.0):
             t = r * (gain / math.sqrt(fan_in))
         sd[name] = t.contiguous()
     return sd
+
+
+# ----------------------------------------------------------------------------- evaluation (third_party/unimatch/supervised.py:40-164)
+def predict_reference(model, img, mask, mode, cfg):
+    """CPU restatement of `predict` for any callable `model(img) -> logits [b, nclass, h, w]`; returns (labels, stitched scores)."""
+    n = cfg["nclass"]
+    b, _, h, w = img.shape
+    if mode == "padded_sliding_window":                                      # supervised.py:41-65
+        grid, stride = cfg["crop_size"], cfg["stride"]
+        stride = int(grid * stride) if stride < 1 else stride
+        final = torch.zeros(b, n, h, w)
+        for row in range(0, h, stride):
+            for col in range(0, w, stride):
+                y2, x2 = min(h, row + grid), min(w, col + grid)
+                crop = torch.zeros(b, 3, grid, grid)
+                crop[:, :, :y2 - row, :x2 - col] = img[:, :, row:y2, col:x2]
+                final[:, :, row:y2, col:x2] += model(crop).softmax(dim=1)[:, :, :y2 - row, :x2 - col]
+    elif mode == "zegclip_sliding_window":                                   # supervised.py:67-103
+        s, c = cfg["stride"], cfg["crop_size"]
+        hg, wg = max(h - c + s - 1, 0) // s + 1, max(w - c + s - 1, 0) // s + 1
+        final, count = torch.zeros(b, n, h, w), torch.zeros(b, 1, h, w)
+        for hi in range(hg):
+            for wi in range(wg):
+                y2, x2 = min(hi * s + c, h), min(wi * s + c, w)
+                y1, x1 = max(y2 - c, 0), max(x2 - c, 0)
+                final += F.pad(model(img[:, :, y1:y2, x1:x2]), (x1, w - x2, y1, h - y2))
+                count[:, :, y1:y2, x1:x2] += 1
+        assert (count == 0).sum() == 0
+        final = F.interpolate(final / count, size=mask.shape[-2:], mode="bilinear", align_corners=True)
+    elif mode == "sliding_window":                                           # supervised.py:105-117
+        grid = cfg["crop_size"]
+        step = int(grid * 2 / 3)
+        final = torch.zeros(b, n, h, w)
+        for row in range(0, h, step):
+            for col in range(0, w, step):
+                y2, x2 = min(h, row + grid), min(w, col + grid)
+                final[:, :, row:y2, col:x2] += model(img[:, :, row:y2, col:x2]).softmax(dim=1)
+    else:
+        if mode == "center_crop":                                            # supervised.py:120-124
+            c = cfg["crop_size"]
+            sh, sw = (h - c) // 2, (w - c) // 2
+            img = img[:, :, sh:sh + c, sw:sw + c]
+        final = model(img)
+    return final.argmax(dim=1), final
+
+
+def intersection_and_union(output, target, K, ignore_index=255):
+    """third_party/unimatch/util/utils.py:91-103 (numpy): (area_intersection, area_union, area_target), each int64 [K]."""
+    import numpy as np
+    output = np.asarray(output).reshape(-1).copy()
+    target = np.asarray(target).reshape(-1)
+    output[target == ignore_index] = ignore_index
+    inter = output[output == target]
+    bins = np.arange(K + 1)
+    ai = np.histogram(inter, bins=bins)[0]
+    ao = np.histogram(output, bins=bins)[0]
+    at = np.histogram(target, bins=bins)[0]
+    return ai, ao + at - ai, at

@@ -110,6 +110,10 @@ _PROTOS = {
     "svl_cutmix_img": [_P, _P, _P, _P, _I, _I, _L, _P],
     "svl_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "svl_adamw_dev": [_P, _P, _P, _P, _L, _P, _I, _F, _F, _F, _F, _F, _P],
+    "svl_window_accumulate": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "svl_divide_count": [_P, _P, _I, _I, _L, _P],
+    "svl_argmax_classes": [_P, _P, _I, _I, _L, _P],
+    "svl_intersection_union": [_P, _P, _L, _I, _I, _P, _P],
     "svl_attention_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P],
     "svl_attention_bwd": [_P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _I, _I, _I, _F, _P],
 }

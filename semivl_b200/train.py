@@ -180,9 +180,9 @@ class Trainer:
     def graphed_supervised_step(self, img, mask):
         """`supervised_step(img, mask)` as ONE CUDA-graph launch (~690 kernel launches and their host-side descriptor set-up
         collapse into a replay).  Captured on first use for the given input shapes; inputs are copied into the graph's static
-        buffers, the per-step AdamW scalars (LR schedule, bias corrections) into a device vector.  Single-GPU only: with more
-        ranks the eager step overlaps the NCCL exchange with the backward pass instead."""
-        assert self.world == 1, "graph replay is the single-GPU path; multi-GPU steps run eagerly with the overlapped exchange"
+        buffers, the per-step AdamW scalars (LR schedule, bias corrections) into a device vector.  With more than one rank the
+        bucketed NCCL all-reduces of GradExchange are captured too: the side stream forks from and re-joins the capturing stream,
+        so the replayed graph keeps the exchange overlapped with the backward kernels."""
         key = (tuple(img.shape), tuple(mask.shape))
         if self._graph is None or self._graph_key != key:
             assert img.shape[-1] % 16 == 0 and img.shape[-2] % 16 == 0, "crops that need the pos-embed resize run eagerly"

@@ -184,6 +184,53 @@ def step_fixture(name, crop, b, seed, nclass=21, hp_over=None):
     print(name, "loss", loss.item(), "terms", out["terms"], "conf_frac", out["conf_frac"], "mclip_valid", out["mclip_valid_frac"])
 
 
+EVAL_CASES = [("original", 33, 50, 24, 0), ("center_crop", 33, 50, 24, 0), ("padded_sliding_window", 33, 50, 24, 16),
+              ("padded_sliding_window", 33, 50, 24, 0.5), ("zegclip_sliding_window", 33, 50, 24, 17), ("sliding_window", 33, 50, 21, 0)]
+
+
+def eval_fixture(name="eval_predict_iou"):
+    """`predict` (third_party/unimatch/supervised.py:40-130) and `intersectionAndUnion` (third_party/unimatch/util/utils.py:91-103)
+    of the UNMODIFIED reference on a stand-in model.  supervised.py cannot be imported whole here (its tqdm / mmseg imports), so
+    the `predict` function is compiled from the reference file as it lies under /root/reference (nothing is copied); `.cuda()` is
+    the identity while it runs on this GPU-less box."""
+    import ast
+    import importlib
+    import types
+    ref_root = ref_shim.REF_ROOT if hasattr(ref_shim, "REF_ROOT") else "/root/reference"
+    path = os.path.join(ref_root, "third_party", "unimatch", "supervised.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "predict"]
+    mmseg = types.SimpleNamespace(ops=types.SimpleNamespace(resize=lambda x, size, mode, align_corners, warning=False:
+                                                          F.interpolate(x, size=size, mode=mode, align_corners=align_corners)))
+    ns = dict(torch=torch, F=F, mmseg=mmseg)
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    with ref_shim.in_reference_cwd():
+        ref_iou = importlib.import_module("third_party.unimatch.util.utils").intersectionAndUnion
+    nclass = 5
+    model = O.StubSegModel(nclass, seed=4)
+    out = dict(weight=model.w.detach().numpy(), nclass=nclass, cases=np.array([f"{m}|{h}|{w}|{c}|{s}" for m, h, w, c, s in EVAL_CASES]))
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for i, (mode, h, w, crop, stride) in enumerate(EVAL_CASES):
+            g = torch.Generator().manual_seed(40 + i)
+            img = torch.randn(1, 3, h, w, generator=g)
+            mask = torch.randint(0, nclass, (1, h, w), generator=g)
+            mask[:, :4] = 255
+            pred, final = ns["predict"](model, img, mask, mode, dict(nclass=nclass, crop_size=crop, stride=stride), return_logits=True)
+            m2 = mask
+            if mode == "center_crop":
+                sh, sw = (h - crop) // 2, (w - crop) // 2
+                m2 = mask[:, sh:sh + crop, sw:sw + crop]
+            ai, au, at = ref_iou(pred.numpy(), m2.numpy(), nclass, 255)
+            out.update({f"img{i}": img.numpy(), f"mask{i}": mask.numpy().astype(np.int16), f"pred{i}": pred.numpy().astype(np.uint8),
+                        f"final{i}": final.numpy(), f"iou{i}": np.stack((ai, au, at)).astype(np.int64)})
+    finally:
+        torch.Tensor.cuda = real_cuda
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "cases", len(EVAL_CASES))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -196,6 +243,7 @@ def main():
     # Cityscapes-style loss modes (experiments.py:451 conf_mode='pixelavg'; train_utils.py:40-46; semivl.py:52-58)
     step_fixture("step_c64_b2_pixelavg_mv", 64, 2, seed=23, hp_over=dict(conf_mode="pixelavg", mcc_loss_reduce="mean_valid"))
     step_fixture("step_c64_b2_pixelratio_mean", 64, 2, seed=24, hp_over=dict(conf_mode="pixelratio", mcc_loss_reduce="mean"))
+    eval_fixture()
 
 
 if __name__ == "__main__":

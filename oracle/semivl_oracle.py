@@ -492,3 +492,20 @@ def intersection_and_union(output, target, K, ignore_index=255):
     ao = np.histogram(output, bins=bins)[0]
     at = np.histogram(target, bins=bins)[0]
     return ai, ao + at - ai, at
+
+
+class StubSegModel(torch.nn.Module):
+    """Deterministic stand-in for a segmentor in the evaluation fixtures: logits = 3x3 conv of the image + a class-dependent
+    horizontal ramp (so that windows cut at different offsets disagree near their borders, like a real model does)."""
+
+    def __init__(self, nclass, weight=None, seed=0):
+        super().__init__()
+        if weight is None:
+            weight = torch.randn(nclass, 3, 3, 3, generator=torch.Generator().manual_seed(seed))
+        self.w = torch.nn.Parameter(torch.as_tensor(weight).float(), requires_grad=False)
+
+    def forward(self, x):
+        y = F.conv2d(x, self.w.to(x.device), padding=1)
+        ramp = torch.linspace(0, 1, x.shape[-1], device=x.device)[None, None, None, :] * \
+            torch.arange(y.shape[1], device=x.device, dtype=y.dtype)[None, :, None, None]
+        return y + 0.1 * ramp

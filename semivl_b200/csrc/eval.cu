@@ -111,8 +111,9 @@ extern "C" int svl_argmax_classes(const float* x, int64_t* out, int B, int N, in
   return SVL_OK;
 }
 extern "C" int svl_intersection_union(const int64_t* pred, const int64_t* target, int64_t n, int K, int ignore_index, int64_t* counts, void* stream) {
-  SVL_CHECK_ARG(pred && target && counts && K >= 1 && K <= 4096, "svl_intersection_union: bad arguments");
-  if (n == 0) return SVL_OK;
+  SVL_CHECK_ARG(counts && K >= 1 && K <= 4096 && n >= 0, "svl_intersection_union: bad arguments");
+  if (n == 0) return SVL_OK;                      // an empty batch (torch gives empty tensors a null data pointer) adds nothing
+  SVL_CHECK_ARG(pred && target, "svl_intersection_union: null pointer");
   int64_t blocks = cdiv(n, 256 * 16);
   if (blocks > 148 * 8) blocks = 148 * 8;
   intersection_union_kernel<<<(unsigned)blocks, 256, 3 * K * sizeof(unsigned int), ST>>>(pred, target, n, K, ignore_index,

@@ -9,18 +9,9 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-class _Stub(torch.nn.Module):
-    """logits = 3x3 conv of the image + a position-dependent ramp: windows at different offsets give different logits"""
-
-    def __init__(self, nclass):
-        super().__init__()
-        g = torch.Generator().manual_seed(0)
-        self.w = torch.nn.Parameter(torch.randn(nclass, 3, 3, 3, generator=g), requires_grad=False)
-
-    def forward(self, x):
-        y = F.conv2d(x, self.w.to(x.device), padding=1)
-        ramp = torch.linspace(0, 1, x.shape[-1], device=x.device)[None, None, None, :] * torch.arange(y.shape[1], device=x.device)[None, :, None, None]
-        return y + 0.1 * ramp
+def _Stub(nclass):
+    from oracle import semivl_oracle as O
+    return O.StubSegModel(nclass)
 
 
 @pytest.mark.parametrize("mode,h,w,crop,stride", [
@@ -90,3 +81,31 @@ def test_evaluate_loop_matches_reference():
     want = inter / (union + 1e-10) * 100.0
     miou, iou = E.evaluate(stub.cuda(), data, "zegclip_sliding_window", cfg)
     assert np.allclose(iou, want, atol=0.05) and abs(miou - want.mean()) < 0.05          # a label may flip on a near tie
+
+
+def test_predict_and_iou_match_reference_golden(golden_dir):
+    """CUDA evaluation path against outputs of the UNMODIFIED reference's `predict` + `intersectionAndUnion` (eval_predict_iou.npz):
+    stitched scores within fp32 rounding, labels equal wherever the reference's top-2 margin is decidable, histograms bit-exact
+    when fed the reference's own labels."""
+    import os
+    from oracle import semivl_oracle as O
+    from semivl_b200 import evaluate as E
+    g = dict(np.load(os.path.join(golden_dir, "eval_predict_iou.npz"), allow_pickle=False))
+    nclass = int(g["nclass"])
+    model = O.StubSegModel(nclass, weight=g["weight"]).cuda()
+    for i, case in enumerate(g["cases"]):
+        mode, h, w, crop, stride = str(case).split("|")
+        cfg = dict(nclass=nclass, crop_size=int(crop), stride=float(stride) if "." in stride else int(stride))
+        img, mask = torch.from_numpy(g[f"img{i}"]), torch.from_numpy(g[f"mask{i}"].astype(np.int64))
+        pred, final = E.predict(model, img.cuda(), mask, mode, cfg, return_logits=True)
+        ref_final = torch.from_numpy(g[f"final{i}"])
+        err = (final.cpu() - ref_final).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref_final.abs().max().item()), (mode, err)
+        top2 = ref_final.topk(2, dim=1).values
+        decidable = (top2[:, 0] - top2[:, 1]) > 4 * err
+        ref_pred = torch.from_numpy(g[f"pred{i}"].astype(np.int64))
+        assert torch.equal(pred.cpu()[decidable], ref_pred[decidable]), mode
+        target = E.crop_mask_for(mode, mask, cfg)
+        counts = E.intersection_union_counts(ref_pred.cuda(), target.cuda(), nclass, 255).cpu().numpy()
+        want = g[f"iou{i}"]
+        assert np.array_equal(counts[0], want[0]) and np.array_equal(counts[1] + counts[2] - counts[0], want[1]) and np.array_equal(counts[2], want[2])

@@ -127,6 +127,9 @@ def _bucket_worker(rank, world, port, q):
     ex.reduce(600, 900)
     ex.reduce(250, 600)
     ex.finish()                   # the uncovered prefix [0, 250)
+    from semivl_b200.evaluate import reduce_counts          # mIoU histograms: one all-reduce of the [3, K] int64 matrix (supervised.py:158-160)
+    counts = reduce_counts(torch.arange(3 * 4, dtype=torch.int64).view(3, 4) * (rank + 1))
+    assert torch.equal(counts, torch.arange(3 * 4, dtype=torch.int64).view(3, 4) * 3)
     q.put((rank, flat))
     dist.barrier()
     dist.destroy_process_group()

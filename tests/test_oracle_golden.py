@@ -107,3 +107,25 @@ def test_optimizer_rules():
         O.adamw_step(w2, gr, m, v, step, 1e-3, 0.01)
     assert torch.allclose(w.detach(), w2, atol=1e-7)
     assert abs(O.poly_lr(1e-4, 50, 100) - 1e-4 * 0.5 ** 0.9) < 1e-12
+
+
+def test_evaluation_restatement_matches_reference(golden_dir):
+    """oracle predict_reference / intersection_and_union against `predict` and `intersectionAndUnion` of the unmodified reference
+    (tests/golden/eval_predict_iou.npz, oracle/make_golden.py::eval_fixture)."""
+    g = dict(np.load(os.path.join(golden_dir, "eval_predict_iou.npz"), allow_pickle=False))
+    nclass = int(g["nclass"])
+    model = O.StubSegModel(nclass, weight=g["weight"])
+    for i, case in enumerate(g["cases"]):
+        mode, h, w, crop, stride = str(case).split("|")
+        cfg = dict(nclass=nclass, crop_size=int(crop), stride=float(stride) if "." in stride else int(stride))
+        img, mask = torch.from_numpy(g[f"img{i}"]), torch.from_numpy(g[f"mask{i}"].astype(np.int64))
+        pred, final = O.predict_reference(model, img, mask, mode, cfg)
+        assert np.abs(final.numpy() - g[f"final{i}"]).max() < 1e-5, mode
+        assert np.array_equal(pred.numpy().astype(np.uint8), g[f"pred{i}"]), mode
+        m2 = mask
+        if mode == "center_crop":
+            c = int(crop)
+            sh, sw = (int(h) - c) // 2, (int(w) - c) // 2
+            m2 = mask[:, sh:sh + c, sw:sw + c]
+        ai, au, at = O.intersection_and_union(g[f"pred{i}"].astype(np.int64), m2.numpy(), nclass, 255)
+        assert np.array_equal(np.stack((ai, au, at)), g[f"iou{i}"]), mode

@@ -272,6 +272,17 @@ int svl_argmax_classes(const float* x, int64_t* out, int B, int N, int64_t plane
  * with pred forced to ignore_index where target == ignore_index; bit-exact integer histograms */
 int svl_intersection_union(const int64_t* pred, const int64_t* target, int64_t n, int K, int ignore_index, int64_t* counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input stage (third_party/unimatch/dataset/transform.py:9-41,66-84; semi.py:76-107): the per-pixel tail of the sample pipeline on
+ * uint8 sources.  mean3 / std3 are HOST pointers to 3 floats.  Outputs are bit-identical to PIL crop / flip + torchvision
+ * ToTensor + Normalize for the same crop offset and flip decision.
+ * ---------------------------------------------------------------------------------------------- */
+int svl_crop_flip_normalize(const uint8_t* src_hwc, int sh, int sw, float* dst_chw, int size, int x0, int y0, int flip, const float* mean3,
+                            const float* std3, void* stream);
+int svl_crop_flip_mask(const uint8_t* src, int sh, int sw, int64_t* dst, int64_t* ignore_mask, int size, int x0, int y0, int flip, int pad_value,
+                       void* stream);
+int svl_cutmix_box(float* box, int size, int bx, int by, int bw, int bh, void* stream);
+
 /* svl_adamw with the per-step scalars in DEVICE memory: hyper = {lr of class 0, lr of class 1, 1 - beta1^t, sqrt(1 - beta2^t)};
  * lets a captured CUDA graph of the whole training step be replayed under the poly LR schedule (semivl.py:338-345). */
 int svl_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int lr_index, float beta1, float beta2,

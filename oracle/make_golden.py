@@ -231,6 +231,40 @@ def eval_fixture(name="eval_predict_iou"):
     print(name, "cases", len(EVAL_CASES))
 
 
+INPUT_CASES = [(40, 56, 32, 255), (30, 50, 48, 254), (64, 20, 32, 254), (33, 33, 33, 255)]       # (h, w, crop size, pad value)
+
+
+def input_fixture(name="input_stage"):
+    """crop / hflip / normalize / obtain_cutmix_box of the UNMODIFIED reference (third_party/unimatch/dataset/transform.py), driven
+    with seeded `random` / `numpy.random`; the ignore mask follows semi.py:99-103."""
+    import importlib
+    import random
+    from PIL import Image
+    sys.path.insert(0, "/root/reference")
+    T = importlib.import_module("third_party.unimatch.dataset.transform")
+    out = dict(cases=np.array([f"{h}|{w}|{s}|{pad}" for h, w, s, pad in INPUT_CASES]))
+    for i, (h, w, size, pad) in enumerate(INPUT_CASES):
+        rng = np.random.RandomState(70 + i)
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        mask = rng.randint(0, 21, (h, w)).astype(np.uint8)
+        random.seed(500 + i)
+        pi, pm = T.crop(Image.fromarray(img), Image.fromarray(mask), size, pad)
+        pi, pm = T.hflip(pi, pm, p=0.5)
+        ti, tm = T.normalize(pi, pm)
+        ign = torch.zeros(size, size).long()                    # semi.py:99-103
+        ign[tm == 254] = 255
+        out.update({f"img{i}": img, f"mask{i}": mask, f"out_img{i}": ti.numpy(), f"out_mask{i}": tm.numpy().astype(np.int16),
+                    f"out_ign{i}": ign.numpy().astype(np.int16)})
+    boxes = []
+    for j in range(12):
+        random.seed(900 + j)
+        np.random.seed(900 + j)
+        boxes.append(T.obtain_cutmix_box(48, p=0.5).numpy().astype(np.uint8))
+    out["boxes"] = np.stack(boxes)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "cases", len(INPUT_CASES), "non-empty boxes", int(sum(b.any() for b in boxes)))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -244,6 +278,7 @@ def main():
     step_fixture("step_c64_b2_pixelavg_mv", 64, 2, seed=23, hp_over=dict(conf_mode="pixelavg", mcc_loss_reduce="mean_valid"))
     step_fixture("step_c64_b2_pixelratio_mean", 64, 2, seed=24, hp_over=dict(conf_mode="pixelratio", mcc_loss_reduce="mean"))
     eval_fixture()
+    input_fixture()
 
 
 if __name__ == "__main__":

@@ -509,3 +509,27 @@ class StubSegModel(torch.nn.Module):
         ramp = torch.linspace(0, 1, x.shape[-1], device=x.device)[None, None, None, :] * \
             torch.arange(y.shape[1], device=x.device, dtype=y.dtype)[None, :, None, None]
         return y + 0.1 * ramp
+
+
+# ----------------------------------------------------------------------------- input stage (third_party/unimatch/dataset/transform.py)
+def crop_flip_normalize_reference(img_u8, mask_u8, size, x0, y0, flip, pad_value=255):
+    """numpy/torch restatement of transform.crop (9-24) + hflip (27-31) + normalize (34-41) for GIVEN draws (x0, y0, flip), and the
+    ignore mask of semi.py:99-103.  img_u8 [h,w,3] uint8, mask_u8 [h,w] uint8 -> (f32 [3,size,size], int64 labels, int64 ignore mask)."""
+    import numpy as np
+    h, w = mask_u8.shape
+    ph, pw = max(h, size), max(w, size)
+    pi = np.zeros((ph, pw, 3), np.uint8)
+    pi[:h, :w] = img_u8
+    pm = np.full((ph, pw), pad_value, np.uint8)
+    pm[:h, :w] = mask_u8
+    pi, pm = pi[y0:y0 + size, x0:x0 + size], pm[y0:y0 + size, x0:x0 + size]
+    if flip:
+        pi, pm = pi[:, ::-1], pm[:, ::-1]
+    t = torch.from_numpy(np.ascontiguousarray(pi)).permute(2, 0, 1).float().div(255)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    t = t.sub(mean).div(std)
+    lab = torch.from_numpy(np.ascontiguousarray(pm)).long()
+    ign = torch.zeros_like(lab)
+    ign[lab == 254] = 255
+    return t, lab, ign

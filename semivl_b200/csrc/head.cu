@@ -336,13 +336,13 @@ gn_bwd_stats_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, con
           const float dd = (xh * ga[i] + be[i] > 0.f) ? d[i] : 0.f;
           dg[i] += dd * xh;
           db[i] += dd;
-          const float gg = dd * ga[i];
-          s1 += gg;
-          s2 += gg * xh;
         }
       }
     }
   }
+  // s1 = sum dd * gamma and s2 = sum dd * gamma * xhat are linear in the per-channel sums just accumulated: no per-element work
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1 += ga[i] * db[i]; s2 += ga[i] * dg[i]; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { part[i][threadIdx.x] = dg[i]; part[8 + i][threadIdx.x] = db[i]; }
   part[16][threadIdx.x] = s1;

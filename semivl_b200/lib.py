@@ -114,6 +114,9 @@ _PROTOS = {
     "svl_divide_count": [_P, _P, _I, _I, _L, _P],
     "svl_argmax_classes": [_P, _P, _I, _I, _L, _P],
     "svl_intersection_union": [_P, _P, _L, _I, _I, _P, _P],
+    "svl_crop_flip_normalize": [_P, _I, _I, _P, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
+    "svl_crop_flip_mask": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P],
+    "svl_cutmix_box": [_P, _I, _I, _I, _I, _I, _P],
     "svl_attention_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P],
     "svl_attention_bwd": [_P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _I, _I, _I, _F, _P],
 }

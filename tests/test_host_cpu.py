@@ -212,3 +212,30 @@ def test_clip_checkpoint_conversion_and_pretrained_load(built, tmp_path):
     assert sd["proj.weight"].shape == (512, E, 1, 1) and torch.equal(sd["proj.weight"][:, :, 0, 0], clip["visual.proj"].float().t())
     want = O.resize_pos_embed(clip["visual.positional_embedding"].float()[None], (6, 6), (g0, g0))
     assert sd["pos_embed"].shape == (1, 37, E) and torch.allclose(sd["pos_embed"], want, atol=1e-6)
+
+
+def test_input_stage_draws_and_restatement_match_reference(built, golden_dir):
+    """tests/golden/input_stage.npz holds outputs of the reference's crop / hflip / normalize / obtain_cutmix_box under seeded RNGs:
+    the host-side samplers of semivl_b200.input_pipeline must make the same draws in the same order, and the oracle restatement of the
+    per-pixel work must reproduce the tensors bit for bit."""
+    import random
+    from oracle import semivl_oracle as O
+    from semivl_b200 import input_pipeline as P
+    g = dict(np.load(os.path.join(golden_dir, "input_stage.npz"), allow_pickle=False))
+    for i, case in enumerate(g["cases"]):
+        h, w, size, pad = (int(v) for v in str(case).split("|"))
+        random.seed(500 + i)
+        x0, y0 = P.sample_crop(w, h, size)
+        flip = P.sample_hflip(0.5)
+        t, lab, ign = O.crop_flip_normalize_reference(g[f"img{i}"], g[f"mask{i}"], size, x0, y0, flip, pad)
+        assert np.array_equal(t.numpy(), g[f"out_img{i}"]), case
+        assert np.array_equal(lab.numpy(), g[f"out_mask{i}"].astype(np.int64)) and np.array_equal(ign.numpy(), g[f"out_ign{i}"].astype(np.int64))
+    for j, want in enumerate(g["boxes"]):
+        random.seed(900 + j)
+        np.random.seed(900 + j)
+        params = P.sample_cutmix_box(48, p=0.5)
+        box = np.zeros((48, 48), np.uint8)
+        if params is not None:
+            x, y, bw, bh = params
+            box[y:y + bh, x:x + bw] = 1
+        assert np.array_equal(box, want), j

@@ -416,6 +416,157 @@ inline int log2_exact(int v) {
   return (1 << s) == v ? s : -1;
 }
 
+// ---------------------------------------------------------------------------------------------- bf16 fast paths of the token / skip glue
+// Same idea as the GroupNorm kernels: one 8-channel vector (16 bytes) per thread access instead of a 2-byte element, loads batched.
+__device__ __forceinline__ void bilin_src(int o, float scale, int in_size, int& i0, int& i1, float& w1);      // defined with the generic kernels
+// out[map, c] = scale * sum_pix x[map, pix, c];  grid = maps, 256 threads = (256 / vpp pixel lanes) x (vpp channel vectors)
+__global__ void __launch_bounds__(256)
+map_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out, int hw, int C, float scale) {
+  __shared__ float red[256 * 8 + 256];
+  const int vpp = C / 8, lanes = 256 / vpp, v = threadIdx.x % vpp, pl = threadIdx.x / vpp;
+  const __nv_bfloat16* xb = x + (int64_t)blockIdx.x * hw * ld + v * 8;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int p = pl; p < hw; p += 4 * lanes) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = ld_stream16(xb + (int64_t)(p + u * lanes < hw ? p + u * lanes : p) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * lanes < hw) {
+        float f[8];
+        bf16x8_to_f32(r[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i];
+      }
+    }
+  }
+  const int pitch = C + 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[pl * pitch + v * 8 + i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int j = 0; j < lanes; ++j) t += red[j * pitch + threadIdx.x];
+    out[(int64_t)blockIdx.x * C + threadIdx.x] = t * scale;
+  }
+}
+// tok[(b, py, px), n, 0:C] = avgpool x[(b, n)];  tok[..., C:C+Ct] = text[n]: a thread owns 8 columns of one token
+__global__ void __launch_bounds__(256)
+pool_tokens_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ text, float* __restrict__ tok, int B, int N,
+                        int h, int w, int C, int Ct, int pool) {
+  const int hp = h / pool, wp = w / pool, vt = (C + Ct) / 8;
+  const int64_t total = (int64_t)B * hp * wp * N * vt;
+  const float inv = 1.f / (pool * pool);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % vt) * 8;
+    int64_t t = idx / vt;
+    const int n = (int)(t % N); t /= N;
+    const int px = (int)(t % wp), py = (int)((t / wp) % hp), b = (int)(t / ((int64_t)wp * hp));
+    float s[8];
+    if (c8 >= C) {
+      ldg8f(text + n * Ct + c8 - C, s);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = 0.f;
+      const __nv_bfloat16* base = x + ((((int64_t)b * N + n) * h + py * pool) * w + px * pool) * ldx + c8;
+      for (int i = 0; i < pool; ++i) {
+#pragma unroll 4
+        for (int j = 0; j < pool; ++j) {
+          float f[8];
+          bf16x8_to_f32(ld_stream16(base + ((int64_t)i * w + j) * ldx), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s[k] += f[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] *= inv;
+    }
+    float4* o = (float4*)(tok + (idx / vt) * (int64_t)(C + Ct) + c8);
+    o[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o[1] = make_float4(s[4], s[5], s[6], s[7]);
+  }
+}
+// out = x + bilinear_ac(tok): grid = (chunks of 512 items, B * N maps), item = (pixel, 8-channel vector), two items per thread
+__global__ void __launch_bounds__(256)
+unpool_add_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ tok, int64_t ldt, __nv_bfloat16* __restrict__ out,
+                       int64_t ldo, int N, int h, int w, int C, int hp, int wp) {
+  const int vpp = C / 8, items = h * w * vpp;
+  const int map = blockIdx.y, b = map / N, n = map - b * N;
+  const float sy = hp > 1 && h > 1 ? (float)(hp - 1) / (h - 1) : 0.f, sx = wp > 1 && w > 1 ? (float)(wp - 1) / (w - 1) : 0.f;
+  const int base = blockIdx.x * 512 + threadIdx.x;
+  uint4 xv[2];
+  int pix[2], c8[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int idx = base + u * 256 < items ? base + u * 256 : 0;
+    pix[u] = idx / vpp;
+    c8[u] = (idx - pix[u] * vpp) * 8;
+    xv[u] = ld_stream16(x + ((int64_t)map * h * w + pix[u]) * ldx + c8[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (base + u * 256 >= items) break;
+    const int yy = pix[u] / w, xx = pix[u] - yy * w;
+    int y0, y1, x0, x1;
+    float wy, wx;
+    bilin_src(yy, sy, hp, y0, y1, wy);
+    bilin_src(xx, sx, wp, x0, x1, wx);
+    float f[8], t00[8], t01[8], t10[8], t11[8];
+    ldg8f(tok + ((((int64_t)b * hp + y0) * wp + x0) * N + n) * ldt + c8[u], t00);
+    ldg8f(tok + ((((int64_t)b * hp + y0) * wp + x1) * N + n) * ldt + c8[u], t01);
+    ldg8f(tok + ((((int64_t)b * hp + y1) * wp + x0) * N + n) * ldt + c8[u], t10);
+    ldg8f(tok + ((((int64_t)b * hp + y1) * wp + x1) * N + n) * ldt + c8[u], t11);
+    bf16x8_to_f32(xv[u], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      f[i] += (1.f - wy) * ((1.f - wx) * t00[i] + wx * t01[i]) + wy * ((1.f - wx) * t10[i] + wx * t11[i]);       // same expression as the generic kernel
+    *(uint4*)(out + ((int64_t)map * h * w + pix[u]) * ldo + c8[u]) = f32_to_bf16x8(f);
+  }
+}
+// cat[(b,n), Y, X, c0 + c] = bilinear_ac(skip[b]) for every class n: a thread interpolates 8 channels once and stores them N times
+__global__ void __launch_bounds__(256)
+skip_fill_bf16_kernel(const float* __restrict__ skip, int64_t lds, __nv_bfloat16* __restrict__ cat, int64_t ldc, int c0, int B, int N, int h, int w,
+                      int Cs, int H2, int W2) {
+  const int vs = Cs / 8;
+  const int64_t total = (int64_t)B * H2 * W2 * vs;
+  const float sy = h > 1 && H2 > 1 ? (float)(h - 1) / (H2 - 1) : 0.f, sx = w > 1 && W2 > 1 ? (float)(w - 1) / (W2 - 1) : 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % vs) * 8;
+    int64_t pix = idx / vs;
+    const int X = (int)(pix % W2), Y = (int)((pix / W2) % H2), b = (int)(pix / ((int64_t)W2 * H2));
+    int y0, y1, x0, x1;
+    float wy, wx;
+    bilin_src(Y, sy, h, y0, y1, wy);
+    bilin_src(X, sx, w, x0, x1, wx);
+    float s00[8], s01[8], s10[8], s11[8], v[8];
+    ldg8f(skip + (((int64_t)b * h + y0) * w + x0) * lds + c, s00);
+    ldg8f(skip + (((int64_t)b * h + y0) * w + x1) * lds + c, s01);
+    ldg8f(skip + (((int64_t)b * h + y1) * w + x0) * lds + c, s10);
+    ldg8f(skip + (((int64_t)b * h + y1) * w + x1) * lds + c, s11);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (1.f - wy) * ((1.f - wx) * s00[i] + wx * s01[i]) + wy * ((1.f - wx) * s10[i] + wx * s11[i]);
+    const uint4 pk = f32_to_bf16x8(v);
+    __nv_bfloat16* dst = cat + (((int64_t)b * N * H2 + Y) * W2 + X) * ldc + c0 + c;
+    for (int n = 0; n < N; ++n) *(uint4*)(dst + (int64_t)n * H2 * W2 * ldc) = pk;
+  }
+}
+// x[map, pix, c] += scale * v[map, c], four channels per thread (f32 x, f32 v)
+__global__ void map_bcast_add_f32x4_kernel(float* __restrict__ x, const float* __restrict__ v, int64_t ldv, int64_t maps, int hw, int C, float scale) {
+  const int c4n = C / 4;
+  const int64_t total = maps * hw * c4n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    const int64_t map = idx / ((int64_t)hw * c4n);
+    const float4 a = __ldg((const float4*)(v + map * ldv + c));
+    float4* d = (float4*)x + idx;
+    float4 t = *d;
+    t.x += scale * a.x; t.y += scale * a.y; t.z += scale * a.z; t.w += scale * a.w;
+    *d = t;
+  }
+}
+
 inline int gn_splits(int64_t maps, int hw, int C) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("SVL_GN_SPLITS"); forced = e ? atoi(e) : 0; }
@@ -1139,6 +1290,11 @@ extern "C" int svl_sim_col2im(const void* dcol, int dtype, int64_t ld, void* dsi
 extern "C" int svl_map_sum(const void* x, int dtype, int64_t ld, float* out, int64_t maps, int hw, int C, float scale, void* stream) {
   SVL_CHECK_ARG(x && out && C <= 128, "svl_map_sum: bad arguments");
   if (maps == 0) return SVL_OK;
+  if (dtype == SVL_BF16 && C % 8 == 0 && 256 % (C / 8) == 0 && ld % 8 == 0 && al16(x)) {
+    map_sum_bf16_kernel<<<(unsigned)maps, 256, 0, ST>>>((const __nv_bfloat16*)x, ld, out, hw, C, scale);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   int ry = 1024 / C;
   if (ry > 8) ry = 8;
   map_sum_kernel<<<(unsigned)maps, dim3(C, ry), 0, ST>>>(x, dtype, ld, out, hw, C, scale);
@@ -1147,6 +1303,11 @@ extern "C" int svl_map_sum(const void* x, int dtype, int64_t ld, float* out, int
 }
 extern "C" int svl_map_bcast_add(float* x, const void* v, int v_dtype, int64_t ldv, int64_t maps, int hw, int C, float scale, void* stream) {
   SVL_CHECK_ARG(x && v, "svl_map_bcast_add: null pointer");
+  if (v_dtype == SVL_F32 && C % 4 == 0 && ldv % 4 == 0 && al16(x) && al16(v)) {
+    map_bcast_add_f32x4_kernel<<<ew_grid(maps * hw * (C / 4)), 256, 0, ST>>>(x, (const float*)v, ldv, maps, hw, C, scale);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   map_bcast_add_kernel<<<ew_grid(maps * hw * C), 256, 0, ST>>>(x, v, v_dtype, ldv, maps, hw, C, scale);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
@@ -1155,6 +1316,12 @@ extern "C" int svl_map_bcast_add(float* x, const void* v, int v_dtype, int64_t l
 extern "C" int svl_pool_tokens(const void* x, int x_dtype, int64_t ldx, const float* text, float* tok, int B, int N, int h, int w, int C, int Ct,
                                int pool, void* stream) {
   SVL_CHECK_ARG(x && text && tok && pool > 0 && h >= pool && w >= pool, "svl_pool_tokens: bad arguments");
+  if (x_dtype == SVL_BF16 && C % 8 == 0 && Ct % 8 == 0 && ldx % 8 == 0 && al16(x) && al16(text) && al16(tok)) {
+    pool_tokens_bf16_kernel<<<ew_grid((int64_t)B * (h / pool) * (w / pool) * N * ((C + Ct) / 8)), 256, 0, ST>>>((const __nv_bfloat16*)x, ldx, text, tok, B, N,
+                                                                                                            h, w, C, Ct, pool);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   pool_tokens_kernel<<<ew_grid((int64_t)B * (h / pool) * (w / pool) * N * (C + Ct)), 256, 0, ST>>>(x, x_dtype, ldx, text, tok, B, N, h, w, C, Ct, pool);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
@@ -1169,6 +1336,13 @@ extern "C" int svl_pool_tokens_bwd(const float* dtok, int64_t ldt, float* dx, in
 extern "C" int svl_unpool_add(const void* x, int x_dtype, int64_t ldx, const float* tok, int64_t ldt, void* out, int out_dtype, int64_t ldo, int B,
                               int N, int h, int w, int C, int hp, int wp, void* stream) {
   SVL_CHECK_ARG(x && tok && out && C % 8 == 0, "svl_unpool_add: bad arguments");
+  if (x_dtype == SVL_BF16 && out_dtype == SVL_BF16 && ldx % 8 == 0 && ldo % 8 == 0 && ldt % 4 == 0 && al16(x) && al16(out) && al16(tok) &&
+      (int64_t)B * N <= 65535 && (int64_t)h * w * (C / 8) < (1ll << 30)) {
+    const dim3 grid((unsigned)cdiv((int64_t)h * w * (C / 8), 512), (unsigned)(B * N));
+    unpool_add_bf16_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)x, ldx, tok, ldt, (__nv_bfloat16*)out, ldo, N, h, w, C, hp, wp);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   unpool_add_kernel<<<ew_grid((int64_t)B * N * h * w * (C / 8)), 256, 0, ST>>>(x, x_dtype, ldx, tok, ldt, out, out_dtype, ldo, B, N, h, w, C, hp, wp);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
@@ -1189,6 +1363,12 @@ extern "C" int svl_unpool_bwd(const void* dout, int dtype, int64_t ld, float* dt
 extern "C" int svl_skip_fill(const void* skip, int s_dtype, int64_t lds, void* cat, int c_dtype, int64_t ldc, int c0, int B, int N, int h, int w,
                              int Cs, int H2, int W2, void* stream) {
   SVL_CHECK_ARG(skip && cat, "svl_skip_fill: null pointer");
+  if (s_dtype == SVL_F32 && c_dtype == SVL_BF16 && Cs % 8 == 0 && c0 % 8 == 0 && ldc % 8 == 0 && lds % 4 == 0 && al16(skip) && al16(cat)) {
+    skip_fill_bf16_kernel<<<ew_grid((int64_t)B * H2 * W2 * (Cs / 8)), 256, 0, ST>>>((const float*)skip, lds, (__nv_bfloat16*)cat, ldc, c0, B, N, h, w, Cs, H2,
+                                                                                  W2);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   skip_fill_kernel<<<ew_grid((int64_t)B * H2 * W2 * Cs), 256, 0, ST>>>(skip, s_dtype, lds, cat, c_dtype, ldc, c0, B, N, h, w, Cs, H2, W2);
   SVL_LAUNCH_CHECK();
   return SVL_OK;

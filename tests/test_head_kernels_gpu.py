@@ -77,6 +77,14 @@ def test_pool_unpool_tokens(L, B, N, h, w):
     ref = xp.reshape(B, N, C, hp, wp).permute(0, 3, 4, 1, 2).reshape(B * hp * wp, N, C)
     ref = torch.cat((ref, text[None].expand(B * hp * wp, N, Ct)), -1).reshape(-1, C + Ct)
     assert _rel(tok, ref) < 1e-6
+    # bf16 input (vectorised kernel): exact average of the bf16-rounded values
+    xb = x.to(torch.bfloat16)
+    tok_b = torch.full_like(tok, 3.0)
+    L.call("svl_pool_tokens", xb, L.BF16, C, text, tok_b, B, N, h, w, C, Ct, pool)
+    xpb = F.avg_pool2d(xb.float().permute(0, 3, 1, 2), pool)
+    refb = xpb.reshape(B, N, C, hp, wp).permute(0, 3, 4, 1, 2).reshape(B * hp * wp, N, C)
+    refb = torch.cat((refb, text[None].expand(B * hp * wp, N, Ct)), -1).reshape(-1, C + Ct)
+    assert _rel(tok_b, refb) < 1e-6
     # unpool + add
     tk = torch.randn(B * hp * wp * N, C + Ct, device="cuda", generator=g).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
@@ -87,6 +95,10 @@ def test_pool_unpool_tokens(L, B, N, h, w):
     out = torch.empty(B * N, h, w, C, device="cuda")
     L.call("svl_unpool_add", x, L.F32, C, tk.detach(), C + Ct, out, L.F32, C, B, N, h, w, C, hp, wp)
     assert _rel(out, refo) < 1e-5
+    out_b = torch.empty(B * N, h, w, C, device="cuda", dtype=torch.bfloat16)
+    L.call("svl_unpool_add", xb, L.BF16, C, tk.detach(), C + Ct, out_b, L.BF16, C, B, N, h, w, C, hp, wp)
+    refo_b = xb.float() + F.interpolate(t2.detach(), size=(h, w), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    assert _rel(out_b, refo_b) < 5e-3                      # bf16 output rounding
     dtok = torch.empty_like(tk)
     L.call("svl_unpool_bwd", dout, L.F32, C, dtok, C + Ct, B, N, h, w, C, hp, wp)
     assert _rel(dtok, tk.grad) < 1e-5
@@ -117,6 +129,9 @@ def test_skip_fill_grad(L, B, N, h, w, Cs):
     cat = torch.zeros(B * N, H2, W2, cup + Cs, device="cuda")
     L.call("svl_skip_fill", skip, L.F32, Cs, cat, L.F32, cup + Cs, cup, B, N, h, w, Cs, H2, W2)
     assert _rel(cat[..., cup:], ref) < 1e-5 and cat[..., :cup].abs().max() == 0
+    cat_b = torch.zeros(B * N, H2, W2, cup + Cs, device="cuda", dtype=torch.bfloat16)
+    L.call("svl_skip_fill", skip, L.F32, Cs, cat_b, L.BF16, cup + Cs, cup, B, N, h, w, Cs, H2, W2)
+    assert _rel(cat_b[..., cup:], ref) < 5e-3 and cat_b[..., :cup].abs().max() == 0
     dcat = torch.randn(B * N, H2, W2, cup + Cs, device="cuda", generator=g)
     ref.backward(dcat[..., cup:])
     dsk = torch.empty(B, h, w, Cs, device="cuda")
@@ -150,6 +165,12 @@ def test_map_sum_bcast(L):
     y = x.clone()
     L.call("svl_map_bcast_add", y, out, L.F32, C, maps, hw, C, 2.0)
     assert _rel(y, x + 2 * out[:, None]) < 1e-6
+    # bf16 input (vectorised, 16 pixel lanes x 16 channel vectors), ragged pixel counts
+    for hw2 in (100, 1024, 7):
+        xb = torch.randn(maps, hw2, C, device="cuda").to(torch.bfloat16)
+        out_b = torch.full((maps, C), 9.0, device="cuda")
+        L.call("svl_map_sum", xb, L.BF16, C, out_b, maps, hw2, C, 0.5)
+        assert _rel(out_b, xb.float().sum(1) * 0.5) < 1e-5
 
 
 @pytest.mark.parametrize("maps,h,w", [(3, 20, 24), (2, 128, 128), (5, 9, 70)])

@@ -47,7 +47,8 @@ def test_full_size_crop_properties():
     a = P.crop_flip_normalize(img, 512, 123, 77, False)
     b = P.crop_flip_normalize(img, 512, 123, 77, True)
     assert torch.equal(a, b.flip(-1))
-    mean = torch.tensor(P.MEAN, device="cuda").view(3, 1, 1)
-    std = torch.tensor(P.STD, device="cuda").view(3, 1, 1)
-    ref = img[77:77 + 512, 123:123 + 512].permute(2, 0, 1).float().div(255).sub(mean).div(std)
-    assert torch.equal(a, ref)
+    # the reference normalises on the CPU (DataLoader workers); torch's CUDA `div(255)` multiplies by a reciprocal and is not the oracle
+    mean = torch.tensor(P.MEAN).view(3, 1, 1)
+    std = torch.tensor(P.STD).view(3, 1, 1)
+    ref = img.cpu()[77:77 + 512, 123:123 + 512].permute(2, 0, 1).float().div(255).sub(mean).div(std)
+    assert torch.equal(a.cpu(), ref)

@@ -196,6 +196,9 @@ int svl_map_bcast_add(float* x, const void* v, int v_dtype, int64_t ldv, int64_t
 int svl_pool_tokens(const void* x, int x_dtype, int64_t ldx, const float* text, float* tok, int B, int N, int h, int w, int C, int Ct,
                     int pool, void* stream);
 int svl_pool_tokens_bwd(const float* dtok, int64_t ldt, float* dx, int B, int N, int h, int w, int C, int pool, void* stream);
+/* dx = src + pool-gradient of dtok in ONE pass (src bf16 or f32 [B*N*h*w, lds]; dx f32 [.., C]): replaces svl_cast + svl_pool_tokens_bwd */
+int svl_pool_tokens_bwd_from(const void* src, int src_dtype, int64_t lds, const float* dtok, int64_t ldt, float* dx, int B, int N, int h, int w,
+                             int C, int pool, void* stream);
 int svl_unpool_add(const void* x, int x_dtype, int64_t ldx, const float* tok, int64_t ldt, void* out, int out_dtype, int64_t ldo, int B,
                    int N, int h, int w, int C, int hp, int wp, void* stream);
 int svl_unpool_bwd(const void* dout, int dtype, int64_t ld, float* dtok, int64_t ldt, int B, int N, int h, int w, int C, int hp, int wp,

@@ -9,6 +9,8 @@
 // TMEM: S[2] (2 x 128 columns) | O_tile[2] (2 x 64 columns).  Shared memory: Q 16 KB, K/V 2 x 32 KB, P 2 x 32 KB.
 // replaces the nn.MultiheadAttention core (maskclip_vit.py:77-84,141) for head_dim 64; the split-bf16 precise mode keeps the
 // mma.sync kernels of attention.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma.h"
@@ -26,6 +28,7 @@ struct FwdParams {
   float* lse;
   int L, heads;
   float scale;
+  int s_first;        // MMA issue order: 1 = S_{j+1} before P_j V_j (the softmax of tile j+1 does not wait behind the P V product)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -106,18 +109,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
     const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), pa = tmpl + (uint64_t)(sP >> 4);
     ptx::mbar_wait(q_full, 0);
-    for (int j = 0; j < nt; ++j) {
+    auto issue_s = [&](int j) {              // S_j = Q K_j^T into the (single) S buffer once the softmax warps have released it
       const int st = j & 1, k = j >> 1;
       ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
       ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
       ptx::tc_fence_after();
-      const uint64_t kd = tmpl + (uint64_t)((sK + st * kTile) >> 4), vb = tmpl + (uint64_t)((sV + st * kTile) >> 4);
+      const uint64_t kd = tmpl + (uint64_t)((sK + st * kTile) >> 4);
       if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16(tmem_base, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk > 0);
         ptx::umma_commit(s_full);
       }
       __syncwarp();
+    };
+    auto issue_pv = [&](int j) {             // O_tile[j & 1] = P_j V_j, then the K/V stage is free
+      const int st = j & 1, k = j >> 1;
+      const uint64_t vb = tmpl + (uint64_t)((sV + st * kTile) >> 4);
       ptx::mbar_wait(p_full, (uint32_t)(j & 1));
       ptx::mbar_wait(o_empty(st), (uint32_t)((k & 1) ^ 1));
       ptx::tc_fence_after();
@@ -132,6 +139,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         ptx::umma_commit(kv_empty(st));
       }
       __syncwarp();
+    };
+    if (p.s_first) {
+      issue_s(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) issue_s(j + 1);      // waits for s_empty(j): the softmax warps are done reading S_j; P_j follows right behind
+        issue_pv(j);
+      }
+    } else {
+      for (int j = 0; j < nt; ++j) {
+        issue_s(j);
+        issue_pv(j);
+      }
     }
   } else {
     const int q = warp & 3;
@@ -601,6 +620,9 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int h
   if (int rc = tma_encode_bf16(&tm, qkv, 3, dims, strides, box)) return rc;
   FwdParams p;
   p.out = (__nv_bfloat16*)out; p.ldo = E; p.lse = lse; p.L = L; p.heads = heads; p.scale = scale;
+  static int s_first = -1;
+  if (s_first < 0) { const char* e = getenv("SVL_ATTN_S_FIRST"); s_first = e ? atoi(e) : 0; }
+  p.s_first = s_first;
   const size_t smem = 7 * kTile + 8 * 13 + 16;
   static bool attr_set = false;
   if (!attr_set) {

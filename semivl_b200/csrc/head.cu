@@ -748,10 +748,13 @@ __global__ void unpool_bwd_kernel(const void* __restrict__ dout, int dtype, int6
     dtok[idx] = s;
   }
 }
-// bf16 fast path of the above: a thread owns 8 channels of one token (16-byte loads instead of 2-byte ones)
+// vectorised variant of the above (bf16 or f32 gradient): a thread owns 8 channels of one token (16-byte loads instead of single elements)
+template <bool BF16>
 __global__ void __launch_bounds__(256)
-unpool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld, float* __restrict__ dtok, int64_t ldt, int B, int N, int h, int w, int C,
-                       int hp, int wp) {
+unpool_bwd_vec_kernel(const void* __restrict__ dout_, int64_t ld, float* __restrict__ dtok, int64_t ldt, int B, int N, int h, int w, int C,
+                      int hp, int wp) {
+  const __nv_bfloat16* dout = (const __nv_bfloat16*)dout_;
+  const float* doutf = (const float*)dout_;
   const int vt = (int)(ldt / 8);
   const int64_t total = (int64_t)B * hp * wp * N * vt;
   const float sy = hp > 1 && h > 1 ? (float)(hp - 1) / (h - 1) : 0.f, sx = wp > 1 && w > 1 ? (float)(wp - 1) / (w - 1) : 0.f;
@@ -766,7 +769,7 @@ unpool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld, float
     if (c8 < C) {
       const int ylo = sy > 0.f ? max(0, (int)ceilf((py - 1) / sy)) : 0, yhi = sy > 0.f ? min(h - 1, (int)floorf((py + 1) / sy)) : h - 1;
       const int xlo = sx > 0.f ? max(0, (int)ceilf((px - 1) / sx)) : 0, xhi = sx > 0.f ? min(w - 1, (int)floorf((px + 1) / sx)) : w - 1;
-      const __nv_bfloat16* base = dout + ((int64_t)b * N + n) * h * w * ld + c8;
+      const int64_t base = ((int64_t)b * N + n) * h * w * ld + c8;
       for (int yy = ylo; yy <= yhi; ++yy) {
         int y0, y1; float wy;
         bilin_src(yy, sy, hp, y0, y1, wy);
@@ -778,7 +781,8 @@ unpool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld, float
           const float ax = (x0 == px ? 1.f - wx : 0.f) + (x1 == px ? wx : 0.f);
           if (ax == 0.f) continue;
           float f[8];
-          bf16x8_to_f32(__ldg((const uint4*)(base + ((int64_t)yy * w + xx) * ld)), f);
+          if (BF16) bf16x8_to_f32(__ldg((const uint4*)(dout + base + ((int64_t)yy * w + xx) * ld)), f);
+          else ldg8f(doutf + base + ((int64_t)yy * w + xx) * ld, f);
           const float a = ay * ax;
 #pragma unroll
           for (int i = 0; i < 8; ++i) s[i] += a * f[i];
@@ -810,6 +814,36 @@ __global__ void pool_tokens_bwd_kernel(const float* __restrict__ dtok, int64_t l
       v.x += inv * t.x; v.y += inv * t.y; v.z += inv * t.z; v.w += inv * t.w;
       *d = v;
     }
+  }
+}
+
+// dx[(b,n), y, x, c] = src[(b,n), y, x, c] + dtok[(b, y/pool, x/pool), n, c] / pool^2  (f32 dx written once: the cast of the incoming gradient and the
+// pooling gradient in one pass instead of a cast kernel followed by a read-modify-write); src bf16 or f32; 8 channels per thread
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pool_tokens_bwd_from_kernel(const void* __restrict__ src_, int64_t lds, const float* __restrict__ dtok, int64_t ldt, float* __restrict__ dx, int B,
+                            int N, int h, int w, int C, int pool) {
+  const int hp = h / pool, wp = w / pool, vpp = C / 8;
+  const int64_t total = (int64_t)B * N * h * w * vpp;
+  const float inv = 1.f / (pool * pool);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % vpp) * 8;
+    const int64_t pix = idx / vpp;
+    const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+    const int n = (int)((pix / ((int64_t)w * h)) % N), b = (int)(pix / ((int64_t)w * h * N));
+    float f[8];
+    if (BF16) bf16x8_to_f32(ld_stream16((const __nv_bfloat16*)src_ + pix * lds + c), f);
+    else ldg8f((const float*)src_ + pix * lds + c, f);
+    const int py = yy / pool, px = xx / pool;
+    if (py < hp && px < wp) {
+      float t[8];
+      ldg8f(dtok + ((((int64_t)b * hp + py) * wp + px) * N + n) * ldt + c, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += inv * t[i];
+    }
+    float4* d = (float4*)(dx + pix * C + c);
+    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
 }
 
@@ -851,6 +885,38 @@ __global__ void class_sum_kernel(const void* __restrict__ x, int dtype, int64_t 
       for (int i = 0; i < 8; ++i) s[i] += f[i];
     }
     st8(out, SVL_F32, ((int64_t)b * P + pix) * Cs + c, 0, 8, s);
+  }
+}
+
+// bf16 fast path of class_sum: the N per-class loads of a thread are issued four at a time
+__global__ void __launch_bounds__(256)
+class_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int c0, float* __restrict__ out, int B, int N, int64_t P, int Cs) {
+  const int c8n = Cs / 8;
+  const int64_t total = (int64_t)B * P * c8n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c8n) * 8;
+    const int64_t pix = (idx / c8n) % P, b = idx / (c8n * P);
+    const __nv_bfloat16* base = x + ((int64_t)b * N * P + pix) * ld + c0 + c;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    for (int n = 0; n < N; n += 4) {
+      uint4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = ld_stream16(base + (int64_t)(n + u < N ? n + u : n) * P * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (n + u < N) {
+          float f[8];
+          bf16x8_to_f32(r[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += f[i];
+        }
+      }
+    }
+    float4* o = (float4*)(out + ((int64_t)b * P + pix) * Cs + c);
+    o[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o[1] = make_float4(s[4], s[5], s[6], s[7]);
   }
 }
 
@@ -1333,6 +1399,17 @@ extern "C" int svl_pool_tokens_bwd(const float* dtok, int64_t ldt, float* dx, in
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }
+extern "C" int svl_pool_tokens_bwd_from(const void* src, int src_dtype, int64_t lds, const float* dtok, int64_t ldt, float* dx, int B, int N, int h,
+                                       int w, int C, int pool, void* stream) {
+  SVL_CHECK_ARG(src && dtok && dx && pool > 0, "svl_pool_tokens_bwd_from: bad arguments");
+  SVL_CHECK_ARG((src_dtype == SVL_BF16 || src_dtype == SVL_F32) && C % 8 == 0 && ldt % 4 == 0 && lds % 8 == 0 && al16(src) && al16(dtok) && al16(dx),
+                "svl_pool_tokens_bwd_from: needs bf16 / f32 rows of 8-channel vectors, 16-byte aligned");
+  const int grid = ew_grid((int64_t)B * N * h * w * (C / 8));
+  if (src_dtype == SVL_BF16) pool_tokens_bwd_from_kernel<true><<<grid, 256, 0, ST>>>(src, lds, dtok, ldt, dx, B, N, h, w, C, pool);
+  else pool_tokens_bwd_from_kernel<false><<<grid, 256, 0, ST>>>(src, lds, dtok, ldt, dx, B, N, h, w, C, pool);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
 extern "C" int svl_unpool_add(const void* x, int x_dtype, int64_t ldx, const float* tok, int64_t ldt, void* out, int out_dtype, int64_t ldo, int B,
                               int N, int h, int w, int C, int hp, int wp, void* stream) {
   SVL_CHECK_ARG(x && tok && out && C % 8 == 0, "svl_unpool_add: bad arguments");
@@ -1350,8 +1427,11 @@ extern "C" int svl_unpool_add(const void* x, int x_dtype, int64_t ldx, const flo
 extern "C" int svl_unpool_bwd(const void* dout, int dtype, int64_t ld, float* dtok, int64_t ldt, int B, int N, int h, int w, int C, int hp, int wp,
                               void* stream) {
   SVL_CHECK_ARG(dout && dtok, "svl_unpool_bwd: null pointer");
-  if (dtype == SVL_BF16 && ld % 8 == 0 && ldt % 8 == 0 && C % 8 == 0 && al16(dout) && al16(dtok)) {
-    unpool_bwd_bf16_kernel<<<ew_grid((int64_t)B * hp * wp * N * (ldt / 8)), 256, 0, ST>>>((const __nv_bfloat16*)dout, ld, dtok, ldt, B, N, h, w, C, hp, wp);
+  if ((dtype == SVL_BF16 || dtype == SVL_F32) && ld % 8 == 0 && ldt % 8 == 0 && C % 8 == 0 && al16(dout) && al16(dtok)) {
+    if (dtype == SVL_BF16)
+      unpool_bwd_vec_kernel<true><<<ew_grid((int64_t)B * hp * wp * N * (ldt / 8)), 256, 0, ST>>>(dout, ld, dtok, ldt, B, N, h, w, C, hp, wp);
+    else
+      unpool_bwd_vec_kernel<false><<<ew_grid((int64_t)B * hp * wp * N * (ldt / 8)), 256, 0, ST>>>(dout, ld, dtok, ldt, B, N, h, w, C, hp, wp);
     SVL_LAUNCH_CHECK();
     return SVL_OK;
   }
@@ -1375,6 +1455,11 @@ extern "C" int svl_skip_fill(const void* skip, int s_dtype, int64_t lds, void* c
 }
 extern "C" int svl_class_sum(const void* x, int dtype, int64_t ld, int c0, float* out, int B, int N, int64_t P, int Cs, void* stream) {
   SVL_CHECK_ARG(x && out && Cs % 8 == 0, "svl_class_sum: bad arguments");
+  if (dtype == SVL_BF16 && ld % 8 == 0 && c0 % 8 == 0 && al16(x) && al16(out)) {
+    class_sum_bf16_kernel<<<ew_grid((int64_t)B * P * (Cs / 8)), 256, 0, ST>>>((const __nv_bfloat16*)x, ld, c0, out, B, N, P, Cs);
+    SVL_LAUNCH_CHECK();
+    return SVL_OK;
+  }
   class_sum_kernel<<<ew_grid((int64_t)B * P * (Cs / 8)), 256, 0, ST>>>(x, dtype, ld, c0, out, B, N, P, Cs);
   SVL_LAUNCH_CHECK();
   return SVL_OK;

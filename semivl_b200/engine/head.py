@@ -358,8 +358,11 @@ class HeadEngine:
             L.call("svl_unpool_bwd", d_cur, d_cur_dtype, d_cur.shape[-1], d_tok1, Ed, B, N, h, w, C, hp, wp)
             d_tok0 = self._tlayer_bwd(ctx["Sl"][l], d_tok1, p, f"layers.{l}.transformer.", B * hp * wp, N, grads)
             d_prev = torch.empty(nb * hw, C, **f32)
-            ops.cast(d_cur, d_cur_dtype, d_prev, L.F32, nb * hw, C)
-            L.call("svl_pool_tokens_bwd", d_tok0, Ed, d_prev, B, N, h, w, C, c.pool)
+            if d_cur_dtype in (L.F32, L.BF16):          # one pass: f32 copy of the incoming gradient + pooling gradient
+                L.call("svl_pool_tokens_bwd_from", d_cur, d_cur_dtype, d_cur.shape[-1], d_tok0, Ed, d_prev, B, N, h, w, C, c.pool)
+            else:
+                ops.cast(d_cur, d_cur_dtype, d_prev, L.F32, nb * hw, C)
+                L.call("svl_pool_tokens_bwd", d_tok0, Ed, d_prev, B, N, h, w, C, c.pool)
             tsum = torch.zeros(N * Ed, **f32)
             ops.colsum(d_tok0, L.F32, B * hp * wp, N * Ed, tsum, ld=N * Ed)
             d_t.add_(tsum.view(N, Ed)[:, C:])

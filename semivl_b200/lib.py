@@ -89,6 +89,7 @@ _PROTOS = {
     "svl_map_bcast_add": [_P, _P, _I, _L, _L, _I, _I, _F, _P],
     "svl_pool_tokens": [_P, _I, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_pool_tokens_bwd": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P],
+    "svl_pool_tokens_bwd_from": [_P, _I, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P],
     "svl_unpool_add": [_P, _I, _L, _P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_unpool_bwd": [_P, _I, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_skip_fill": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -116,6 +116,12 @@ def test_pool_unpool_tokens(L, B, N, h, w):
     dx = torch.ones(B * N, h, w, C, device="cuda")
     L.call("svl_pool_tokens_bwd", dtk, C + Ct, dx, B, N, h, w, C, pool)
     assert _rel(dx, xr2.grad + 1) < 1e-5
+    # fused variant: dx = src + pooling gradient, src f32 or bf16, written once
+    src = torch.randn(B * N, h, w, C, device="cuda", generator=g)
+    for sv, dt in ((src, L.F32), (src.to(torch.bfloat16), L.BF16)):
+        dx2 = torch.full((B * N, h, w, C), 5.0, device="cuda")
+        L.call("svl_pool_tokens_bwd_from", sv, dt, C, dtk, C + Ct, dx2, B, N, h, w, C, pool)
+        assert _rel(dx2, sv.float() + xr2.grad) < 1e-5
 
 
 @pytest.mark.parametrize("B,N,h,w,Cs", [(2, 3, 8, 8, 32), (1, 4, 5, 5, 16)])
@@ -196,3 +202,15 @@ def test_conv_out1_bf16_fast_path(L, maps, h, w):
     assert _rel(dx, xr.grad) < 5e-3                         # bf16 output rounding
     assert _rel(dw.view(3, 3, C).permute(2, 0, 1)[None], wr.grad) < 1e-4
     assert _rel(dbias, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,N,P,Cs,c0,ld", [(2, 21, 300, 32, 96, 128), (1, 5, 77, 16, 48, 64), (3, 4, 64, 8, 0, 8)])
+def test_class_sum(L, B, N, P, Cs, c0, ld):
+    """out[b, p, c] = sum_n x[(b, n), p, c0 + c]: generic (f32) and the batched-load bf16 path"""
+    g = torch.Generator(device="cuda").manual_seed(P)
+    x = torch.randn(B * N, P, ld, device="cuda", generator=g)
+    for t, dt, tol in ((x, L.F32, 1e-6), (x.to(torch.bfloat16), L.BF16, 1e-6)):
+        out = torch.full((B, P, Cs), 4.0, device="cuda")
+        L.call("svl_class_sum", t, dt, ld, c0, out, B, N, P, Cs)
+        ref = t.float().reshape(B, N, P, ld)[..., c0:c0 + Cs].sum(1)
+        assert _rel(out, ref) < tol

@@ -3,7 +3,8 @@
 // tcgen05.ld, write P as a K-major SWIZZLE_128B operand into shared memory and fold each O_tile into fp32 registers.
 //
 //   warp 0      : TMA producer (Q once; K/V tiles of 128 keys, 2-stage ring; 3-D tensor map -> rows >= L are zero-filled)
-//   warp 1      : MMA issuer  (S_{j+1} is issued before P_j V_j so the tensor pipe works while the softmax of tile j runs)
+//   warp 1      : MMA issuer  (S_{j+1} is issued as soon as the softmax warps release S_j, BEFORE P_j V_j: the softmax of tile j+1 never
+//                 waits behind a P V product; same order in the backward kernels: scores of tile j+1 before the accumulates of tile j)
 //   warps 2..5  : softmax / output (thread = query row = TMEM lane)
 //
 // TMEM: S[2] (2 x 128 columns) | O_tile[2] (2 x 64 columns).  Shared memory: Q 16 KB, K/V 2 x 32 KB, P 2 x 32 KB.
@@ -256,6 +257,7 @@ struct BwdParams {
   __nv_bfloat16* dqkv; int64_t ldg;
   int L, Lp, heads;
   float scale;
+  int s_first;        // MMA issue order: 1 = the score products of tile j+1 are issued before the accumulate products of tile j
 };
 
 __global__ void attn_prep_tc_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int64_t ldo,
@@ -275,6 +277,47 @@ __global__ void attn_prep_tc_kernel(const __nv_bfloat16* __restrict__ out, const
         ls = lse[(bi * heads + h) * L + l] * kLog2e;
       }
       if (lane == 0) {
+        delta_p[(bi * heads + h) * Lp + l] = s;
+        lse_p[(bi * heads + h) * Lp + l] = ls;
+      }
+    }
+  }
+}
+
+// heads % 4 == 0: 16-byte loads, 8 lanes per head (4 heads per 256-element chunk), all of a row's loads issued before the reductions
+template <int CHUNKS>
+__global__ void attn_prep_tc_vec_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int64_t ldo,
+                                        const float* __restrict__ lse, float* __restrict__ lse_p, float* __restrict__ delta_p, int b, int L, int Lp,
+                                        int heads) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)b * Lp;
+  for (int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t bi = row / Lp, l = row % Lp;
+    uint4 a[CHUNKS], g[CHUNKS];
+    if (l < L) {
+      const int64_t src = (bi * L + l) * ldo + lane * 8;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        a[c] = __ldg((const uint4*)(out + src + c * 256));
+        g[c] = __ldg((const uint4*)(dout + src + c * 256));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int h = c * 4 + (lane >> 3);
+      float s = 0.f, ls = INFINITY;
+      if (l < L) {
+        float fa[8], fg[8];
+        bf16x8_to_f32(a[c], fa);
+        bf16x8_to_f32(g[c], fg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += fa[i] * fg[i];
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if ((lane & 7) == 0) {
+        if (l < L) ls = lse[(bi * heads + h) * L + l] * kLog2e;
         delta_p[(bi * heads + h) * Lp + l] = s;
         lse_p[(bi * heads + h) * Lp + l] = ls;
       }
@@ -360,7 +403,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
     const uint64_t kd = tmpl + (uint64_t)(sK >> 4), vd = tmpl + (uint64_t)(sV >> 4), pd = tmpl + (uint64_t)(sP >> 4), sd = tmpl + (uint64_t)(sS >> 4);
     ptx::mbar_wait(kv_full, 0);
-    for (int j = 0; j < nt; ++j) {
+    auto scores = [&](int j) {               // S^T_j = K Q_j^T and dP^T_j = V dO_j^T once the softmax warps have copied the previous pair out
       const int st = j & 1, k = j >> 1;
       ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));
       ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
@@ -374,6 +417,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         ptx::umma_commit(s_full);
       }
       __syncwarp();
+    };
+    auto accumulate = [&](int j) {           // dV += P^T_j dO_j, dK += dS^T_j Q_j, then the operand buffers and the Q / dO stage are free
+      const int st = j & 1;
+      const uint64_t qd = tmpl + (uint64_t)((sQ + st * kHalf) >> 4), gd = tmpl + (uint64_t)((sG + st * kHalf) >> 4);
       ptx::mbar_wait(p_full, (uint32_t)(j & 1));
       ptx::tc_fence_after();
       if (leader) {
@@ -387,6 +434,18 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         ptx::umma_commit(q_empty(st));
       }
       __syncwarp();
+    };
+    if (p.s_first) {
+      scores(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) scores(j + 1);       // runs on the tensor pipe while the softmax warps do the exp / dS algebra of tile j
+        accumulate(j);
+      }
+    } else {
+      for (int j = 0; j < nt; ++j) {
+        scores(j);
+        accumulate(j);
+      }
     }
     if (leader) ptx::umma_commit(acc_full);
     __syncwarp();
@@ -529,7 +588,7 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const uint64_t tmpl = ptx::make_smem_desc(0, 8192, 1024);
     const uint64_t qd = tmpl + (uint64_t)(sQ >> 4), gd = tmpl + (uint64_t)(sG >> 4), sd = tmpl + (uint64_t)(sS >> 4);
     ptx::mbar_wait(q_full, 0);
-    for (int j = 0; j < nt; ++j) {
+    auto scores = [&](int j) {               // S_j = Q K_j^T, dP_j = dO V_j^T
       const int st = j & 1, k = j >> 1;
       ptx::mbar_wait(kv_full(st), (uint32_t)(k & 1));
       ptx::mbar_wait(s_empty, (uint32_t)((j & 1) ^ 1));
@@ -543,6 +602,10 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         ptx::umma_commit(s_full);
       }
       __syncwarp();
+    };
+    auto accumulate = [&](int j) {           // dQ += dS_j K_j
+      const int st = j & 1;
+      const uint64_t kd = tmpl + (uint64_t)((sK + st * kHalf) >> 4);
       ptx::mbar_wait(p_full, (uint32_t)(j & 1));
       ptx::tc_fence_after();
       if (leader) {
@@ -553,6 +616,18 @@ attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         ptx::umma_commit(kv_empty(st));
       }
       __syncwarp();
+    };
+    if (p.s_first) {
+      scores(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) scores(j + 1);
+        accumulate(j);
+      }
+    } else {
+      for (int j = 0; j < nt; ++j) {
+        scores(j);
+        accumulate(j);
+      }
     }
     if (leader) ptx::umma_commit(acc_full);
     __syncwarp();
@@ -621,7 +696,7 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int h
   FwdParams p;
   p.out = (__nv_bfloat16*)out; p.ldo = E; p.lse = lse; p.L = L; p.heads = heads; p.scale = scale;
   static int s_first = -1;
-  if (s_first < 0) { const char* e = getenv("SVL_ATTN_S_FIRST"); s_first = e ? atoi(e) : 0; }
+  if (s_first < 0) { const char* e = getenv("SVL_ATTN_S_FIRST"); s_first = e ? atoi(e) : 1; }   // measured: forward 168 -> 153 us per layer at 16 x 12 x 1025 (profiles/README.md)
   p.s_first = s_first;
   const size_t smem = 7 * kTile + 8 * 13 + 16;
   static bool attr_set = false;
@@ -648,7 +723,10 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
   float* delta_p = ws + (size_t)b * heads * Lp;
   const int64_t rows = (int64_t)b * Lp;
   int pgrid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-  attn_prep_tc_kernel<<<pgrid, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, E, lse, lse_p, delta_p, b, L, Lp, heads);
+  if (heads == 12 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dout & 15) == 0)
+    attn_prep_tc_vec_kernel<3><<<pgrid, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, E, lse, lse_p, delta_p, b, L, Lp, heads);
+  else
+    attn_prep_tc_kernel<<<pgrid, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, E, lse, lse_p, delta_p, b, L, Lp, heads);
   SVL_LAUNCH_CHECK();
   CUtensorMap tmQKV64, tmQKV128, tmDO64, tmDO128;
   uint64_t dims[3] = {(uint64_t)3 * E, (uint64_t)L, (uint64_t)b};
@@ -663,6 +741,9 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
   BwdParams p;
   p.lse_p = lse_p; p.delta_p = delta_p; p.dv_add = dv_add; p.dv_add_dtype = dv_add_dtype; p.ld_dv_add = ld_dv_add;
   p.dqkv = (__nv_bfloat16*)dqkv; p.ldg = 3 * E; p.L = L; p.Lp = Lp; p.heads = heads; p.scale = scale;
+  static int s_first_b = -1;
+  if (s_first_b < 0) { const char* e = getenv("SVL_ATTN_S_FIRST"); s_first_b = e ? atoi(e) : 1; }   // measured: backward 415 -> 377 us per layer
+  p.s_first = s_first_b;
   const size_t smem_kv = 6 * (size_t)kTile + 1024 + 8 * 11 + 16, smem_q = 5 * (size_t)kTile + 8 * 11 + 16;
   static bool attr_set = false;
   if (!attr_set) {

@@ -161,7 +161,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout at the first collective: park fd 1 on stderr until the result line is due, so
+        # that rank 0's stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     from semivl_b200 import lib as L
@@ -323,6 +329,9 @@ def main():
                                               f"{args.cpu_crop}x{args.cpu_crop}, N={args.nclass}: 14 timed steps after 2 warm-up ({cms:.0f} ms/step)"}
         except Exception as e:      # the baseline must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     teardown(world, tr)
 

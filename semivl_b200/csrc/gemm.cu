@@ -40,6 +40,7 @@ struct GemmParams {
   int tiles_x, tiles_y;            // conv tiles per image row / column-of-tiles
   int num_m_tiles, num_n_tiles;
   int n_fastest;                   // tile order (see the note at the top)
+  int cluster;                     // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast
   int n, block_n, k_per_tap, num_taps;
   int stages, tmem_cols, acc_stages;
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes;
@@ -114,7 +115,8 @@ __device__ __forceinline__ void transpose_cells_8x4(float* o, int lane) {
 //          4 F32 output + F32 residual through the warp-transposed (coalesced) path
 template <int OUT, int ACT, int PRE, int DACT, int RES, int EXT, bool GEN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+            const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A][stages x B][barriers][tmem ptr]
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -132,14 +134,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_per_tap = (p.k_per_tap + BK - 1) / BK;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // Cluster mode (plain GEMMs): the two CTAs of a cluster take the row blocks 2s and 2s + 1 of the same column block in lockstep; each
+  // loads its own A tile and HALF of the B tile, multicast into both CTAs, so a CTA pulls 32 KB instead of 48 KB per k-block through
+  // L2 -> SMEM (the wide GEMMs run at the ~6300 B/clk L2 ceiling otherwise, profiles/README.md).  A stage is free when BOTH CTAs have
+  // consumed it (the peer's multicast writes into this CTA's copy), hence the 2-arrival empty barriers and the multicast commits.
+  const int crank = p.cluster ? (int)ptx::cluster_ctarank() : 0;
+  const int m_slots = p.cluster ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  const int num_tiles = m_slots * p.num_n_tiles;
+  const int tile0 = p.cluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstride = p.cluster ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), p.cluster ? 2 : 1);
     }
     for (int s = 0; s < p.acc_stages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
@@ -154,6 +163,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster) ptx::cluster_sync();          // the peer's barriers are initialised before any multicast can reach them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -175,8 +185,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / p.num_m_tiles, m_tile = p.n_fastest ? tile / p.num_n_tiles : tile % p.num_m_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tstride) {
+        const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / m_slots, m_slot = p.n_fastest ? tile / p.num_n_tiles : tile % m_slots;
+        const int m_tile = p.cluster ? 2 * m_slot + crank : m_slot;      // may be one past the last row block: TMA zero-fills, the epilogue skips
         const int n0 = n_tile * p.block_n;
         int cx = 0, cy = 0, cn = 0;
         if (p.a_conv) {
@@ -193,7 +204,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               ptx::tma_load_4d(sa, &tmA, full_bar(stage), p.tap_a_koff[t] + kb * BK, cx + p.tap_dx[t], cy + p.tap_dy[t], cn);
             else
               ptx::tma_load_2d(sa, &tmA, full_bar(stage), p.tap_a_koff[t] + kb * BK, m_tile * BM);
-            ptx::tma_load_2d(sb, &tmB, full_bar(stage), p.tap_b_col[t] + kb * BK, p.tap_b_row[t] + n0);
+            if (p.cluster)
+              ptx::tma_load_2d_multicast(sb + (uint32_t)crank * (p.b_stage_bytes >> 1), &tmBh, full_bar(stage), p.tap_b_col[t] + kb * BK,
+                                         p.tap_b_row[t] + n0 + crank * (p.block_n >> 1), (uint16_t)3);
+            else
+              ptx::tma_load_2d(sb, &tmB, full_bar(stage), p.tap_b_col[t] + kb * BK, p.tap_b_row[t] + n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -243,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     } else {
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstride) {
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
@@ -260,7 +275,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int kk = 0; kk < 4; ++kk) {
                 if (kk < nk) ptx::umma_bf16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk == 0 ? accum : 1u);
               }
-              ptx::umma_commit(empty_bar(stage));
+              if (p.cluster) ptx::umma_commit_multicast(empty_bar(stage), (uint16_t)3);
+              else ptx::umma_commit(empty_bar(stage));
             }
             accum = 1;
             __syncwarp();
@@ -285,8 +301,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // column groups without a 32-column chunk of this block_n (narrow conv outputs) take no part: the accumulator-free barrier counts
     // only the active groups
     const bool active = cgrp * 32 < p.block_n;
-    for (int tile = active ? blockIdx.x : num_tiles; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / p.num_m_tiles, m_tile = p.n_fastest ? tile / p.num_n_tiles : tile % p.num_m_tiles;
+    for (int tile = active ? (p.strip ? (int)blockIdx.x : tile0) : num_tiles; tile < num_tiles; tile += (p.strip ? (int)gridDim.x : tstride)) {
+      const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / m_slots, m_slot = p.n_fastest ? tile / p.num_n_tiles : tile % m_slots;
+      const int m_tile = p.cluster ? 2 * m_slot + crank : m_slot;
       const int n0 = n_tile * p.block_n;
       const int64_t grow = tile_row_to_global(p, m_tile, r, rib);
       int64_t ct_base = 0;                  // CONVT2X2: element offset of output pixel (2y, 2x), channel 0
@@ -535,6 +552,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster) ptx::cluster_sync();          // no CTA leaves while its peer may still signal into its shared memory
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -589,7 +607,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.n_fastest = p.num_n_tiles > 1 && !d->a_conv && (int64_t)d->m * d->k_per_tap * d->num_taps * 2 > (48ll << 20);
   const int64_t a_cols = d->a_cols > 0 ? d->a_cols : d->lda;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBh;
   if (d->a_conv) {
     SVL_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0 && (int64_t)d->nb * d->h * d->w == d->m, "svl_gemm: conv geometry does not match m");
     p.nb = d->nb; p.h = d->h; p.w = d->w;
@@ -658,6 +676,14 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
     uint32_t box[2] = {(uint32_t)BK, (uint32_t)p.block_n};
     if (int rc = tma_encode_bf16(&tmB, d->b, 2, dims, strides, box)) return rc;
+    tmBh = tmB;
+    static int cluster_on = -1;
+    if (cluster_on < 0) { const char* e = getenv("SVL_GEMM_CLUSTER"); cluster_on = e ? atoi(e) : 0; }
+    p.cluster = cluster_on && !d->a_conv && p.num_m_tiles >= 2 && p.block_n % 16 == 0;
+    if (p.cluster) {                                        // half-height box for the multicast halves
+      uint32_t boxh[2] = {(uint32_t)BK, (uint32_t)(p.block_n / 2)};
+      if (int rc = tma_encode_bf16(&tmBh, d->b, 2, dims, strides, boxh)) return rc;
+    }
   }
   p.a_stage_bytes = BM * 128u;
   p.b_stage_bytes = (uint32_t)p.block_n * 128u;      // block_n % 16 == 0 -> multiple of 2048, keeps every stage 1024-aligned
@@ -698,8 +724,10 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.accumulate = d->accumulate;
 
   const size_t smem = 1024 + smem_data + 8 * (2 * kMaxStages + 2 * kMaxAcc + 2) + 16;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (p.strip) p.cluster = 0;
+  const int num_tiles = (p.cluster ? (p.num_m_tiles + 1) / 2 * 2 : p.num_m_tiles) * p.num_n_tiles;
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (p.cluster) grid &= ~1;                                // whole clusters
   const bool plain = !p.row_bias && !p.accumulate && p.out_mode == SVL_OUT_LINEAR;
   const bool no_extra = !p.preact_out && !p.dact_src && !p.residual && p.act == SVL_ACT_NONE;
 #define SVL_LAUNCH_GEMM(...)                                                                                              \
@@ -709,7 +737,17 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
       SVL_CUDA(cudaFuncSetAttribute(gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
-    gemm_kernel<__VA_ARGS__><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);                               \
+    if (p.cluster) {                                                                                                      \
+      cudaLaunchConfig_t cfg = {};                                                                                        \
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream; \
+      cudaLaunchAttribute at[1];                                                                                          \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                                 \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                                                   \
+      SVL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<__VA_ARGS__>, tmA, tmB, tmBh, p));                                     \
+    } else {                                                                                                              \
+      gemm_kernel<__VA_ARGS__><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmBh, p);                        \
+    }                                                                                                                     \
   } while (0)
   if (plain && no_extra && p.out_dtype == SVL_BF16) {
     SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 0, false);

@@ -239,3 +239,16 @@ def test_throughput_report(ops):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"wgrad {rows}x{m}x{n}: {ms * 1e3:.1f} us  {2 * m * n * rows / ms / 1e9:.1f} TFLOP/s")
+
+
+def test_cluster_multicast_mode_subprocess():
+    """SVL_GEMM_CLUSTER=1 (2-CTA clusters, B tile multicast, 2-arrival stage barriers) is an opt-in launch mode read once per process:
+    run the plain / epilogue GEMM tests in a child process with it switched on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SVL_GEMM_CLUSTER="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gemm_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "plain_gemm or epilogue or ffn_epilogues or wgrad_linear"], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -40,7 +40,9 @@ struct GemmParams {
   int tiles_x, tiles_y;            // conv tiles per image row / column-of-tiles
   int num_m_tiles, num_n_tiles;
   int n_fastest;                   // tile order (see the note at the top)
-  int cluster;                     // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast
+  int tma_store;                   // 1: bf16 output tiles are staged in shared memory and written by TMA (full 128-byte lines)
+  int cluster;                     // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast;
+                                   // 2: CTA pairs run ONE cta_group::2 UMMA (M = 256), each CTA holds half of the B tile
   int n, block_n, k_per_tap, num_taps;
   int stages, tmem_cols, acc_stages;
   uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes;
@@ -113,17 +115,19 @@ __device__ __forceinline__ void transpose_cells_8x4(float* o, int lane) {
 //   RES  : dtype of the residual or -1        GEN : runtime-generic epilogue (all features, everything a runtime branch)
 //   EXT  : 0 linear output; 1 ConvT 2x2 scatter; 2 per-row-block bias (row_bias); 3 accumulate into an F32 output;
 //          4 F32 output + F32 residual through the warp-transposed (coalesced) path
-template <int OUT, int ACT, int PRE, int DACT, int RES, int EXT, bool GEN>
+template <int OUT, int ACT, int PRE, int DACT, int RES, int EXT, bool GEN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
-            const __grid_constant__ GemmParams p) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A][stages x B][barriers][tmem ptr]
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + p.stages * p.a_stage_bytes;
   // strip mode: smem_b holds the resident weights of all taps (num_taps tiles), the A ring holds strips
-  const uint32_t bar_base = smem_b + (p.strip ? (uint32_t)p.num_taps * p.b_tile_bytes : p.stages * p.b_stage_bytes);   // 1024-aligned
+  // TMA-store mode: four 128-row x 64-column bf16 boxes (SWIZZLE_128B, 16 KB each) staged after the operand ring
+  const uint32_t smem_c = smem_b + (p.strip ? (uint32_t)p.num_taps * p.b_tile_bytes : p.stages * p.b_stage_bytes);   // 1024-aligned
+  const uint32_t bar_base = smem_c + (p.tma_store ? 4u * 16384u : 0u);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
@@ -139,6 +143,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // L2 -> SMEM (the wide GEMMs run at the ~6300 B/clk L2 ceiling otherwise, profiles/README.md).  A stage is free when BOTH CTAs have
   // consumed it (the peer's multicast writes into this CTA's copy), hence the 2-arrival empty barriers and the multicast commits.
   const int crank = p.cluster ? (int)ptx::cluster_ctarank() : 0;
+  constexpr bool pair = PAIR;                  // cta_group::2 code only exists in the PAIR instantiations (they must be launched as clusters)
   const int m_slots = p.cluster ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
   const int num_tiles = m_slots * p.num_n_tiles;
   const int tile0 = p.cluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstride = p.cluster ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -148,18 +153,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), p.cluster ? 2 : 1);
+      ptx::mbar_init(empty_bar(s), p.cluster == 1 ? 2 : 1);
     }
     for (int s = 0; s < p.acc_stages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 4 * (p.block_n < kEpiGroups * 32 ? (p.block_n + 31) / 32 : kEpiGroups));
+      // pair mode: the epilogue warps of BOTH CTAs release the accumulator stage on the leader's barrier
+      ptx::mbar_init(tempty_bar(s), (pair ? 2 : 1) * 4 * (p.block_n < kEpiGroups * 32 ? (p.block_n + 31) / 32 : kEpiGroups));
     }
     ptx::mbar_init(wbar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
-    ptx::tmem_relinquish();
+    if (pair) {
+      ptx::tmem_alloc_pair(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -198,13 +209,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int t = 0; t < p.num_taps; ++t) {
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_tx_bytes + p.b_stage_bytes);
             const uint32_t sa = smem_a + stage * p.a_stage_bytes, sb = smem_b + stage * p.b_stage_bytes;
+            if (pair) {
+              // both CTAs' tiles complete on the LEADER's barrier (only its MMA warp waits); the leader arms it with the bytes of the pair
+              if (crank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2u * (p.a_tx_bytes + p.b_stage_bytes));
+              const uint32_t lead_bar = ptx::cluster_map(full_bar(stage), 0);
+              ptx::tma_load_2d_pair(sa, &tmA, lead_bar, p.tap_a_koff[t] + kb * BK, m_tile * BM);
+              ptx::tma_load_2d_pair(sb, &tmBh, lead_bar, p.tap_b_col[t] + kb * BK, p.tap_b_row[t] + n0 + crank * (p.block_n >> 1));
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.a_tx_bytes + p.b_stage_bytes);
             if (p.a_conv)
               ptx::tma_load_4d(sa, &tmA, full_bar(stage), p.tap_a_koff[t] + kb * BK, cx + p.tap_dx[t], cy + p.tap_dy[t], cn);
             else
               ptx::tma_load_2d(sa, &tmA, full_bar(stage), p.tap_a_koff[t] + kb * BK, m_tile * BM);
-            if (p.cluster)
+            if (p.cluster == 1)
               ptx::tma_load_2d_multicast(sb + (uint32_t)crank * (p.b_stage_bytes >> 1), &tmBh, full_bar(stage), p.tap_b_col[t] + kb * BK,
                                          p.tap_b_row[t] + n0 + crank * (p.block_n >> 1), (uint16_t)3);
             else
@@ -221,7 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ~30 instructions per MMA (vector->uniform moves inside a waterfall loop) and small-N convolutions become bound by this one
     // thread (profiles/r01_up2_conv_issue_bound.md).  The strip mode reads its per-tile MMA list (A offset inside the strip,
     // B offset inside the resident weights) from a host-built table in the constant bank.
-    const uint32_t idesc = ptx::make_idesc_bf16(BM, p.block_n, 0, 0);
+    const uint32_t idesc = ptx::make_idesc_bf16(pair ? 2 * BM : BM, p.block_n, 0, 0);
     const bool leader = ptx::elect_one();
     const uint64_t tmpl = ptx::make_smem_desc(0, 16, 1024);
     int stage = 0;
@@ -258,7 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     } else {
-      for (int tile = tile0; tile < num_tiles; tile += tstride) {
+      for (int tile = (pair && crank != 0) ? num_tiles : tile0; tile < num_tiles; tile += tstride) {      // pair mode: the leader issues for both SMs
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
@@ -273,9 +293,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (leader) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
-                if (kk < nk) ptx::umma_bf16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk == 0 ? accum : 1u);
+                if (kk < nk) {
+                  if (pair) ptx::umma_bf16_pair(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk == 0 ? accum : 1u);
+                  else ptx::umma_bf16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk == 0 ? accum : 1u);
+                }
               }
-              if (p.cluster) ptx::umma_commit_multicast(empty_bar(stage), (uint16_t)3);
+              if (pair) ptx::umma_commit_pair(empty_bar(stage), (uint16_t)3);
+              else if (p.cluster) ptx::umma_commit_multicast(empty_bar(stage), (uint16_t)3);
               else ptx::umma_commit(empty_bar(stage));
             }
             accum = 1;
@@ -283,7 +307,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
-        if (leader) ptx::umma_commit(tfull_bar(as));
+        if (leader) {
+          if (pair) ptx::umma_commit_pair(tfull_bar(as), (uint16_t)3);      // both CTAs' epilogue warps read their half of the accumulator
+          else ptx::umma_commit(tfull_bar(as));
+        }
         __syncwarp();
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
@@ -418,6 +445,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (!GEN) {
         // specialised epilogue: 32-column chunks, one output row per thread, 32-byte vector accesses (full sectors);
         // bias / act / act' / residual fused in registers
+        if (OUT == SVL_BF16 && p.tma_store) {
+          // the previous tile's TMA stores must have finished READING the staging boxes before anyone overwrites them
+          if (threadIdx.x == 64) ptx::bulk_wait_group_read0();
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiGroups) : "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                  // block_n <= 256: at most two chunks per warp
           const int c0 = (cgrp + j * kEpiGroups) * 32;
@@ -539,23 +571,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] += sv[i];
             }
-            st16(p.out, OUT, off, p.ldc / 2, cnt, f);
+            if (OUT == SVL_BF16 && p.tma_store) {
+              // stage the 16 values (32 bytes) in the SWIZZLE_128B box of their 64-column group: row r, 16-byte chunks XOR-swizzled by r % 8
+              const int tc = c0 + g * 16;                       // column inside the tile
+              uint8_t* rowp = smem_raw + (smem_c - ptx::smem_u32(smem_raw)) + (uint32_t)(tc >> 6) * 16384u + (uint32_t)r * 128u;
+              const int k0 = (tc & 63) >> 3;
+              *(uint4*)(rowp + (((k0) ^ (r & 7)) << 4)) = f32_to_bf16x8(f);
+              *(uint4*)(rowp + (((k0 + 1) ^ (r & 7)) << 4)) = f32_to_bf16x8(f + 8);
+            } else {
+              st16(p.out, OUT, off, p.ldc / 2, cnt, f);
+            }
           }
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (pair && crank != 0) ptx::mbar_arrive_cluster(ptx::cluster_map(tempty_bar(as), 0));
+        else ptx::mbar_arrive(tempty_bar(as));
+      }
+      if (!GEN && OUT == SVL_BF16 && p.tma_store) {
+        ptx::fence_proxy_async();                                // generic-proxy writes of the staging boxes -> visible to the TMA engine
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiGroups) : "memory");
+        if (threadIdx.x == 64) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (b * 64 < p.block_n && n0 + b * 64 < p.n) ptx::tma_store_2d(&tmC, smem_c + (uint32_t)b * 16384u, n0 + b * 64, m_tile * BM);
+          ptx::bulk_commit_group();                              // rows >= M / columns >= N are clipped by the tensor map
+        }
+      }
       if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
     }
   }
 
+  if (p.tma_store && threadIdx.x == 64) ptx::bulk_wait_group0();      // the last tile's stores are complete before the CTA retires
   ptx::tc_fence_before();
   __syncthreads();
   if (p.cluster) ptx::cluster_sync();          // no CTA leaves while its peer may still signal into its shared memory
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (pair) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -591,6 +647,8 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   if (int rc = svl_check_device()) return rc;
 
   GemmParams p;
+  p.tma_store = 0;
+  p.cluster = 0;
   memset(&p, 0, sizeof(p));
   p.a_conv = d->a_conv;
   p.m = d->m;
@@ -607,7 +665,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.n_fastest = p.num_n_tiles > 1 && !d->a_conv && (int64_t)d->m * d->k_per_tap * d->num_taps * 2 > (48ll << 20);
   const int64_t a_cols = d->a_cols > 0 ? d->a_cols : d->lda;
 
-  CUtensorMap tmA, tmB, tmBh;
+  CUtensorMap tmA, tmB, tmBh, tmC;
   if (d->a_conv) {
     SVL_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0 && (int64_t)d->nb * d->h * d->w == d->m, "svl_gemm: conv geometry does not match m");
     p.nb = d->nb; p.h = d->h; p.w = d->w;
@@ -679,14 +737,15 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     tmBh = tmB;
     static int cluster_on = -1;
     if (cluster_on < 0) { const char* e = getenv("SVL_GEMM_CLUSTER"); cluster_on = e ? atoi(e) : 0; }
-    p.cluster = cluster_on && !d->a_conv && p.num_m_tiles >= 2 && p.block_n % 16 == 0;
-    if (p.cluster) {                                        // half-height box for the multicast halves
+    p.cluster = (cluster_on == 1 || cluster_on == 2) && !d->a_conv && p.num_m_tiles >= 2 && p.block_n % 32 == 0 ? cluster_on : 0;
+    if (p.cluster) {                                        // half-height box: the B half a CTA loads (multicast to both, or kept, in pair mode)
       uint32_t boxh[2] = {(uint32_t)BK, (uint32_t)(p.block_n / 2)};
       if (int rc = tma_encode_bf16(&tmBh, d->b, 2, dims, strides, boxh)) return rc;
     }
   }
   p.a_stage_bytes = BM * 128u;
   p.b_stage_bytes = (uint32_t)p.block_n * 128u;      // block_n % 16 == 0 -> multiple of 2048, keeps every stage 1024-aligned
+  if (p.cluster == 2) p.b_stage_bytes >>= 1;         // pair mode: a CTA stores only its half of the B tile (block_n % 32 == 0)
   p.b_tile_bytes = p.b_stage_bytes;
   size_t smem_data;
   if (p.strip) {
@@ -707,10 +766,27 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
       p.g_nmma[g] = nm;
     }
   } else {
-    p.stages = (int)(kSmemBudget / (p.a_stage_bytes + p.b_stage_bytes));
+    // TMA-store epilogue: single bf16 output of a plain GEMM, full-width tiles (all 16 epilogue warps take part in its barriers)
+    static int tma_store_on = -1;
+    if (tma_store_on < 0) { const char* e = getenv("SVL_GEMM_TMA_STORE"); tma_store_on = e ? atoi(e) : 0; }
+    p.tma_store = tma_store_on && !d->a_conv && d->out_dtype == SVL_BF16 && d->out_mode == SVL_OUT_LINEAR && !d->preact_out && !d->row_bias &&
+                  !d->accumulate && !d->residual && p.block_n == 256 && d->ldc % 8 == 0 && ((uintptr_t)d->out & 15) == 0 &&
+                  (d->act == SVL_ACT_NONE || d->act == SVL_ACT_GELU) &&
+                  (!d->dact_src || ((d->dact_kind == SVL_ACT_GELU || d->dact_kind == SVL_ACT_SAVED) && d->dact_dtype == SVL_BF16 && d->n % 32 == 0 &&
+                                    d->ld_dact % 8 == 0 && ((uintptr_t)d->dact_src & 15) == 0));
+    const size_t stage_c = p.tma_store ? 4 * 16384 : 0;
+    const size_t budget = p.tma_store ? (size_t)(227 * 1024 - 2048) : (size_t)kSmemBudget;       // operand ring + staging boxes fill the SM
+    p.stages = (int)((budget - stage_c) / (p.a_stage_bytes + p.b_stage_bytes));
     if (p.stages > kMaxStages) p.stages = kMaxStages;
-    smem_data = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes);
+    smem_data = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + stage_c;
+    if (p.tma_store) {
+      uint64_t dimsc[2] = {(uint64_t)d->n, (uint64_t)d->m};
+      uint64_t stridesc[1] = {(uint64_t)d->ldc * 2};
+      uint32_t boxc[2] = {64u, (uint32_t)BM};
+      if (int rc = tma_encode_bf16(&tmC, d->out, 2, dimsc, stridesc, boxc)) return rc;
+    }
   }
+  if (!p.tma_store) tmC = tmA;
   p.acc_stages = 512 / p.block_n < kMaxAcc ? 512 / p.block_n : kMaxAcc;
   if (const char* e = getenv("SVL_ACC_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.acc_stages) p.acc_stages = v; }
   p.tmem_cols = pow2ceil(p.acc_stages * p.block_n < 32 ? 32 : p.acc_stages * p.block_n);
@@ -730,11 +806,11 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   if (p.cluster) grid &= ~1;                                // whole clusters
   const bool plain = !p.row_bias && !p.accumulate && p.out_mode == SVL_OUT_LINEAR;
   const bool no_extra = !p.preact_out && !p.dact_src && !p.residual && p.act == SVL_ACT_NONE;
-#define SVL_LAUNCH_GEMM(...)                                                                                              \
+#define SVL_LAUNCH_GEMM_AS(PAIRV, ...)                                                                                    \
   do {                                                                                                                    \
     static bool attr_set = false;                                                                                         \
     if (!attr_set) {                                                                                                      \
-      SVL_CUDA(cudaFuncSetAttribute(gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
+      SVL_CUDA(cudaFuncSetAttribute(gemm_kernel<__VA_ARGS__, PAIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
     if (p.cluster) {                                                                                                      \
@@ -744,10 +820,15 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
       at[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                                 \
       cfg.attrs = at; cfg.numAttrs = 1;                                                                                   \
-      SVL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<__VA_ARGS__>, tmA, tmB, tmBh, p));                                     \
+      SVL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<__VA_ARGS__, PAIRV>, tmA, tmB, tmBh, tmC, p));                              \
     } else {                                                                                                              \
-      gemm_kernel<__VA_ARGS__><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmBh, p);                        \
+      gemm_kernel<__VA_ARGS__, PAIRV><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmBh, tmC, p);            \
     }                                                                                                                     \
+  } while (0)
+#define SVL_LAUNCH_GEMM(...)                                          \
+  do {                                                                \
+    if (p.cluster == 2) SVL_LAUNCH_GEMM_AS(true, __VA_ARGS__);        \
+    else SVL_LAUNCH_GEMM_AS(false, __VA_ARGS__);                      \
   } while (0)
   if (plain && no_extra && p.out_dtype == SVL_BF16) {
     SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 0, false);
@@ -782,6 +863,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, -1, 0, true);
   }
 #undef SVL_LAUNCH_GEMM
+#undef SVL_LAUNCH_GEMM_AS
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

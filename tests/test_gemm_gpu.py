@@ -241,14 +241,17 @@ def test_throughput_report(ops):
         print(f"wgrad {rows}x{m}x{n}: {ms * 1e3:.1f} us  {2 * m * n * rows / ms / 1e9:.1f} TFLOP/s")
 
 
-def test_cluster_multicast_mode_subprocess():
-    """SVL_GEMM_CLUSTER=1 (2-CTA clusters, B tile multicast, 2-arrival stage barriers) is an opt-in launch mode read once per process:
-    run the plain / epilogue GEMM tests in a child process with it switched on."""
+@pytest.mark.parametrize("env", [dict(SVL_GEMM_CLUSTER="1"), dict(SVL_GEMM_CLUSTER="2"), dict(SVL_GEMM_TMA_STORE="1"),
+                                 dict(SVL_GEMM_CLUSTER="2", SVL_GEMM_TMA_STORE="1")])
+def test_optin_launch_modes_subprocess(env):
+    """Opt-in launch modes of the contraction engine, read once per process, exercised in a child process on the plain / epilogue GEMM tests:
+    SVL_GEMM_CLUSTER=1 (2-CTA clusters, B tile TMA-multicast, 2-arrival stage barriers), =2 (CTA pairs running one cta_group::2 UMMA with
+    M = 256, half of B per CTA, leader-side barriers), SVL_GEMM_TMA_STORE=1 (bf16 tiles staged in shared memory and written by TMA)."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, SVL_GEMM_CLUSTER="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gemm_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
-                        "plain_gemm or epilogue or ffn_epilogues or wgrad_linear"], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+                        "plain_gemm or epilogue or ffn_epilogues or wgrad_linear"], env=dict(os.environ, **env), cwd=root, capture_output=True,
+                       text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -736,8 +736,12 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     if (int rc = tma_encode_bf16(&tmB, d->b, 2, dims, strides, box)) return rc;
     tmBh = tmB;
     static int cluster_on = -1;
-    if (cluster_on < 0) { const char* e = getenv("SVL_GEMM_CLUSTER"); cluster_on = e ? atoi(e) : 0; }
-    p.cluster = (cluster_on == 1 || cluster_on == 2) && !d->a_conv && p.num_m_tiles >= 2 && p.block_n % 32 == 0 ? cluster_on : 0;
+    // SVL_GEMM_CLUSTER: 0 off, 1 multicast, 2 pair everywhere; default (3) = pair mode where it was measured to pay: long-K plain GEMMs
+    // (K >= 2048: 71 % -> 83 % tensor-active, profiles/r01_ncu_targets_c.md); the K = 768 shapes are epilogue-paced and gain nothing
+    if (cluster_on < 0) { const char* e = getenv("SVL_GEMM_CLUSTER"); cluster_on = e ? atoi(e) : 3; }
+    const bool eligible = !d->a_conv && p.num_m_tiles >= 2 && p.block_n % 32 == 0;
+    p.cluster = !eligible ? 0 : (cluster_on == 1 || cluster_on == 2) ? cluster_on
+              : (cluster_on == 3 && (int64_t)d->k_per_tap * d->num_taps >= 2048 && d->num_taps == 1) ? 2 : 0;
     if (p.cluster) {                                        // half-height box: the B half a CTA loads (multicast to both, or kept, in pair mode)
       uint32_t boxh[2] = {(uint32_t)BK, (uint32_t)(p.block_n / 2)};
       if (int rc = tma_encode_bf16(&tmBh, d->b, 2, dims, strides, boxh)) return rc;

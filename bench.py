@@ -29,7 +29,7 @@ GF_PER_UNIT_SEMIVL = 4542.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="supervised", choices=["supervised", "semivl"])
@@ -197,7 +197,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 12)):       # W untimed steps, and never fewer than 12: graph capture + clock ramp of a cold box
         step(resident)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None

@@ -265,6 +265,39 @@ def input_fixture(name="input_stage"):
     print(name, "cases", len(INPUT_CASES), "non-empty boxes", int(sum(b.any() for b in boxes)))
 
 
+HEAD_CONV_KW = dict(img_size=64, num_classes=5, text_in_channels=512, text_channels=128, up_channels=(64, 32), skip_in_channels=(768, 256),
+                    skip_channels=(32, 32), skip_from_conv_feat=True, num_layers=2, num_heads=4, channels=128, pool_size=(4, 4), conv1_ksize=7,
+                    loss_decode=None, align_corners=False)
+
+
+def head_conv_fixture(name="head_convfeat_b2"):
+    """The UNMODIFIED reference VLGHead with `skip_from_conv_feat=True` (the Cityscapes skr04 head, vlg_head.py:196-205): one ViT tap + the
+    CLIP embedding at 4 x 4 tokens and a 256-channel conv-encoder feature at 16 x 16 (the ResNet stem's stride 4); forward and backward."""
+    import importlib
+    ref_shim.install()
+    with ref_shim.in_reference_cwd():
+        mod = importlib.import_module("model.decode_heads.vlg_head")
+        head = mod.VLGHead(**HEAD_CONV_KW)
+    shapes = {"decode_head." + k: tuple(v.shape) for k, v in head.state_dict().items()}
+    sd = O.fixture_state_dict(shapes, seed=3)
+    head.load_state_dict({k[len("decode_head."):]: v for k, v in sd.items()})
+    g = torch.Generator().manual_seed(31)
+    B, N = 2, HEAD_CONV_KW["num_classes"]
+    v4 = torch.randn(B, 768, 4, 4, generator=g).requires_grad_(True)
+    emb = torch.randn(B, 512, 4, 4, generator=g).requires_grad_(True)
+    conv = torch.randn(B, 256, 16, 16, generator=g).requires_grad_(True)
+    text = torch.randn(N, 512, generator=g)
+    wgt = torch.randn(B, N, 16, 16, generator=g)
+    head.train()
+    out = head([[[v4, emb], None], text, [conv]])
+    (out * wgt).sum().backward()
+    res = dict(v4=v4.detach().numpy(), emb=emb.detach().numpy(), conv=conv.detach().numpy(), text=text.numpy(), wgt=wgt.numpy(),
+               out=out.detach().numpy(), d_v4=v4.grad.numpy(), d_emb=emb.grad.numpy(), d_conv=conv.grad.numpy())
+    res.update(grad_summary([("decode_head." + n, q.grad) for n, q in head.named_parameters() if q.grad is not None]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **res)
+    print(name, "out", tuple(out.shape), "absmax", out.abs().max().item(), "ngrads", len(res["grad_names"]))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -279,6 +312,7 @@ def main():
     step_fixture("step_c64_b2_pixelratio_mean", 64, 2, seed=24, hp_over=dict(conf_mode="pixelratio", mcc_loss_reduce="mean"))
     eval_fixture()
     input_fixture()
+    head_conv_fixture()
 
 
 if __name__ == "__main__":

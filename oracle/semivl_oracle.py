@@ -177,10 +177,11 @@ def up_forward(x, skip, p, pre, n_per_img):
     return x
 
 
-def vlg_head_forward(feats, text, p, cfg, pre="decode_head.", class_to_concept=None):
-    """VLGHead.forward (vlg_head.py:192-251) up to the 4x-resolution logits [B,N,4h,4w]."""
+def vlg_head_forward(feats, text, p, cfg, pre="decode_head.", class_to_concept=None, conv_feats=None):
+    """VLGHead.forward (vlg_head.py:192-251) up to the 4x-resolution logits [B,N,4h,4w]; `conv_feats` = the conv encoder's feature
+    list of the `skip_from_conv_feat` branch (vlg_head.py:196-205)."""
     img = feats[-1]
-    skips = list(feats[:-1])[::-1]
+    skips = list(feats[:-1])[::-1] + list(conv_feats or [])[::-1]
     B, C, H, W = img.shape
     text = text.to(img.dtype)[None].expand(B, -1, -1)
     N = text.shape[1]

@@ -219,14 +219,17 @@ class HeadEngine:
         return dx, d_skip
 
     # ------------------------------------------------------------------ forward
-    def forward(self, feats, text, p, need_grad=True):
-        """feats: [skip taps (shallow..deep)..., clip embedding], each f32 NHWC [B,h,w,C]; text f32/f16 [N, in_dim].
+    def forward(self, feats, text, p, need_grad=True, conv_feats=None):
+        """feats: [skip taps (shallow..deep)..., clip embedding], each f32 NHWC [B,h,w,C]; text f32/f16 [N, in_dim];
+        conv_feats: optional list of f32 NHWC [B,sh,sw,Cc] features of a conv encoder (`skip_from_conv_feat`, vlg_head.py:196-205): they
+        follow the ViT taps in the skip list, deepest first, at their own resolution.
         Returns (low-resolution logits f32 [B, N, 4h, 4w], ctx)."""
         c, pr = self.cfg, self.precise
         adt = ops.act_dtype(pr)
         gtorch = torch.float32 if pr else torch.bfloat16
         emb = feats[-1]
-        skips_in = list(feats[:-1])[::-1]                    # deepest first (vlg_head.py:208)
+        skips_in = list(feats[:-1])[::-1] + list(conv_feats or [])[::-1]      # deepest first (vlg_head.py:196-208)
+        n_taps = len(feats) - 1
         B, h, w, D = emb.shape
         dev = emb.device
         hw = h * w
@@ -288,21 +291,23 @@ class HeadEngine:
         sk, fa = [], []
         for j, f in enumerate(skips_in):
             cs = c.skip[j]
-            a = ops.to_act(f.reshape(B * hw, c.skip_dim), pr)
-            s = torch.empty(B * hw, cs, **f32)
-            ops.gemm(a, self._prep(p, f"skip_proj.{j}.0.weight", "conv"), s, n=cs, k=c.skip_dim, precise=pr, conv=(B, h, w), filt=_f3(1),
+            sh, sw, cin = f.shape[1], f.shape[2], f.shape[3]
+            a = ops.to_act(f.reshape(B * sh * sw, cin), pr)
+            s = torch.empty(B * sh * sw, cs, **f32)
+            ops.gemm(a, self._prep(p, f"skip_proj.{j}.0.weight", "conv"), s, n=cs, k=cin, precise=pr, conv=(B, sh, sw), filt=_f3(1),
                      b_row_stride=cs, bias=p[f"skip_proj.{j}.0.bias"], act=L.ACT_RELU)
             sk.append(s)
             fa.append(a)
+        geo = [(f.shape[1], f.shape[2], f.shape[3]) for f in skips_in]
         # decoder (vlg_head.py:236-240)
-        u1, Su1 = self._up_fwd(xcur, sk[0], (h, w), nb, B, N, h, w, C, "up1.", c.up[0] // 16, p, need_grad)
-        u2, Su2 = self._up_fwd(u1, sk[1], (h, w), nb, B, N, 2 * h, 2 * w, c.up[0], "up2.", c.up[1] // 16, p, need_grad)
+        u1, Su1 = self._up_fwd(xcur, sk[0], geo[0][:2], nb, B, N, h, w, C, "up1.", c.up[0] // 16, p, need_grad)
+        u2, Su2 = self._up_fwd(u1, sk[1], geo[1][:2], nb, B, N, 2 * h, 2 * w, c.up[0], "up2.", c.up[1] // 16, p, need_grad)
         low = torch.empty(B, N, 4 * h, 4 * w, **f32)
         L.call("svl_conv_out1_fwd", u2, adt, u2.shape[-1], self._prep(p, "head.weight", "out1"), p["head.bias"], low, nb, 4 * h, 4 * w, c.up[1])
         if need_grad:
             ctx.update(img_n=img_n, inv_img=inv_img, txt_n=txt_n, txt_act=txt_act, col=col, x1=x1, cat=cat, Sb=Sb, gap_act=gap_act, graw=graw,
                        gmean=gmean, grstd=grstd, pool_act=pool_act, praw=praw, pmean=pmean, prstd=prstd, t=t, Sl=Sl, x_final=xcur, sk=sk, fa=fa,
-                       Su1=Su1, Su2=Su2, u2=u2, hp=hp, wp=wp)
+                       Su1=Su1, Su2=Su2, u2=u2, hp=hp, wp=wp, geo=geo, n_taps=n_taps)
         return low, ctx
 
     # ------------------------------------------------------------------ backward
@@ -336,18 +341,22 @@ class HeadEngine:
         d_skips = []
         for j, d_sk in ((0, d_sk0), (1, d_sk1)):
             cs = c.skip[j]
+            sh, sw, cin = ctx["geo"][j]
             name = f"skip_proj.{j}.0."
-            dw = torch.zeros(9, cs, c.skip_dim, **f32)
-            ops.wgrad(d_sk, ctx["fa"][j], dw, m=cs, n=c.skip_dim, precise=pr, conv=(B, h, w), filt=_f3(1))
-            grads[name + "weight"].add_(dw.view(3, 3, cs, c.skip_dim).permute(2, 3, 0, 1))
-            ops.colsum(d_sk, adt, B * hw, cs, grads[name + "bias"])
+            dw = torch.zeros(9, cs, cin, **f32)
+            ops.wgrad(d_sk, ctx["fa"][j], dw, m=cs, n=cin, precise=pr, conv=(B, sh, sw), filt=_f3(1))
+            grads[name + "weight"].add_(dw.view(3, 3, cs, cin).permute(2, 3, 0, 1))
+            ops.colsum(d_sk, adt, B * sh * sw, cs, grads[name + "bias"])
             if need_feat_grads:
-                d_f = torch.empty(B, h, w, c.skip_dim, **f32)
-                ops.gemm(d_sk, self._prep(p, name + "weight", "conv_t"), d_f, n=c.skip_dim, k=cs, precise=pr, conv=(B, h, w),
-                         filt=[(-a, -b) for a, b in _f3(1)], b_row_stride=c.skip_dim)
+                d_f = torch.empty(B, sh, sw, cin, **f32)
+                ops.gemm(d_sk, self._prep(p, name + "weight", "conv_t"), d_f, n=cin, k=cs, precise=pr, conv=(B, sh, sw),
+                         filt=[(-a, -b) for a, b in _f3(1)], b_row_stride=cin)
                 d_skips.append(d_f)
             else:
                 d_skips.append(None)
+        # back to the caller's order: ViT taps shallow..deep, [embedding], conv features shallow..deep
+        nt = ctx["n_taps"]
+        d_taps, d_conv = d_skips[:nt][::-1], d_skips[nt:][::-1]
         # SemanticTransformer layers
         hp, wp = ctx["hp"], ctx["wp"]
         Ed = C + c.Ct
@@ -403,7 +412,7 @@ class HeadEngine:
         grads["conv1.weight"].add_(dw1[:, : c.ks * c.ks].reshape(C, 1, c.ks, c.ks))
         ops.colsum(d_x1, L.F32, nb * hw, C, grads["conv1.bias"])
         if not need_feat_grads:
-            return d_skips[::-1] + [None]
+            return d_taps + [None] + d_conv
         d_col = torch.empty(nb * hw, 64, device=dev, dtype=gtorch)
         ops.gemm(d_x1_act, self._prep(p, "conv1.weight", "conv1_t"), d_col, n=64, k=C, precise=pr)
         Kp = (N + 15) // 16 * 16
@@ -416,7 +425,7 @@ class HeadEngine:
         ops.gemm(d_sim, ops.prep_weight(txt_t, pr), d_img_n, n=c.in_dim, k=Kp, precise=pr)
         d_emb = torch.empty(B, h, w, c.in_dim, **f32)
         ops.l2norm_bwd(d_img_n, gdt, ctx["img_n"], ctx["inv_img"], d_emb.view(B * hw, c.in_dim))
-        return d_skips[::-1] + [d_emb]
+        return d_taps + [d_emb] + d_conv
 
 
 def _pad_cols(x, mult):

@@ -45,11 +45,14 @@ class _Up(nn.Module):
 class _HeadFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, text, nfeat, grad_mode, names, *tensors):
+        """tensors = (*pyramid, *conv_feats, *params); nfeat = (len(pyramid), len(conv_feats))"""
+        npyr, nconv = nfeat
+        nfeat = npyr + nconv
         feats, params = tensors[:nfeat], tensors[nfeat:]
         p = {k: v.detach() for k, v in zip(names, params)}
         need_grad = grad_mode and any(t.requires_grad for t in tensors)
         fin = [f.detach().permute(0, 2, 3, 1).contiguous().float() for f in feats]           # NHWC; no copy for the backbone's own outputs
-        low, hctx = module.engine.forward(fin, text, p, need_grad=need_grad)
+        low, hctx = module.engine.forward(fin[:npyr], text, p, need_grad=need_grad, conv_feats=fin[npyr:] if nconv else None)
         ctx.module, ctx.names, ctx.hctx, ctx.nfeat = module, names, hctx, nfeat
         ctx.req = [t.requires_grad for t in tensors]
         ctx.save_for_backward(*params)
@@ -97,11 +100,11 @@ class VLGHead(nn.Module):
                  skip_from_conv_feat, num_layers, num_heads, channels, pool_size, conv1_ksize, loss_decode, align_corners, precise=False):
         super().__init__()
         assert loss_decode is None
-        assert not skip_from_conv_feat, "the conv_encoder (Cityscapes skr04) variant is not implemented yet (SURVEY.md §8f-1)"
         assert not align_corners, "semivl_b200 implements align_corners=False for the final resize (the SemiVL configuration)"
         assert pool_size is not None and pool_size[0] == pool_size[1]
         assert channels + text_channels == num_heads * 64, "attention kernels are specialised for head_dim 64"
-        assert len(set(skip_in_channels)) == 1 and len(skip_channels) == 2 and len(up_channels) == 2
+        assert len(skip_in_channels) == 2 and len(skip_channels) == 2 and len(up_channels) == 2
+        assert all(c % 16 == 0 for c in skip_in_channels), "skip inputs are GEMM operands: channel counts must be multiples of 16"
         self.image_size, self.num_classes, self.align_corners = img_size, num_classes, align_corners
         self.text_in_channels, self.num_layers, self.channels, self.skip_from_conv_feat = text_in_channels, num_layers, channels, skip_from_conv_feat
         self.load_text_embedding = None
@@ -131,7 +134,11 @@ class VLGHead(nn.Module):
             "concept-expanded text tables for the head are not implemented (SemiVL uses them for the MaskCLIP guidance only)"
         names = tuple(n for n, _ in self.named_parameters())
         params = tuple(p for _, p in self.named_parameters())
-        return _HeadFunction.apply(self, text, len(pyramid), torch.is_grad_enabled(), names, *pyramid, *params)
+        conv_feats = ()
+        if self.skip_from_conv_feat:                       # vlg_head.py:196-205: the conv encoder's features close the skip list
+            conv_feats = tuple(inputs[2])
+        assert len(pyramid) - 1 + len(conv_feats) == len(self.skip_proj), "number of skip features != number of skip projections"
+        return _HeadFunction.apply(self, text, (len(pyramid), len(conv_feats)), torch.is_grad_enabled(), names, *pyramid, *conv_feats, *params)
 
     def forward(self, inputs, force_output_pred_masks=False):
         low = self.forward_lowres(inputs)

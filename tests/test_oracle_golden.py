@@ -129,3 +129,32 @@ def test_evaluation_restatement_matches_reference(golden_dir):
             m2 = mask[:, sh:sh + c, sw:sw + c]
         ai, au, at = O.intersection_and_union(g[f"pred{i}"].astype(np.int64), m2.numpy(), nclass, 255)
         assert np.array_equal(np.stack((ai, au, at)), g[f"iou{i}"]), mode
+
+
+def test_head_conv_feature_branch_matches_reference(golden_dir):
+    """oracle vlg_head_forward(conv_feats=...) against the unmodified reference VLGHead built with skip_from_conv_feat=True
+    (vlg_head.py:196-205; tests/golden/head_convfeat_b2.npz): logits, input gradients and parameter-gradient norms."""
+    from oracle.make_golden import HEAD_CONV_KW
+    g = dict(np.load(os.path.join(golden_dir, "head_convfeat_b2.npz"), allow_pickle=False))
+    kw = HEAD_CONV_KW
+    mc = O.ModelCfg(img_size=kw["img_size"], num_classes=kw["num_classes"], skip_channels=kw["skip_channels"])
+    names = [str(n) for n in g["grad_names"]]
+    shapes = _head_shapes_with_conv(mc, kw)
+    assert set(names) <= set(shapes)
+    p = {k: v.clone().requires_grad_(True) for k, v in O.fixture_state_dict(shapes, seed=3).items()}
+    v4, emb, conv = (torch.from_numpy(g[k]).requires_grad_(True) for k in ("v4", "emb", "conv"))
+    out = O.vlg_head_forward([v4, emb], torch.from_numpy(g["text"]), p, mc, conv_feats=[conv])
+    assert np.abs(out.detach().numpy() - g["out"]).max() < 2e-5 * np.abs(g["out"]).max()
+    (out * torch.from_numpy(g["wgt"])).sum().backward()
+    for name, t in (("d_v4", v4), ("d_emb", emb), ("d_conv", conv)):
+        assert np.abs(t.grad.numpy() - g[name]).max() < 1e-4 * np.abs(g[name]).max() + 1e-7, name
+    for n, norm in zip(names, g["grad_norms"]):
+        if norm > 1e-7:
+            assert abs(p[n].grad.double().norm().item() - norm) <= 1e-3 * norm, n
+
+
+def _head_shapes_with_conv(mc, kw):
+    """parameter shapes of the head with its second skip taken from a 256-channel conv feature (skip_in_channels = (768, 256))"""
+    shapes = {k: v for k, v in O.param_shapes(mc, with_clip_encoder=False).items() if k.startswith("decode_head.")}
+    shapes["decode_head.skip_proj.1.0.weight"] = (kw["skip_channels"][1], kw["skip_in_channels"][1], 3, 3)
+    return shapes

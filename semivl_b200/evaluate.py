@@ -63,8 +63,10 @@ def predict(model, img, mask, mode, cfg, return_logits=False):
                 _accumulate(final, model(img[:, :, y1:y2, x1:x2].contiguous()).float(), count, y1, x1, y2 - y1, x2 - x1, False)
         assert int((count == 0).sum()) == 0
         L.call("svl_divide_count", final, count, b, n, h * w)
-        if tuple(mask.shape[-2:]) != (h, w):                  # the reference's align_corners=True resize to the label size (rare: same size in its loaders)
-            final = torch.nn.functional.interpolate(final, size=tuple(mask.shape[-2:]), mode='bilinear', align_corners=True)
+        if tuple(mask.shape[-2:]) != (h, w):
+            # supervised.py:95-100 resizes the averaged logits to the label size (align_corners=True); the reference's loaders always give
+            # image and label the same size, so this branch has no kernel here and fails loudly instead of falling back to ATen
+            raise NotImplementedError(f"zegclip_sliding_window with a label size {tuple(mask.shape[-2:])} != image size {(h, w)}")
     elif mode == 'sliding_window':                            # supervised.py:105-117: clipped windows, stride 2/3 grid, softmax summed
         grid = cfg['crop_size']
         final = torch.zeros(b, n, h, w, device=img.device)

@@ -174,3 +174,31 @@ def test_graph_replay_matches_eager_steps(text_dir):
     assert rel(m0, m2) <= max(3 * floor_m, 1e-3)
     assert rel(v0, v2) <= max(3 * floor_v, 1e-3)
     assert (p0 - p2).abs().max().item() <= max(3 * floor_p, 1e-5)
+
+
+def test_gradients_are_additive_over_the_batch(text_dir):
+    """Data-parallel correctness on one GPU (SURVEY.md §4 tier 5): the gradient of the 4-image batch equals the valid-pixel-weighted mean of
+    the gradients of its two halves -- what two ranks holding the halves would all-reduce (no cross-sample op in the sk04 model) -- and the
+    plain mean of the half-batch gradients is what `GradExchange` + the 1/world factor of AdamW produce for equal valid counts."""
+    from semivl_b200.train import OptimCfg, Trainer
+    crop, b = 64, 4
+    m, mc, sd = _build(crop, True)
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(b, 3, crop, crop, generator=g).cuda()
+    mask = torch.randint(0, 21, (b, crop, crop), generator=g)
+    mask[:2, :10] = 255
+    mask[2:, :, :10] = 255                      # same number of ignored pixels in both halves
+    mask = mask.cuda()
+    tr = Trainer(m, OptimCfg())
+    tr.supervised_step(img, mask, update=False)
+    g_full = tr.g_flat.clone()
+    tr.supervised_step(img[:2].contiguous(), mask[:2].contiguous(), update=False)
+    g_a = tr.g_flat.clone()
+    tr.supervised_step(img[2:].contiguous(), mask[2:].contiguous(), update=False)
+    g_b = tr.g_flat.clone()
+    na, nb = (mask[:2] != 255).sum().item(), (mask[2:] != 255).sum().item()
+    assert na == nb
+    want = 0.5 * (g_a + g_b)
+    err = (g_full - want).norm().item() / g_full.norm().item()
+    print("batch additivity of the gradient: rel", err)
+    assert err < 2e-3

@@ -255,3 +255,34 @@ def test_bench_reference_arm_contract(built):
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_conv_encoder_oracle_layer1_matches_torchvision(built):
+    """oracle/resnetv1c_oracle.py (groundwork for the skr04 conv encoder): the residual stage is pinned against torchvision's ResNet-101
+    `layer1` with identical weights, in training (batch statistics) and eval (running statistics) mode; the deep stem's shapes are checked."""
+    torchvision = pytest.importorskip("torchvision")
+    from oracle import resnetv1c_oracle as R
+    gen = torch.Generator().manual_seed(0)
+    tv = torchvision.models.resnet101(weights=None).layer1
+    sd = {}
+    for k, v in tv.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            continue
+        t = torch.randn(v.shape, generator=gen) * (0.1 if v.dim() > 1 else 0.5)
+        sd[k] = t.abs() + 0.5 if k.endswith("running_var") or (k.endswith("weight") and v.dim() == 1) else t
+    tv.load_state_dict(sd, strict=False)
+    p = {"conv_encoder.layer1." + k: v for k, v in sd.items()}
+    assert set(p) == {k for k in R.param_shapes() if ".layer1." in k}
+    x = torch.randn(2, 64, 12, 10, generator=gen)
+    for training in (False, True):           # eval first: a training-mode forward updates torchvision's running statistics in place
+        tv.train(training)
+        with torch.no_grad():
+            want = tv(x)
+            got = x
+            for i in range(3):
+                got = R.bottleneck_forward(got, p, f"conv_encoder.layer1.{i}.", training)
+        assert torch.allclose(got, want, atol=1e-5, rtol=1e-5), training
+    shapes = R.param_shapes()
+    full = {k: torch.randn(s, generator=gen).abs() + 0.1 if k.endswith("running_var") else torch.randn(s, generator=gen) * 0.1 for k, s in shapes.items()}
+    out = R.conv_encoder_forward(torch.randn(1, 3, 64, 64, generator=gen), full)
+    assert len(out) == 1 and tuple(out[0].shape) == (1, 256, 16, 16)

@@ -286,3 +286,38 @@ def test_conv_encoder_oracle_layer1_matches_torchvision(built):
     full = {k: torch.randn(s, generator=gen).abs() + 0.1 if k.endswith("running_var") else torch.randn(s, generator=gen) * 0.1 for k, s in shapes.items()}
     out = R.conv_encoder_forward(torch.randn(1, 3, 64, 64, generator=gen), full)
     assert len(out) == 1 and tuple(out[0].shape) == (1, 256, 16, 16)
+
+
+def test_trainer_exchange_schedule_covers_the_flat_buffer(built):
+    """The order in which Trainer hands slices of the flat gradient buffer to GradExchange during a backward pass (head first, then encoder
+    layers 9-11, 6-8, 3-5, then the rest at finish): disjoint, inside the buffer, each encoder bucket cut at a layer boundary, and together
+    with finish() covering every trainable element exactly once."""
+    from semivl_b200.model import build_model
+    from semivl_b200.train import OptimCfg, Trainer
+    cfg = dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=21, crop_size=64, dataset='pascal', text_embedding_variant='single',
+               mcc_text='single', pl_text='single', clip_encoder=None, disable_dropout=True, fp_rate=0.5, model_args=dict(pretrained=None), precise=False)
+    tr = Trainer(build_model(cfg), OptimCfg())
+    n = tr.n_bb + tr.n_hd
+    assert tr.g_flat.numel() == n and tr.p_flat.numel() == n
+
+    class Rec:
+        def __init__(self):
+            self.ranges = []
+
+        def reduce(self, lo, hi):
+            self.ranges.append((lo, hi))
+
+    rec = Rec()
+    tr.exchange = rec
+    tr._head_grads_final()                                  # after head.backward
+    for i in reversed(range(12)):                            # the encoder backward walks the layers from the last one down
+        tr._layer_grads_final(i)
+    assert rec.ranges[0] == (tr.n_bb, n)
+    enc = rec.ranges[1:]
+    assert [hi for _, hi in enc] == [tr._layers_end] + [lo for lo, _ in enc[:-1]]            # contiguous, descending
+    assert [lo for lo, _ in enc] == [tr.layer_lo[9], tr.layer_lo[6], tr.layer_lo[3]]
+    covered = sum(hi - lo for lo, hi in rec.ranges)
+    rest = tr.layer_lo[3]                                    # position table + layers 0-2: exchanged by finish()
+    assert covered + rest == n
+    # every trainable backbone tensor is an attention or position-embedding tensor (vlm.py:80-88 freeze filter)
+    assert all(("attn" in k) or ("pos_embed" in k) for k in tr.g_bb)

@@ -174,15 +174,17 @@ int svl_attention_bwd(const void* qkv, const void* out, const void* dout, int sp
  * VLG decode head kernels (model/decode_heads/vlg_head.py).  Activations are NHWC, a "map" is one (image, class) pair,
  * maps ordered (image, class).  HBM-bound: vectorised 16-byte accesses, one pass (two for GroupNorm, second L2-resident).
  * ---------------------------------------------------------------------------------------------- */
-/* out = relu(GroupNorm(x)) (+ res); statistics per (map, group) saved to mean/rstd [maps, G] (required: they are also the
- * reduction workspace)   (vlg_head.py:99-111,132-135) */
+/* out = relu(GroupNorm(x)) (+ res); statistics per (map, group) saved to mean/rstd [maps, G]   (vlg_head.py:99-111,132-135).
+ * The statistics are reduced in two fixed-order stages (per-CTA partials in `ws`, then one thread per (map, group)): no
+ * floating-point atomics, so the result is bit-reproducible from run to run.  `ws`: svl_gn_workspace(maps, hw, C, G) floats. */
+size_t svl_gn_workspace(int64_t maps, int hw, int C, int G);
 int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
-                    int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, int64_t maps, int hw, int C,
-                    int G, float eps, void* stream);
-/* dx = GN'(dy * [y > 0]); dgamma/dbeta += (atomics, may be NULL) */
+                    int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, float* ws, int64_t maps,
+                    int hw, int C, int G, float eps, void* stream);
+/* dx = GN'(dy * [y > 0]) (data gradient reduced in fixed order like the forward); dgamma/dbeta += (atomics, may be NULL) */
 int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const float* gamma,
                     const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int64_t lddx, float* dgamma,
-                    float* dbeta, float* ws /* [maps*G*2] scratch */, int64_t maps, int hw, int C, int G, void* stream);
+                    float* dbeta, float* ws /* svl_gn_workspace floats */, int64_t maps, int hw, int C, int G, void* stream);
 /* im2col of the per-class similarity maps for conv1 (ks x ks, 1 -> C; vlg_head.py:169,220-221) and its transpose */
 int svl_sim_im2col(const float* sim, int64_t ld_sim, void* out, int out_dtype, int64_t ldo, int B, int N, int h, int w, int ks, int kpad,
                    void* stream);

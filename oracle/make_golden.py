@@ -298,8 +298,71 @@ def head_conv_fixture(name="head_convfeat_b2"):
     print(name, "out", tuple(out.shape), "absmax", out.abs().max().item(), "ngrads", len(res["grad_names"]))
 
 
+def fp_fixture(name="fp_c64_b2", crop=64, b=2, seed=14, nclass=21):
+    """The feature-perturbation branches of the reference's patched forward (model/builder.py:56-102) through the public call:
+    `model(img, need_fp=True)` -> (pred, pred_fp) and `model(img, only_fp=True)`, with F.dropout2d replaced by recorded keep masks
+    (SURVEY.md §8c caveat ii); forward + backward of a loss that weights the three outputs differently."""
+    m, mc, sd = build(crop, nclass)
+    import model.builder as ref_builder
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(b, 3, crop, crop, generator=g)
+    drop_masks = [(torch.rand(b, c, 1, 1, generator=g) >= 0.5).float() for c in (768, 768, 512)]
+    wgt = [torch.randn(b, nclass, crop, crop, generator=g) for _ in range(3)]
+    calls = {"i": 0}
+    real_dropout2d = F.dropout2d
+
+    def fake_dropout2d(f, p=0.5, training=True, inplace=False):
+        mk = drop_masks[calls["i"] % 3]
+        calls["i"] += 1
+        return f * mk / (1 - p)
+    ref_builder.F.dropout2d = fake_dropout2d
+    try:
+        with ref_shim.in_reference_cwd():
+            m.train()
+            pred, pred_fp = m(img, need_fp=True)
+            only = m(img, only_fp=True)
+            loss = (pred * wgt[0]).mean() + (pred_fp * wgt[1]).mean() + (only * wgt[2]).mean()
+            loss.backward()
+    finally:
+        ref_builder.F.dropout2d = real_dropout2d
+    assert calls["i"] == 6
+    out = dict(img=img.numpy(), crop=crop, nclass=nclass, b=b, seed=seed, loss=np.float64(loss.item()),
+               pred=pred.detach().numpy().astype(np.float32), pred_fp=pred_fp.detach().numpy().astype(np.float32),
+               only_fp=only.detach().numpy().astype(np.float32), wgt_seed_note="weights = 3 x randn after img and masks from the same generator")
+    out.update({f"drop_mask{i}": d.numpy() for i, d in enumerate(drop_masks)})
+    out.update(grad_summary([(n, q.grad) for n, q in m.named_parameters() if q.grad is not None]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "loss", loss.item(), "fp differs from clean:", (pred - pred_fp).abs().max().item(), "ngrads", len(out["grad_names"]))
+
+
+def concept_fixture(name, dataset, nclass, mcc_text, crop=64, b=2, seed=15):
+    """`forward_maskclip` with a concept text table (model/vlm.py:98-109 + aggregate_concept_predictions, model/text_embeddings.py:188-193):
+    the reference's real VOC (`concept4_single`, 98 rows -> 21) and Cityscapes (`concept3_single`, 54 -> 19) settings."""
+    m, mc, sd = build(crop, nclass, dataset=dataset, mcc_text=mcc_text)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(b, 3, crop, crop, generator=g)
+    th_lo = 1.0 / nclass + 1e-3
+    with ref_shim.in_reference_cwd():
+        m.eval()
+        with torch.no_grad():
+            mcl = m.forward_maskclip(img, 0.9)
+            mcl_lo = m.forward_maskclip(img, th_lo)
+            mcl_all = m.forward_maskclip(img, 0.0)
+    out = dict(img=img.numpy(), crop=crop, nclass=nclass, dataset=dataset, mcc_text=mcc_text, maskclip=mcl.numpy().astype(np.uint8),
+               maskclip_lo=mcl_lo.numpy().astype(np.uint8), maskclip_all=mcl_all.numpy().astype(np.uint8), maskclip_lo_thresh=np.float64(th_lo))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "classes used", np.unique(out["maskclip_all"]).tolist(), "valid at lo", float((out["maskclip_lo"] != 255).mean()))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--only-new" in sys.argv:                            # round-2 additions only (the older files regenerate bit-identically)
+        torch.manual_seed(0)
+        torch.set_num_threads(8)
+        fp_fixture()
+        concept_fixture("maskclip_concept4_voc_c64_b2", "pascal", 21, "concept4_single")
+        concept_fixture("maskclip_concept3_city_c64_b2", "cityscapes", 19, "concept3_single")
+        return
     torch.manual_seed(0)
     torch.set_num_threads(8)
     forward_fixture("fwd_c64_b2", 64, 2, seed=11)          # tiny: every op, multiple of 16
@@ -313,6 +376,9 @@ def main():
     eval_fixture()
     input_fixture()
     head_conv_fixture()
+    fp_fixture()
+    concept_fixture("maskclip_concept4_voc_c64_b2", "pascal", 21, "concept4_single")
+    concept_fixture("maskclip_concept3_city_c64_b2", "cityscapes", 19, "concept3_single")
 
 
 if __name__ == "__main__":

@@ -11,8 +11,8 @@ PINNING: the reference ships no tests or golden vectors, s
 this oracle is pinned against outputs of the unmodified reference itself, run in
 the authoring container through oracle/ref_shim.py; the vectors are committed
 under tests/golden/ by oracle/make_golden.py (tests/test_oracle_golden.py checks
-them on every run; tests/test_oracle_vs_reference.py re-runs the live
-comparison whenever /root/reference is present).
+them on every run; `python -m oracle.make_golden` regenerates them from
+/root/reference in the authoring container).
 
 Nothing under semivl_b200/ may import this module.
 """

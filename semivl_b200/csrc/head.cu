@@ -29,17 +29,48 @@ __device__ __forceinline__ void gn_range(int hw, int splits, int split, int& p0,
   p1 = p0 + per < hw ? p0 + per : hw;
 }
 
-__global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, float* __restrict__ sum, float* __restrict__ sq, int hw, int C, int G,
-                int splits) {
-  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
-  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
-  const int vpp = C / 8, cpg = C / G, ppi = kGnThreads / vpp;      // pixels per iteration
-  if (threadIdx.x < kMaxGroups) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
+// Fixed-order reduction of the per-thread (a, b) partials of a statistics CTA to per-group sums.  Thread t owns channel vector
+// t % vpp (8 channels, two vectors per 16-channel group) of pixel slot t / vpp.  Lanes of one group inside a warp are combined
+// by an xor-shuffle tree (bit 0 = the vector pair, bits >= log2(vpp) = pixel slots), the warps by one thread per group in
+// warp order: the result does not depend on scheduling, so the statistics -- and with them every bf16 rounding downstream --
+// are bit-reproducible from run to run (no fp32 atomics; profiles/r01_determinism.md).
+__device__ __forceinline__ void gn_block_reduce2(float a, float b, int vpp, int G, float* s_part /* [2][8][kMaxGroups] */, float& ra, float& rb,
+                                                 bool pair = true) {
+  // pair == false: thread t owns all 16 channels of group t % vpp (vpp = G lanes per pixel slot), no vector pair to combine
+  if (pair) {
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+  }
+  for (int o = vpp; o < 32; o <<= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // vpp <= 32: a warp covers groups [0, vpp/2) (vpp == 32: all 16) -- with vpp > 32 excluded by the C <= 256 check
+  if (lane < vpp && (!pair || (lane & 1) == 0)) {
+    const int gi = pair ? lane >> 1 : lane;
+    s_part[(0 * 8 + warp) * kMaxGroups + gi] = a;
+    s_part[(1 * 8 + warp) * kMaxGroups + gi] = b;
+  }
   __syncthreads();
+  ra = rb = 0.f;
+  if (threadIdx.x < G) {
+#pragma unroll
+    for (int w = 0; w < kGnThreads / 32; ++w) {
+      ra += s_part[(0 * 8 + w) * kMaxGroups + threadIdx.x];
+      rb += s_part[(1 * 8 + w) * kMaxGroups + threadIdx.x];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, float* __restrict__ part, int hw, int C, int G, int splits) {
+  __shared__ float s_part[2 * 8 * kMaxGroups];
+  const int map = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int vpp = C / 8, ppi = kGnThreads / vpp;      // pixels per iteration
   int p0, p1;
   gn_range(hw, splits, split, p0, p1);
-  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / cpg;
+  const int c8 = (threadIdx.x % vpp) * 8;
   const int64_t xbase = (int64_t)map * hw * ldx + c8;
   float pa = 0.f, pb = 0.f;
   for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 4 * ppi) {
@@ -58,21 +89,44 @@ gn_stats_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, float* __r
       for (int i = 0; i < 8; ++i) { pa += f[u][i]; pb += f[u][i] * f[u][i]; }
     }
   }
-  atomicAdd(&s_sum[g], pa);
-  atomicAdd(&s_sq[g], pb);
-  __syncthreads();
-  if (threadIdx.x < G) {
-    atomicAdd(sum + (int64_t)map * G + threadIdx.x, s_sum[threadIdx.x]);
-    atomicAdd(sq + (int64_t)map * G + threadIdx.x, s_sq[threadIdx.x]);
+  float ra, rb;
+  gn_block_reduce2(pa, pb, vpp, G, s_part, ra, rb);
+  if (threadIdx.x < G) {                                 // partial of this (map, split): reduced in split order by gn_finalize_kernel
+    part[((int64_t)blockIdx.x * G + threadIdx.x) * 2] = ra;
+    part[((int64_t)blockIdx.x * G + threadIdx.x) * 2 + 1] = rb;
   }
 }
-__global__ void gn_finalize_kernel(float* __restrict__ mean, float* __restrict__ rstd, int64_t n, float count, float eps) {
+// second stage: the `splits` partials of a (map, group) are summed in split order
+__global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd, int64_t maps, int G, int splits,
+                                   float count, float eps) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float mu = mean[i] / count;
-  const float var = fmaxf(rstd[i] / count - mu * mu, 0.f);
+  if (i >= maps * G) return;
+  const int64_t map = i / G;
+  const int g = (int)(i % G);
+  float a = 0.f, b = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 v = *(const float2*)(part + (((map * splits + s) * G) + g) * 2);
+    a += v.x;
+    b += v.y;
+  }
+  const float mu = a / count;
+  const float var = fmaxf(b / count - mu * mu, 0.f);
   mean[i] = mu;
   rstd[i] = rsqrtf(var + eps);
+}
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ ws, int64_t maps, int G, int splits) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= maps * G) return;
+  const int64_t map = i / G;
+  const int g = (int)(i % G);
+  float a = 0.f, b = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 v = *(const float2*)(part + (((map * splits + s) * G) + g) * 2);
+    a += v.x;
+    b += v.y;
+  }
+  ws[i * 2] = a;
+  ws[i * 2 + 1] = b;
 }
 // apply: one thread = the 16 channels of one (pixel, group) -- every GroupNorm of the head has 16 channels per group -- i.e. two
 // 16-byte vectors in flight per thread at ~40 registers, flat grid-stride indexing for full occupancy.
@@ -117,11 +171,10 @@ gn_bwd_stats_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, con
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ rstd, float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int hw,
                     int C, int G, int splits) {
-  __shared__ float s_s1[kMaxGroups], s_s2[kMaxGroups];
+  __shared__ float s_part[2 * 8 * kMaxGroups];
   __shared__ float s_dg[256], s_db[256];
   const int map = blockIdx.x / splits, split = blockIdx.x % splits;
   const int ppi = kGnThreads / G;                     // pixels per iteration
-  if (threadIdx.x < kMaxGroups) s_s1[threadIdx.x] = s_s2[threadIdx.x] = 0.f;
   s_dg[threadIdx.x] = s_db[threadIdx.x] = 0.f;
   __syncthreads();
   int p0, p1;
@@ -151,14 +204,13 @@ gn_bwd_stats_kernel(const void* __restrict__ dy, int dy_dtype, int64_t lddy, con
       s2 += gg * xh;
     }
   }
-  atomicAdd(&s_s1[g], s1);
-  atomicAdd(&s_s2[g], s2);
 #pragma unroll
   for (int i = 0; i < 16; ++i) { atomicAdd(&s_dg[c0 + i], dg[i]); atomicAdd(&s_db[c0 + i], db[i]); }
-  __syncthreads();
-  if (threadIdx.x < G) {
-    atomicAdd(ws + ((int64_t)map * G + threadIdx.x) * 2, s_s1[threadIdx.x]);
-    atomicAdd(ws + ((int64_t)map * G + threadIdx.x) * 2 + 1, s_s2[threadIdx.x]);
+  float ra, rb;
+  gn_block_reduce2(s1, s2, G, G, s_part, ra, rb, false);           // (contains the __syncthreads that also publishes s_dg / s_db)
+  if (threadIdx.x < G) {                                           // partial of this (map, split), reduced in split order by gn_bwd_finalize_kernel
+    ws[((int64_t)blockIdx.x * G + threadIdx.x) * 2] = ra;
+    ws[((int64_t)blockIdx.x * G + threadIdx.x) * 2 + 1] = rb;
   }
   if (threadIdx.x < C && dgamma) {
     atomicAdd(dgamma + threadIdx.x, s_dg[threadIdx.x]);
@@ -213,16 +265,13 @@ __device__ __forceinline__ void ldg8f(const float* p, float* f) {
 }
 
 __global__ void __launch_bounds__(kGnThreads)
-gn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ sum, float* __restrict__ sq, int hw, int C, int G,
-                     int splits) {
-  __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
+gn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ part, int hw, int C, int G, int splits) {
+  __shared__ float s_part[2 * 8 * kMaxGroups];
   const int map = blockIdx.x / splits, split = blockIdx.x % splits;
   const int vpp = C / 8, ppi = kGnThreads / vpp;
-  if (threadIdx.x < kMaxGroups) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
-  __syncthreads();
   int p0, p1;
   gn_range(hw, splits, split, p0, p1);
-  const int c8 = (threadIdx.x % vpp) * 8, g = c8 / (C / G);
+  const int c8 = (threadIdx.x % vpp) * 8;
   const __nv_bfloat16* xb = x + (int64_t)map * hw * ldx + c8;
   float pa = 0.f, pb = 0.f;
   for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 4 * ppi) {
@@ -242,12 +291,11 @@ gn_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __
       }
     }
   }
-  atomicAdd(&s_sum[g], pa);
-  atomicAdd(&s_sq[g], pb);
-  __syncthreads();
-  if (threadIdx.x < G) {
-    atomicAdd(sum + (int64_t)map * G + threadIdx.x, s_sum[threadIdx.x]);
-    atomicAdd(sq + (int64_t)map * G + threadIdx.x, s_sq[threadIdx.x]);
+  float ra, rb;
+  gn_block_reduce2(pa, pb, vpp, G, s_part, ra, rb);
+  if (threadIdx.x < G) {                                 // partial of this (map, split): reduced in split order by gn_finalize_kernel
+    part[((int64_t)blockIdx.x * G + threadIdx.x) * 2] = ra;
+    part[((int64_t)blockIdx.x * G + threadIdx.x) * 2 + 1] = rb;
   }
 }
 
@@ -360,8 +408,8 @@ gn_bwd_stats_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, con
     float a = 0.f, b = 0.f;
     for (int ps = 0; ps < ppi; ++ps)
       for (int vv = v0; vv < v1; ++vv) { a += part[16][ps * vpp + vv]; b += part[17][ps * vpp + vv]; }
-    atomicAdd(ws + ((int64_t)map * G + gg) * 2, a);
-    atomicAdd(ws + ((int64_t)map * G + gg) * 2 + 1, b);
+    ws[((int64_t)blockIdx.x * G + gg) * 2] = a;               // partial of this (map, split): gn_bwd_finalize_kernel sums them in split order
+    ws[((int64_t)blockIdx.x * G + gg) * 2 + 1] = b;
   }
 }
 
@@ -571,11 +619,10 @@ inline int gn_splits(int64_t maps, int hw, int C) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("SVL_GN_SPLITS"); forced = e ? atoi(e) : 0; }
   if (forced > 0) return forced;
-  // many more CTAs than resident slots (no half-empty last wave), but at least ~16 pixel iterations per thread
-  int64_t want = (148 * 16 + maps - 1) / maps;
-  int64_t cap = (int64_t)hw * (C / 16) / (kGnThreads * 16);
-  if (cap < 1) cap = 1;
-  int64_t s = want < cap ? want : cap;
+  // ~16 pixel iterations per thread.  The split count depends on the map geometry only -- never on the number of maps -- so the
+  // order of the partial sums, and with it every statistic, is independent of the batch an image is processed in.
+  (void)maps;
+  int64_t s = (int64_t)hw * (C / 16) / (kGnThreads * 16);
   return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));
 }
 
@@ -1269,28 +1316,32 @@ conv_out1_wgrad_bf16_kernel(const float* __restrict__ dout, const __nv_bfloat16*
 using namespace svl;
 #define ST (cudaStream_t) stream
 
+// floats of scratch the GroupNorm entry points need: [maps, G, 2] totals + [maps * splits, G, 2] per-CTA partials
+extern "C" size_t svl_gn_workspace(int64_t maps, int hw, int C, int G) {
+  if (maps <= 0 || G <= 0) return 0;
+  return (size_t)(2 * maps * G * (1 + (int64_t)gn_splits(maps, hw, C)));
+}
+
 extern "C" int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
-                               int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, int64_t maps, int hw, int C,
-                               int G, float eps, void* stream) {
-  SVL_CHECK_ARG(x && gamma && beta && out && mean && rstd, "svl_gn_relu_fwd: null pointer (mean/rstd double as the statistics workspace)");
+                               int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, float* ws, int64_t maps,
+                               int hw, int C, int G, float eps, void* stream) {
+  SVL_CHECK_ARG(x && gamma && beta && out && mean && rstd && ws, "svl_gn_relu_fwd: null pointer");
   SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
                 "svl_gn_relu_fwd: unsupported C=%d G=%d", C, G);
   if (maps == 0) return SVL_OK;
   const int splits = gn_splits(maps, hw, C);
   SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_fwd: grid too large");
-  SVL_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * maps * G, ST));
-  SVL_CUDA(cudaMemsetAsync(rstd, 0, sizeof(float) * maps * G, ST));
   // all-bf16 fast path (every large GroupNorm of the throughput mode); anything else takes the generic kernels
   const int vshift = log2_exact(C / 8);
   const bool fast = x_dtype == SVL_BF16 && out_dtype == SVL_BF16 && (!res || res_dtype == SVL_BF16) && al16(x) && al16(out) && al16(res) &&
                     ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldres % 8 == 0) && vshift >= 0 && maps <= 65535 && C / G == 16 &&
                     (int64_t)hw * (C / 8) < (1ll << 30);
   if (fast)
-    gn_stats_bf16_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>((const __nv_bfloat16*)x, ldx, mean, rstd, hw, C, G, splits);
+    gn_stats_bf16_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>((const __nv_bfloat16*)x, ldx, ws, hw, C, G, splits);
   else
-    gn_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, mean, rstd, hw, C, G, splits);
+    gn_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, ws, hw, C, G, splits);
   SVL_LAUNCH_CHECK();
-  gn_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(mean, rstd, maps * G, (float)hw * (C / G), eps);
+  gn_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(ws, mean, rstd, maps, G, splits, (float)hw * (C / G), eps);
   SVL_LAUNCH_CHECK();
   SVL_CHECK_ARG(C / G == 16, "svl_gn_relu_fwd: the apply kernel is specialised for 16 channels per group");
   if (fast) {
@@ -1315,13 +1366,15 @@ extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const
   if (maps == 0) return SVL_OK;
   const int splits = gn_splits(maps, hw, C);
   SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_bwd: grid too large");
-  SVL_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * maps * G * 2, ST));
+  float* part = ws + maps * G * 2;                      // [maps * splits, G, 2] partials behind the [maps, G, 2] totals
   const int vshift = log2_exact(C / 8);
   const bool fast = dy_dtype == SVL_BF16 && x_dtype == SVL_BF16 && dx_dtype == SVL_BF16 && al16(dy) && al16(x) && al16(dx) && lddy % 8 == 0 &&
                     ldx % 8 == 0 && lddx % 8 == 0 && vshift >= 0 && maps <= 65535 && (int64_t)hw * (C / 8) < (1ll << 30);
   if (fast) {
     gn_bwd_stats_bf16_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, gamma,
-                                                                              beta, mean, rstd, ws, dgamma, dbeta, hw, C, G, splits);
+                                                                              beta, mean, rstd, part, dgamma, dbeta, hw, C, G, splits);
+    SVL_LAUNCH_CHECK();
+    gn_bwd_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(part, ws, maps, G, splits);
     SVL_LAUNCH_CHECK();
     const dim3 grid((unsigned)cdiv((int64_t)hw * (C / 8), 256 * kGnBwdApplyU), (unsigned)maps);
     gn_bwd_apply_bf16_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, gamma, beta, mean, rstd, ws,
@@ -1329,8 +1382,10 @@ extern "C" int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const
     SVL_LAUNCH_CHECK();
     return SVL_OK;
   }
-  gn_bwd_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dgamma,
+  gn_bwd_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, part, dgamma,
                                                                        dbeta, hw, C, G, splits);
+  SVL_LAUNCH_CHECK();
+  gn_bwd_finalize_kernel<<<(unsigned)((maps * G + 255) / 256), 256, 0, ST>>>(part, ws, maps, G, splits);
   SVL_LAUNCH_CHECK();
   gn_bwd_apply_kernel<<<ew_grid(maps * hw * G, 256), 256, 0, ST>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, gamma, beta, mean, rstd, ws, dx, dx_dtype, lddx,
                                                                   maps, hw, C, G);

@@ -66,6 +66,8 @@ _lib.svl_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
 
 _lib.svl_attention_bwd_workspace.restype = C.c_size_t
 _lib.svl_attention_bwd_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+_lib.svl_gn_workspace.restype = C.c_size_t
+_lib.svl_gn_workspace.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
 _lib.svl_wgrad.restype = C.c_int
 _lib.svl_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
 
@@ -81,7 +83,7 @@ _PROTOS = {
     "svl_colsum": [_P, _I, _L, _L, _I, _P, _P],
     "svl_batch_sum": [_P, _P, _I, _L, _I, _P],
     "svl_axpy": [_P, _P, _F, _L, _P],
-    "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _L, _I, _I, _I, _F, _P],
+    "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _F, _P],
     "svl_gn_relu_bwd": [_P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P],
     "svl_sim_im2col": [_P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "svl_sim_col2im": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],

@@ -266,11 +266,12 @@ def attention_bwd(qkv, out, dout, lse, b, seq, heads, precise, dv_add=None, dv_a
 def gn_relu_fwd(x, x_dtype, gamma, beta, out, out_dtype, maps, hw, C, G, *, ldx=None, ldo=None, out_col0=0, res=None, res_dtype=L.BF16,
                 ldres=None, save_stats=True, eps=1e-5):
     dev = x.device
-    mean = torch.empty(maps, G, device=dev, dtype=torch.float32)        # also the reduction workspace of the kernel
+    mean = torch.empty(maps, G, device=dev, dtype=torch.float32)
     rstd = torch.empty(maps, G, device=dev, dtype=torch.float32)
+    ws = torch.empty(L.lib().svl_gn_workspace(maps, hw, C, G), device=dev, dtype=torch.float32)     # fixed-order partial sums
     L.call("svl_gn_relu_fwd", x, x_dtype, ldx if ldx is not None else x.shape[-1], gamma, beta,
            out.data_ptr() + out_col0 * out.element_size(), out_dtype, ldo if ldo is not None else out.shape[-1],
-           res, res_dtype, (ldres if ldres is not None else (res.shape[-1] if res is not None else 0)), mean, rstd, maps, hw, C, G, eps,
+           res, res_dtype, (ldres if ldres is not None else (res.shape[-1] if res is not None else 0)), mean, rstd, ws, maps, hw, C, G, eps,
            n_launch=3)
     return mean, rstd
 
@@ -279,6 +280,6 @@ def gn_relu_bwd(dy, dy_dtype, x, x_dtype, gamma, beta, mean, rstd, dx, dx_dtype,
                 ldx=None, lddx=None):
     L.call("svl_gn_relu_bwd", dy.data_ptr() + dy_col0 * dy.element_size(), dy_dtype, lddy if lddy is not None else dy.shape[-1],
            x, x_dtype, ldx if ldx is not None else x.shape[-1], gamma, beta, mean, rstd, dx, dx_dtype,
-           lddx if lddx is not None else dx.shape[-1], dgamma, dbeta, torch.empty(maps * G * 2, device=dx.device, dtype=torch.float32),
-           maps, hw, C, G, n_launch=2)
+           lddx if lddx is not None else dx.shape[-1], dgamma, dbeta,
+           torch.empty(L.lib().svl_gn_workspace(maps, hw, C, G), device=dx.device, dtype=torch.float32), maps, hw, C, G, n_launch=3)
     return dx

@@ -104,6 +104,10 @@ class Trainer:
                 p.data = self.p_flat[off:off + k].view(p.shape)            # parameters become views of the flat buffer
                 gd[name] = self.g_flat[off:off + k].view(p.shape)
                 off += k
+        if _world() > 1:
+            # DDP broadcasts rank 0's module state at construction (semivl.py:139-140): replicas must start from the same parameters
+            # whatever each rank's RNG produced for the randomly initialised head; the Adam moments are zeros on every rank already
+            dist.broadcast(self.p_flat, src=0)
         self.vit, self.head = model.backbone.engine, model.decode_head.engine
         self.vit.cache.volatile = set(self.g_bb)
         self.head.cache.volatile = set(self.g_hd)

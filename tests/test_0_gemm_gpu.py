@@ -251,7 +251,7 @@ def test_optin_launch_modes_subprocess(env):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gemm_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
                         "plain_gemm or epilogue or ffn_epilogues or wgrad_linear"], env=dict(os.environ, **env), cwd=root, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -192,6 +192,8 @@ def test_gradients_are_additive_over_the_batch(text_dir):
     tr = Trainer(m, OptimCfg())
     tr.supervised_step(img, mask, update=False)
     g_full = tr.g_flat.clone()
+    tr.supervised_step(img, mask, update=False)
+    g_again = tr.g_flat.clone()
     tr.supervised_step(img[:2].contiguous(), mask[:2].contiguous(), update=False)
     g_a = tr.g_flat.clone()
     tr.supervised_step(img[2:].contiguous(), mask[2:].contiguous(), update=False)
@@ -199,6 +201,10 @@ def test_gradients_are_additive_over_the_batch(text_dir):
     na, nb = (mask[:2] != 255).sum().item(), (mask[2:] != 255).sum().item()
     assert na == nb
     want = 0.5 * (g_a + g_b)
+    # The forward pass is bit-identical per image whatever batch it sits in (fixed-order GroupNorm statistics whose split count does not
+    # depend on the number of maps; row-independent GEMM tiles), so the only differences left are the fp32 `red.global.add` orders of the
+    # weight-gradient / bias-sum reductions: calibrate on two runs of the SAME batch and bound additivity at 3x that floor.
+    floor = (g_full - g_again).norm().item() / g_full.norm().item()
     err = (g_full - want).norm().item() / g_full.norm().item()
-    print("batch additivity of the gradient: rel", err)
-    assert err < 2e-3
+    print(f"batch additivity of the gradient: rel {err:.3e} (same-batch run-to-run floor {floor:.3e})")
+    assert err <= max(3 * floor, 2e-5)

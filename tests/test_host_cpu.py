@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built):
     assert not missing, missing
     from semivl_b200 import lib as L
     assert L.version() == 100
-    bound = set(L._PROTOS) | {"svl_gemm", "svl_wgrad", "svl_last_error", "svl_version", "svl_check_device", "svl_attention_bwd_workspace"}
+    bound = set(L._PROTOS) | {"svl_gemm", "svl_wgrad", "svl_last_error", "svl_version", "svl_check_device", "svl_attention_bwd_workspace", "svl_gn_workspace"}
     assert names == bound, (names - bound, bound - names)
 
 
@@ -321,3 +321,40 @@ def test_trainer_exchange_schedule_covers_the_flat_buffer(built):
     assert covered + rest == n
     # every trainable backbone tensor is an attention or position-embedding tensor (vlm.py:80-88 freeze filter)
     assert all(("attn" in k) or ("pos_embed" in k) for k in tr.g_bb)
+
+
+def _bcast_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semivl_b200.model import build_model
+    from semivl_b200.train import OptimCfg, Trainer
+    torch.manual_seed(1000 + rank)                           # ranks deliberately initialise the random head differently
+    cfg = dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=21, crop_size=64, dataset='pascal', text_embedding_variant='single',
+               mcc_text='single', pl_text='single', clip_encoder=None, disable_dropout=True, fp_rate=0.5, model_args=dict(pretrained=None), precise=False)
+    model = build_model(cfg)
+    before = torch.cat([p.detach().reshape(-1) for p in model.decode_head.parameters()]).clone()
+    tr = Trainer(model, OptimCfg())
+    idx = torch.randint(0, tr.p_flat.numel(), (4096,), generator=torch.Generator().manual_seed(5))
+    digest = tr.p_flat[idx].tolist() + [tr.p_flat.double().sum().item(), tr.p_flat[tr.n_bb:].double().abs().sum().item()]
+    q.put((rank, before[:64].tolist(), digest, model.decode_head.conv1.weight.detach().reshape(-1)[:16].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_broadcasts_initial_parameters_gloo_world2(built):
+    """DDP broadcasts rank 0's parameters at construction (semivl.py:139-140): two ranks seeded differently must leave Trainer.__init__ with
+    identical flat parameter buffers (= rank 0's), and the module parameters must be views of that buffer."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: rest for r, *rest in (q.get(timeout=240) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][0] != res[1][0], "the two ranks were meant to start from different random heads"
+    assert res[0][1] == res[1][1]                 # sampled entries + sums of the flat parameter buffer
+    assert res[0][2] == res[1][2]                 # the module parameters are views of the (broadcast) flat buffer

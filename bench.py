@@ -3,11 +3,15 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N > 1: launched by torch.distributed.run)
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU PyTorch path (oracle port) on the host cores
+  python bench.py --config {2,3,4,5}                       # the other BASELINE.json configurations (per-GPU batch of that config)
 
-Workload (BASELINE.json configs[1]): VOC 21-class synthetic, 512x512, ViT-B/16 + VLG head, per-GPU batch 16, one supervised
+Default workload (BASELINE.json configs[1]): VOC 21-class synthetic, 512x512, ViT-B/16 + VLG head, per-GPU batch 16, one supervised
 training step = encoder fwd -> head fwd -> fused upsample+CE -> head bwd -> encoder bwd -> (NCCL grad all-reduce) -> AdamW.
-`--workload semivl` times the full SemiVL consistency step (teacher + MaskCLIP + 5-way student head) instead.
-Prints ONE JSON line (rank 0).
+Configs 4 / 5 time the full SemiVL consistency step (teacher + MaskCLIP + 5-way student head).  Prints ONE JSON line (rank 0).
+
+Inputs are synthetic uint8 images / labels (what a data loader delivers); the device-timed `value` runs on their normalised fp32 form
+resident in HBM, the `e2e` number uploads the uint8 bytes from pinned host memory every step and runs the input-stage kernels
+(svl_crop_flip_normalize / svl_crop_flip_mask / svl_cutmix_box) inside the timed region.
 """
 import argparse
 import json
@@ -20,56 +24,139 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CROP, NCLASS, BATCH = 512, 21, 16
-# algorithmic GFLOP per image of the supervised step at 512^2 / N=21 (FlopCounterMode on the reference: matmul+conv, 2*MAC)
-GF_PER_IMG_SUPERVISED = 831.5
-GF_PER_UNIT_SEMIVL = 4542.0
+# BASELINE.json configs[1..4]: per-GPU batch, step shape, algorithmic GFLOP per labelled image of the step
+# (FlopCounterMode on the reference, matmul + conv, 2*MAC; the SemiVL figures leave out the head pass on the perturbed LABELLED
+# images, which the reference computes and discards, semivl.py:247: 12 631 - 1 485.9 and 14 180 - 1 312.4)
+CONFIGS = {
+    2: dict(name="VOC 21-class synthetic 512x512", dataset="pascal", nclass=21, crop=512, batch=16, workload="supervised", gf_per_img=831.5),
+    3: dict(name="Cityscapes 19-class synthetic 801x801", dataset="cityscapes", nclass=19, crop=801, batch=2, workload="supervised", gf_per_img=2487.5),
+    4: dict(name="ADE20K 150-class synthetic 512x512", dataset="ade", nclass=150, crop=512, batch=8, workload="semivl", gf_per_img=11145.1),
+    5: dict(name="COCO 81-class synthetic 641x641", dataset="coco", nclass=81, crop=641, batch=16, workload="semivl", gf_per_img=12867.6),
+}
+GF_PER_UNIT_SEMIVL_VOC = 4542.0 - 208.7
+DATASET_OF = {21: "pascal", 19: "cityscapes", 150: "ade", 81: "coco"}
+TEXT_OF = {"pascal": "voc12_wbg_single", "cityscapes": "cityscapes_single", "ade": "ade_single", "coco": "coco_single"}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="supervised", choices=["supervised", "semivl"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--crop", type=int, default=CROP)
-    ap.add_argument("--nclass", type=int, default=NCLASS)
-    ap.add_argument("--precise", action="store_true", help="split-bf16 parity mode instead of the bf16 throughput mode")
-    ap.add_argument("--graph-multi", action="store_true", help="N > 1: capture the step (NCCL exchange included) in a CUDA graph as well")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--workload", default=None, choices=["supervised", "semivl"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--crop", type=int, default=None)
+    ap.add_argument("--nclass", type=int, default=None)
+    ap.add_argument("--precise", action="store_true", help="time the split-bf16 parity mode as the main number instead of the bf16 throughput mode")
+    ap.add_argument("--no-precise-leg", action="store_true", help="skip the second timed leg in the parity mode (N=1, config 2 only)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run logit parity check against the CPU oracle")
+    ap.add_argument("--no-graph-multi", action="store_true", help="N > 1: launch eagerly instead of replaying the captured step (NCCL exchange included)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch the ~690 kernels of the step eagerly instead of replaying the captured CUDA graph (N=1)")
-    ap.add_argument("--cpu-crop", type=int, default=CROP)
-    return ap.parse_args()
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels of the step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--cpu-crop", type=int, default=None)
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.workload = a.workload or c["workload"]
+    a.batch = a.batch or c["batch"]
+    a.crop = a.crop or c["crop"]
+    a.nclass = a.nclass or c["nclass"]
+    a.dataset = DATASET_OF.get(a.nclass, c["dataset"])
+    a.cpu_crop = a.cpu_crop or a.crop
+    custom = (a.workload, a.batch, a.crop, a.nclass) != (c["workload"], c["batch"], c["crop"], c["nclass"])
+    a.gf_per_img = c["gf_per_img"] if not custom else (GF_PER_UNIT_SEMIVL_VOC if (a.workload == "semivl" and a.nclass == 21 and a.crop == 512) else
+                                                      (c["gf_per_img"] if (a.workload, a.crop, a.nclass) == (c["workload"], c["crop"], c["nclass"]) else None))
+    a.name = c["name"] if not custom else f"{a.dataset} {a.nclass}-class synthetic {a.crop}x{a.crop}"
+    return a
 
 
-def model_cfg(crop, nclass, precise):
-    return dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=nclass, crop_size=crop, dataset='pascal' if nclass == 21 else 'ade',
+def model_cfg(args, precise):
+    return dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=args.nclass, crop_size=args.crop, dataset=args.dataset,
                 text_embedding_variant='single', mcc_text='single', pl_text='single', clip_encoder='mcvit16', disable_dropout=True,
                 fp_rate=0.5, model_args=dict(pretrained=None), clip_encoder_args=dict(pretrained=None), precise=precise)
 
 
-def synth_batch(torch, b, crop, nclass, seed, device, semivl):
-    """Synthetic inputs of SURVEY.md §8d: randn images, labels with a 5% ignore region, pad-strip ignore masks, CutMix boxes."""
+# ------------------------------------------------------------------------------------------------ synthetic inputs
+def synth_host_u8(torch, b, crop, nclass, seed, semivl, pin):
+    """What a data loader hands over (SURVEY.md §8d shapes): uint8 HWC images, uint8 label maps with a ~5% ignore region (255), and -- for
+    the SemiVL step -- uint8 pad maps of the unlabelled samples (254 where padded, semi.py:74,99-103) plus CutMix box geometry (ints)."""
     g = torch.Generator().manual_seed(seed)
-    r = lambda: torch.randn(b, 3, crop, crop, generator=g)
-    mask = torch.randint(0, nclass, (b, crop, crop), generator=g)
+    r = lambda: torch.randint(0, 256, (b, crop, crop, 3), generator=g, dtype=torch.uint8)
+    mask = torch.randint(0, nclass, (b, crop, crop), generator=g, dtype=torch.uint8)
     mask[:, : crop // 5, : crop // 4] = 255
     out = dict(img_x=r(), mask_x=mask)
+    boxes = None
     if semivl:
         for k in ("img_w", "img_s1", "img_s2", "img_w_other", "img_s1_other", "img_s2_other"):
             out[k] = r()
-        ign = torch.zeros(b, crop, crop, dtype=torch.long)
-        ign[:, -crop // 10:, :] = 255
-        ign_o = torch.zeros(b, crop, crop, dtype=torch.long)
-        ign_o[:, :, -crop // 12:] = 255
-        def box(frac):
+        pad = torch.zeros(b, crop, crop, dtype=torch.uint8)
+        pad[:, -crop // 10:, :] = 254
+        pad_o = torch.zeros(b, crop, crop, dtype=torch.uint8)
+        pad_o[:, :, -crop // 12:] = 254
+        out.update(pad=pad, pad_other=pad_o)
+        h1, h2 = int(crop * 0.5), int(crop * 0.3)
+        boxes = dict(mix1=[(crop // 4, crop // 5, h1, h1) if i % 2 == 0 else None for i in range(b)],
+                     mix2=[(crop // 4, crop // 5, h2, h2) if i % 2 == 0 else None for i in range(b)])
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out, boxes
+
+
+def device_batch(torch, ip, u8, boxes, crop, out=None):
+    """uint8 device tensors -> the step's inputs with the repo's input-stage kernels: ToTensor + Normalize (transform.py:30-41), label /
+    ignore-mask conversion (semi.py:99-103), CutMix boxes (transform.py:66-84).  No crop offset / flip here: the synthetic sources already
+    have the crop size."""
+    dev = u8["img_x"].device
+    b = u8["img_x"].shape[0]
+    out = out if out is not None else {}
+    for k, v in u8.items():
+        if k.startswith("img"):
+            dst = out.get(k)
+            if dst is None:
+                dst = out[k] = torch.empty(b, 3, crop, crop, device=dev, dtype=torch.float32)
+            for i in range(b):
+                ip.crop_flip_normalize(v[i], crop, 0, 0, False, out=dst[i])
+    from semivl_b200 import lib as L
+    def conv_mask(src, key, labels):
+        dst = out.get(key)
+        if dst is None:
+            dst = out[key] = torch.empty(b, crop, crop, device=dev, dtype=torch.int64)
+        for i in range(b):
+            L.call("svl_crop_flip_mask", src[i], crop, crop, dst[i] if labels else None, None if labels else dst[i], crop, 0, 0, 0, 255)
+    conv_mask(u8["mask_x"], "mask_x", True)
+    if boxes is not None:
+        conv_mask(u8["pad"], "ignore_mask", False)
+        conv_mask(u8["pad_other"], "ignore_mask_other", False)
+        for key in ("mix1", "mix2"):
+            dst = out.get(key)
+            if dst is None:
+                dst = out[key] = torch.empty(b, crop, crop, device=dev, dtype=torch.float32)
+            for i in range(b):
+                ip.cutmix_box(crop, boxes[key][i], out=dst[i])
+    return out
+
+
+def synth_batch(torch, b, crop, nclass, seed, device, semivl):
+    """fp32 / int64 host tensors of the same synthetic sample (CPU reference arm, scratch scripts)."""
+    u8, boxes = synth_host_u8(torch, b, crop, nclass, seed, semivl, False)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    out = {}
+    for k, v in u8.items():
+        if k.startswith("img"):
+            out[k] = (v.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    out["mask_x"] = u8["mask_x"].long()
+    if semivl:
+        out["ignore_mask"] = (u8["pad"] == 254).long() * 255
+        out["ignore_mask_other"] = (u8["pad_other"] == 254).long() * 255
+        for key in ("mix1", "mix2"):
             m = torch.zeros(b, crop, crop)
-            h = int(crop * frac)
-            m[::2, crop // 5: crop // 5 + h, crop // 4: crop // 4 + h] = 1
-            return m
-        out.update(ignore_mask=ign, ignore_mask_other=ign_o, mix1=box(0.5), mix2=box(0.3))
+            for i, bx in enumerate(boxes[key]):
+                if bx is not None:
+                    x, y, w, h = bx
+                    m[i, y:y + h, x:x + w] = 1
+            out[key] = m
     return {k: (v.pin_memory() if device != "cpu" else v) for k, v in out.items()}
 
 
@@ -103,19 +190,18 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None), "reasons": reasons}
 
 
+# ------------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_rate(args, steps, warmup, crop, b=1):
-    """The reference's CPU PyTorch path (oracle port, fp32) on the host cores: supervised step fwd + CE + bwd at batch b."""
+    """The reference's CPU PyTorch path (oracle port, fp32) on the host cores: supervised step fwd + CE + bwd + AdamW at batch b."""
     import numpy as np
     import torch
-    import torch.nn.functional as F
     from oracle import semivl_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     mc = O.ModelCfg(img_size=crop, num_classes=args.nclass)
     sd = O.fixture_state_dict(O.param_shapes(mc, with_clip_encoder=False), seed=0)
     p = {k: v.clone().requires_grad_(("attn" in k or "pos_embed" in k) if k.startswith("backbone.") else True) for k, v in sd.items()}
-    tname = "voc12_wbg_single" if args.nclass == 21 else "ade_single"
-    text = torch.from_numpy(np.load(os.path.join(ROOT, "semivl_b200", "configs", "_base_", "datasets", "text_embedding", tname + ".npy")))
+    text = torch.from_numpy(np.load(os.path.join(ROOT, "semivl_b200", "configs", "_base_", "datasets", "text_embedding", TEXT_OF[args.dataset] + ".npy")))
     batch = synth_batch(torch, b, crop, args.nclass, 1234, "cpu", False)
     # the reference's optimizer (experiments.py:246-255 via mmcv's constructor): torch.optim.AdamW, backbone lr x0.01, head lr x10
     train = {k: v for k, v in p.items() if v.requires_grad}
@@ -139,16 +225,50 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 16)), max(1, min(args.warmup, 2))        # ~0.7 s per CPU step at 512^2: bounded to ~12 s
+    per_step_s = 0.7 * (args.cpu_crop / 512.0) ** 2 * max(1.0, args.nclass / 21.0 * 0.4 + 0.6)         # rough: bounds the run to ~15 s
+    steps = max(1, min(args.steps, int(12 / per_step_s) or 1))
+    warmup = max(1, min(args.warmup, 2))
     value, ms, cores = cpu_reference_rate(args, steps, warmup, args.cpu_crop)
     sample = f"supervised step fwd+CE+bwd+AdamW at batch 1, {args.cpu_crop}x{args.cpu_crop}, N={args.nclass}, {steps} timed steps after {warmup} warm-up"
     line = {"impl": "reference", "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": f"VOC {args.nclass}-class synthetic {args.cpu_crop}x{args.cpu_crop} ViT-B/16+VLG head supervised step",
+            "data": "synthetic", "config": {"workload": f"{args.name} ViT-B/16+VLG head supervised step",
                                             "batch_per_step": 1, "note": "reference CPU path = oracle port of the reference (pure PyTorch fp32)"},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ in-run parity
+def parity_block(torch, args, model, label):
+    """Logits of ONE synthetic image through the timed model's public forward against the CPU oracle (fp32 restatement of the reference,
+    pinned to the unmodified reference by tests/golden) run with THE SAME weights: max |d| / max |ref| (the north star's '1e-3 rel'),
+    arg-max agreement overall and on the pixels whose reference top-1/top-2 margin exceeds twice the measured error.  The weights are the
+    parity tests' seeded fixture (oracle.fixture_state_dict(seed 0)), loaded into the timed model after the timed region: the reference's
+    own init_weights leaves the random head so close to class-degenerate that an arg-max comparison says nothing."""
+    import numpy as np
+    from oracle import semivl_oracle as O
+    mc = O.ModelCfg(img_size=args.crop, num_classes=args.nclass)
+    sd = O.fixture_state_dict(O.param_shapes(mc, with_clip_encoder=False), seed=0)
+    model.load_state_dict(sd, strict=False)
+    for part in (model.backbone, model.decode_head):
+        part.engine.cache.clear()
+    text = torch.from_numpy(np.load(os.path.join(ROOT, "semivl_b200", "configs", "_base_", "datasets", "text_embedding", TEXT_OF[args.dataset] + ".npy")))
+    img = synth_batch(torch, 1, args.crop, args.nclass, 4321, "cpu", False)["img_x"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = O.model_forward(img, sd, text, mc)
+        y = model(img.cuda()).float().cpu()
+    err = (y - ref).abs().max().item()
+    top2 = ref.topk(2, dim=1).values
+    dec = (top2[:, 0] - top2[:, 1]) > 2 * err
+    same = y.argmax(1) == ref.argmax(1)
+    return {"mode": label, "logits_rel": err / ref.abs().max().item(), "tolerance_north_star": 1e-3, "argmax_agree": same.float().mean().item(),
+            "decidable_frac": dec.float().mean().item(), "argmax_exact_on_decidable": bool(same[dec].all()),
+            "how": f"1 synthetic image {args.crop}x{args.crop}, N={args.nclass}, same weights (seeded fixture of the parity tests) through the CPU oracle (fp32); rel = max|d| / max|ref|; "
+                   f"decidable = reference top-1/top-2 margin > 2 x max|d| (random-init weights give near-tied classes, SURVEY.md §0 fact 6)",
+            "seconds": round(time.perf_counter() - t0, 2)}
 
 
 def main():
@@ -170,97 +290,118 @@ def main():
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    from semivl_b200 import input_pipeline as ip
     from semivl_b200 import lib as L
     from semivl_b200 import ops
     from semivl_b200.model import build_model
     from semivl_b200.train import OptimCfg, Trainer
     L.check_device()
     semivl = args.workload == "semivl"
-    torch.manual_seed(0)
-    model = build_model(model_cfg(args.crop, args.nclass, args.precise)).to(dev)
-    tr = Trainer(model, OptimCfg(lr=1e-4, total_iters=100000))
     b = args.batch
-    host = synth_batch(torch, b, args.crop, args.nclass, 1234 + rank, "cuda", semivl)
-    resident = {k: v.to(dev) for k, v in host.items()}
+    host_u8, boxes = synth_host_u8(torch, b, args.crop, args.nclass, 1234 + rank, semivl, True)
 
-    use_graph = not semivl and not args.no_graph and args.crop % 16 == 0 and (world == 1 or args.graph_multi)
-
-    def step(batch):
-        if semivl:
-            return tr.semivl_step(batch)[0]
-        if use_graph and ops.PROFILE is None:         # the instrumented steps (events around each contraction) run eagerly
-            return tr.graphed_supervised_step(batch["img_x"], batch["mask_x"])
-        return tr.supervised_step(batch["img_x"], batch["mask_x"])
+    def make_trainer(precise):
+        torch.manual_seed(0)
+        model = build_model(model_cfg(args, precise)).to(dev)
+        return model, Trainer(model, OptimCfg(lr=1e-4, total_iters=100000))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 12)):       # W untimed steps, and never fewer than 12: graph capture + clock ramp of a cold box
-        step(resident)
-    barrier()
+    def timed_leg(tr, resident, steps, warmup, use_graph):
+        """W untimed warm-up steps, then exactly K timed steps between barrier + synchronize; one event per step for the median."""
+        def step(batch):
+            if semivl:
+                return tr.semivl_step(batch)[0]
+            if use_graph and ops.PROFILE is None:         # the instrumented steps (events around each contraction) run eagerly
+                return tr.graphed_supervised_step(batch["img_x"], batch["mask_x"])
+            return tr.supervised_step(batch["img_x"], batch["mask_x"])
+        n_setup = 0
+        if use_graph:                                     # capture (one eager pass + the capture pass): set-up, not a warm-up step
+            step(resident)
+            n_setup = 1
+        for _ in range(warmup):
+            step(resident)
+        barrier()
+        l0 = L.launches
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        evs[0].record()
+        loss = None
+        for i in range(steps):
+            loss = step(resident)
+            evs[i + 1].record()
+        barrier()
+        ms = evs[0].elapsed_time(evs[-1]) / steps
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        return step, ms, per[len(per) // 2], (L.launches - l0) // steps, loss, n_setup
+
+    use_graph = not semivl and not args.no_graph and (world == 1 or not args.no_graph_multi)
+    model, tr = make_trainer(args.precise)
+    u8_dev = {k: v.to(dev) for k, v in host_u8.items()}
+    resident = device_batch(torch, ip, u8_dev, boxes, args.crop)
+    torch.cuda.reset_peak_memory_stats(dev)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     # ---- device-timed region: inputs resident in HBM
-    l0 = L.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        loss = step(resident)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = (L.launches - l0) // args.steps
-    # ---- end-to-end region: host (pinned) buffers; every step's inputs cross PCIe inside the timed region and the loss is read
-    # back every step.  The copies are double-buffered on a copy stream (what a pinned-memory data loader does): the H2D of step
-    # i+1 runs under the kernels of step i, each step waits for its own inputs.
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    stages = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    step, ms, ms_median, launches, loss, n_setup = timed_leg(tr, resident, args.steps, args.warmup, use_graph)
+    # ---- end-to-end region: pinned uint8 host buffers; every step's inputs cross PCIe inside the timed region on a copy stream
+    # (double-buffered: the H2D of step i+1 runs under the kernels of step i), the input-stage kernels turn them into the step's fp32 / int64
+    # tensors on the compute stream, and the loss is copied back to pinned memory every step and read one step behind.
+    h2d = sum(v.numel() * v.element_size() for v in host_u8.values())
+    stages = [{k: torch.empty_like(v, device=dev) for k, v in host_u8.items()} for _ in range(2)]
+    work = [{}, {}]
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def upload(i):
+        """H2D of step i's uint8 inputs and their conversion by the input-stage kernels, both on the copy stream: they run under the
+        kernels of step i-1; step i waits for `ready`."""
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])              # the step that last read this staging buffer has finished
-            for k, v in host.items():
+            copy_stream.wait_event(consumed[i % 2])              # the step that last read this buffer pair has finished
+            for k, v in host_u8.items():
                 stages[i % 2][k].copy_(v, non_blocking=True)
+            device_batch(torch, ip, stages[i % 2], boxes, args.crop, out=work[i % 2])
             ready[i % 2].record(copy_stream)
 
+    e2e_steps = args.steps
     barrier()
     for ev in consumed:
         ev.record()
+    for w_ in work:
+        device_batch(torch, ip, u8_dev, boxes, args.crop, out=w_)     # allocate the work tensors outside the timed region
+    barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     upload(0)
-    # every step's loss crosses PCIe into pinned memory; the host reads it one step behind (what an asynchronous logger does), so the
-    # launch of step i+1 is not held back by the read-back of step i
     loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     lv = float("nan")
-    for i in range(args.steps):
-        if i + 1 < args.steps:
+    for i in range(e2e_steps):
+        if i + 1 < e2e_steps:
             upload(i + 1)
         torch.cuda.current_stream().wait_event(ready[i % 2])
-        out = step(stages[i % 2])
+        out = step(work[i % 2])
         consumed[i % 2].record()
         loss_host[i % 2].copy_(out.reshape(1), non_blocking=True)
         loss_ready[i % 2].record()
         if i > 0:
             loss_ready[(i - 1) % 2].synchronize()
             lv = float(loss_host[(i - 1) % 2][0])
-    loss_ready[(args.steps - 1) % 2].synchronize()
-    lv = float(loss_host[(args.steps - 1) % 2][0])
+    loss_ready[(e2e_steps - 1) % 2].synchronize()
+    lv = float(loss_host[(e2e_steps - 1) % 2][0])
     f1.record()
     barrier()
-    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3) / args.steps
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3) / e2e_steps
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    peak_mem = torch.cuda.max_memory_allocated(dev)
     # ---- instrumented steps: CUDA events (on the launching stream) around every tensor-core contraction launch
     ops.PROFILE = []
     n_inst = 2
@@ -284,10 +425,10 @@ def main():
         with open(os.environ["SVL_PROFILE_DUMP"], "w") as fh:
             for t_ms, f, lab in prof[:n_gemm]:
                 fh.write(f"{t_ms * 1e3:10.1f} us {f / t_ms / 1e9 if t_ms > 0 else 0:8.1f} TF/s  {lab}\n")
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_median], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_median = t.tolist()
     if rank != 0:
         teardown(world, tr)
         return
@@ -304,21 +445,28 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dom_label, {})
     except Exception:
         pass
-    unit_gf = GF_PER_UNIT_SEMIVL if semivl else GF_PER_IMG_SUPERVISED
-    step_tf = unit_gf * b / 1e3
+    step_tf = args.gf_per_img * b / 1e3 if args.gf_per_img else None
     value = world * b / (ms / 1e3)
+    mode_name = "bf16x3" if args.precise else "bf16"
     line = {
         "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3" if args.precise else "bf16",
+        "ms_per_step": ms, "ms_per_step_median": ms_median, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": mode_name,
         "data": "synthetic",
-        "config": {"workload": (f"VOC {args.nclass}-class synthetic {args.crop}x{args.crop} ViT-B/16+VLG head, "
-                                + ("full SemiVL consistency step" if semivl else "supervised step fwd+bwd+AdamW")),
-                   "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}",
-                   "launch": "one CUDA-graph replay per step" if use_graph else "eager kernel launches", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
-                   "weights": "random init (reference init_weights)", "loss": float(loss.item())},
+        "config": {"workload": f"{args.name} ViT-B/16+VLG head, " + ("full SemiVL consistency step (teacher + MaskCLIP + 5-way student head, 7 loss terms)"
+                                                                       if semivl else "supervised step fwd+bwd+AdamW"),
+                   "baseline_config": args.config, "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}",
+                   "launch": "one CUDA-graph replay per step" + (" (NCCL gradient exchange captured in the graph)" if world > 1 else "")
+                             if use_graph else "eager kernel launches",
+                   "setup_steps_before_warmup": n_setup, "l2": "per-step working set (GBs of activations) >> 126 MB L2",
+                   "inputs": "synthetic uint8 images / labels, ImageNet-normalised on the device", "weights": "random init (reference init_weights)",
+                   "arithmetic": ("split-bf16 x3 operands (parity mode)" if args.precise else
+                                  "bf16 operands, fp32 accumulation / statistics / residual stream (throughput mode; see `parity` for its measured "
+                                  "logit error: it does NOT meet the north star's 1e-3, the `precise` leg does)"),
+                   "loss": float(loss.item()), "peak_memory_gb": round(peak_mem / 1e9, 2)},
         "e2e": {"value": world * b / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "last_loss": lv,
-                "how": "pinned host inputs uploaded every step on a copy stream (double-buffered), every step's loss copied to pinned host memory and read one step behind"},
+                "how": "pinned uint8 host images / labels uploaded every step on a copy stream (double-buffered), normalised / converted by the "
+                       "input-stage kernels inside the timed region, every step's loss copied to pinned host memory and read one step behind"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None,
         "roofline": {"bound": "tensor", "kernel": f"gemm_kernel [{dom_label}] (persistent TMA + tcgen05 GEMM, csrc/gemm.cu)",
@@ -328,17 +476,42 @@ def main():
                      "avg_launch_us": 1e3 * dom_ms / dom_n, "launches_per_step": dom_n, "share_of_step": dom_ms / ms if ms else None,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                      "measured_on": f"{n_inst} instrumented steps after the timed region (CUDA events on the launching stream around every contraction launch)",
-                     "engine": {"what": "all gemm_kernel / wgrad_kernel / wgrad_strip_kernel launches of the step", "launches": n_gemm,
-                                "achieved": achieved_tf, "frac": achieved_tf / peak_tf if peak_tf else None, "ms_per_step": gemm_ms,
-                                "share_of_step": gemm_ms / ms if ms else None},
-                     "whole_step_algorithmic_tflops": step_tf / (ms / 1e3), "whole_step_frac": step_tf / (ms / 1e3) / peak_tf},
+                     "engine_launches": n_gemm, "engine_achieved": achieved_tf, "engine_frac": achieved_tf / peak_tf if peak_tf else None,
+                     "engine_ms_per_step": gemm_ms, "engine_share_of_step": gemm_ms / ms if ms else None,
+                     "engine_what": "all gemm_kernel / wgrad_kernel / wgrad_strip_kernel launches of the step",
+                     "whole_step_algorithmic_tflops": step_tf / (ms / 1e3) if step_tf else None,
+                     "whole_step_frac": step_tf / (ms / 1e3) / peak_tf if step_tf else None},
     }
-    if not args.no_cpu_baseline and world == 1:
+    single = world == 1
+    if single and not args.no_parity:
         try:
-            v, cms, cores = cpu_reference_rate(args, 14, 2, args.cpu_crop)          # ~10 s of host work
+            line["parity"] = parity_block(torch, args, model, mode_name)
+        except Exception as e:
+            line["parity"] = {"mode": mode_name, "failed": str(e)[:200]}
+    if single and args.config == 2 and not args.precise and not args.no_precise_leg and not semivl:
+        # second timed leg: the parity mode (split-bf16 x3 on the same kernels), the mode whose logits are inside the north star's 1e-3
+        try:
+            tr._graph = None
+            del tr, step
+            torch.cuda.empty_cache()
+            model_p, tr_p = make_trainer(True)
+            _, ms_p, med_p, _, loss_p, _ = timed_leg(tr_p, resident, max(5, args.steps // 5), 3, use_graph)
+            leg = {"dtype": "bf16x3", "value": b / (ms_p / 1e3), "unit": "images/s", "ms_per_step": ms_p, "ms_per_step_median": med_p,
+                   "steps": max(5, args.steps // 5), "warmup": 3, "loss": float(loss_p.item())}
+            if not args.no_parity:
+                leg["parity"] = parity_block(torch, args, model_p, "bf16x3")
+            line["precise"] = leg
+            tr_p._graph = None
+            tr = tr_p
+        except Exception as e:
+            line["precise"] = {"failed": str(e)[:200]}
+    if not args.no_cpu_baseline and single:
+        try:
+            n_cpu = 14 if args.config == 2 else 3
+            v, cms, cores = cpu_reference_rate(args, n_cpu, 2 if args.config == 2 else 1, args.cpu_crop)          # ~10 s of host work
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"oracle port of the reference (CPU PyTorch fp32), supervised step fwd+CE+bwd+AdamW at batch 1, "
-                                              f"{args.cpu_crop}x{args.cpu_crop}, N={args.nclass}: 14 timed steps after 2 warm-up ({cms:.0f} ms/step)"}
+                                              f"{args.cpu_crop}x{args.cpu_crop}, N={args.nclass}: {n_cpu} timed steps ({cms:.0f} ms/step)"}
         except Exception as e:      # the baseline must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     if saved_stdout is not None:

@@ -134,6 +134,11 @@ int svl_wgrad(const svl_wgrad_desc* d, void* stream);
 int svl_patchify(const float* img, void* out, int out_dtype, int b, int H, int W, int p, int hp, int wp, void* stream);
 /* x[b,0,:] = cls + pos[0]; x[b,1+i,:] = patches[b*hw+i,:] + pos[1+i]   (maskclip_vit.py:498-500) */
 int svl_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int b, int hw, int c, void* stream);
+/* Position-table resize for crops whose token grid differs from the table's (maskclip_vit.py:448-459,462-490; 801^2 -> 51^2 from 50^2,
+ * 641^2 -> 41^2 from 40^2): out[0] = pos[0] (cls), out[1 + oy*ow + ox] = bicubic(pos[1:] as a [gh, gw, c] grid), torch's kernel
+ * (A = -0.75, align_corners=False).  Backward: dpos += resize^T(dout) (red.global.add: dpos is a parameter gradient). */
+int svl_pos_resize_fwd(const float* pos, float* out, int gh, int gw, int oh, int ow, int c, void* stream);
+int svl_pos_resize_bwd(const float* dout, float* dpos, int gh, int gw, int oh, int ow, int c, void* stream);
 /* LayerNorm over the last dim (maskclip_vit.py:111,132,141-142,507,539-541).  mean/rstd [rows] saved when non-NULL. */
 int svl_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y, int y_dtype, int64_t ldy,
                       float* mean, float* rstd, int64_t rows, int c, float eps, void* stream);

@@ -57,6 +57,80 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patches, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- position-table resize
+// MaskClipVisionTransformer.resize_pos_embed (maskclip_vit.py:462-490): the cls row is copied, the [gh, gw, c] grid rows are resized to
+// [oh, ow] with torch's bicubic kernel (A = -0.75, align_corners=False: src = (dst + 0.5) * in/out - 0.5 WITHOUT clamping, taps at
+// floor(src) - 1 .. + 2 with the tap index clamped to the grid).  Forward gathers 16 taps per output row; backward scatters them
+// with red.global.add (the position table is a parameter: its gradient tolerates the atomics' order like every weight gradient).
+__device__ __forceinline__ void cubic_taps(int o, float scale, int in_size, int idx[4], float w[4]) {
+  const float A = -0.75f;
+  const float real = scale * ((float)o + 0.5f) - 0.5f;
+  const float fl = floorf(real);
+  const float t = real - fl;
+  const int i0 = (int)fl;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v = i0 - 1 + k;
+    idx[k] = v < 0 ? 0 : (v > in_size - 1 ? in_size - 1 : v);
+  }
+}
+// one thread = one float4 of one output row; row 0 is the cls entry
+template <bool kBackward>
+__global__ void pos_resize_kernel(const float* __restrict__ src, float* __restrict__ dst, int gh, int gw, int oh, int ow, int c) {
+  const int c4 = c / 4;
+  const int64_t total = (int64_t)(oh * ow + 1) * c4;
+  const float sy = (float)gh / (float)oh, sx = (float)gw / (float)ow;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % c4);
+    const int row = (int)(idx / c4);
+    if (row == 0) {
+      const float4 v = __ldg((const float4*)src + j);
+      if (kBackward) {
+        float* d = dst + 4 * j;
+        atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
+      } else {
+        ((float4*)dst)[j] = v;
+      }
+      continue;
+    }
+    const int oy = (row - 1) / ow, ox = (row - 1) % ow;
+    int iy[4], ix[4];
+    float wy[4], wx[4];
+    cubic_taps(oy, sy, gh, iy, wy);
+    cubic_taps(ox, sx, gw, ix, wx);
+    if (kBackward) {
+      const float4 g = __ldg((const float4*)(src + (int64_t)row * c) + j);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float w = wy[a] * wx[b];
+          float* d = dst + (int64_t)(1 + iy[a] * gw + ix[b]) * c + 4 * j;
+          atomicAdd(d, w * g.x); atomicAdd(d + 1, w * g.y); atomicAdd(d + 2, w * g.z); atomicAdd(d + 3, w * g.w);
+        }
+    } else {
+      // torch accumulates row by row: out = sum_a wy[a] * (sum_b wx[b] * in[iy[a], ix[b]])
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float4 v = __ldg((const float4*)(src + (int64_t)(1 + iy[a] * gw + ix[b]) * c) + j);
+          r.x += wx[b] * v.x; r.y += wx[b] * v.y; r.z += wx[b] * v.z; r.w += wx[b] * v.w;
+        }
+        acc.x += wy[a] * r.x; acc.y += wy[a] * r.y; acc.z += wy[a] * r.z; acc.w += wy[a] * r.w;
+      }
+      ((float4*)(dst + (int64_t)row * c))[j] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -493,6 +567,20 @@ extern "C" int svl_assemble_tokens(const float* patches, const float* cls, const
   SVL_CHECK_ARG(patches && cls && pos && x && c % 4 == 0, "svl_assemble_tokens: bad arguments");
   const int64_t total = (int64_t)b * (hw + 1) * (c / 4);
   assemble_tokens_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(patches, cls, pos, x, b, hw, c);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_pos_resize_fwd(const float* pos, float* out, int gh, int gw, int oh, int ow, int c, void* stream) {
+  SVL_CHECK_ARG(pos && out && c % 4 == 0 && gh > 0 && gw > 0 && oh > 0 && ow > 0, "svl_pos_resize_fwd: bad arguments");
+  pos_resize_kernel<false><<<ew_grid((int64_t)(oh * ow + 1) * (c / 4)), 256, 0, (cudaStream_t)stream>>>(pos, out, gh, gw, oh, ow, c);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
+extern "C" int svl_pos_resize_bwd(const float* dout, float* dpos, int gh, int gw, int oh, int ow, int c, void* stream) {
+  SVL_CHECK_ARG(dout && dpos && c % 4 == 0 && gh > 0 && gw > 0 && oh > 0 && ow > 0, "svl_pos_resize_bwd: bad arguments");
+  pos_resize_kernel<true><<<ew_grid((int64_t)(oh * ow + 1) * (c / 4)), 256, 0, (cudaStream_t)stream>>>(dout, dpos, gh, gw, oh, ow, c);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

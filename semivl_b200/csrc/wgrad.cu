@@ -400,7 +400,10 @@ int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) 
                                  // 1: additionally set the descriptor base_offset field (wrong on B200, kept for experiments); 0: disabled
   }
   if (mode == 0 || !d->conv || d->num_taps < 2 || d->num_taps > SVL_MAX_TAPS) return 0;
-  if (d->x_map_w != 0 || d->w % 16 != 0) return 0;
+  // rows at least one K block wide: a K block is 64 pixels of ONE image row, the last block of a row may hang over the edge (TMA
+  // zero-fills dy and x there: no contribution) -- 641^2 / 801^2 crops give 164- / 204-pixel rows.  Narrower rows are packed several per
+  // K block and must then be a multiple of the 16-pixel MMA K step.
+  if (d->x_map_w != 0 || (d->w < KB && d->w % 16 != 0)) return 0;
   StripParams p;
   memset(&p, 0, sizeof(p));
   p.bw = d->w < KB ? d->w : KB;

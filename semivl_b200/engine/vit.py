@@ -9,7 +9,6 @@ bf16 pair (precise).  Only `attn.*` weights/biases and `pos_embed` receive gradi
 runs dgrad everywhere and wgrad only for in_proj / out_proj.
 """
 import torch
-import torch.nn.functional as F
 
 from .. import lib as L
 from .. import ops
@@ -79,14 +78,10 @@ class VitEngine:
         if pos.shape[1] == hp * wp + 1:
             return pos[0], None
         g = int(round((pos.shape[1] - 1) ** 0.5))
-        src = pos.detach()
-        if need_grad:
-            src = src.clone().requires_grad_(True)
-        with torch.enable_grad() if need_grad else torch.no_grad():
-            grid = src[:, 1:].reshape(1, g, g, -1).permute(0, 3, 1, 2)
-            grid = F.interpolate(grid, size=(hp, wp), mode="bicubic", align_corners=False)      # ATen bicubic (rare path: crop % 16 != 0)
-            out = torch.cat((src[:, :1], grid.flatten(2).transpose(1, 2)), dim=1)[0]
-        return out.detach().contiguous(), ((src, out) if need_grad else None)
+        assert g * g + 1 == pos.shape[1], "square position grids only (maskclip_vit.py:278-285)"
+        out = torch.empty(hp * wp + 1, pos.shape[2], device=pos.device, dtype=torch.float32)
+        L.call("svl_pos_resize_fwd", pos.detach().contiguous(), out, g, g, hp, wp, pos.shape[2])
+        return out, ((g, hp, wp) if need_grad else None)
 
     # ------------------------------------------------------------------ forward
     def forward(self, img, p, need_grad=True, want_global=True):
@@ -302,7 +297,6 @@ class VitEngine:
             if ctx["pos_ctx"] is None:
                 ops.axpy(grads["pos_embed"].view(-1), dpos.view(-1))
             else:
-                src, out = ctx["pos_ctx"]
-                out.backward(dpos)                               # ATen bicubic backward (crop % 16 != 0 only)
-                ops.axpy(grads["pos_embed"].view(-1), src.grad.contiguous().view(-1))
+                g, oh, ow = ctx["pos_ctx"]                        # transpose of the bicubic resize, straight into the parameter gradient
+                L.call("svl_pos_resize_bwd", dpos, grads["pos_embed"], g, g, oh, ow, E)
         return grads

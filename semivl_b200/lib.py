@@ -75,6 +75,8 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _PROTOS = {
     "svl_patchify": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "svl_assemble_tokens": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "svl_pos_resize_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "svl_pos_resize_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "svl_layernorm_fwd": [_P, _L, _P, _P, _P, _I, _L, _P, _P, _L, _I, _F, _P],
     "svl_layernorm_bwd": [_P, _I, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _L, _P, _P, _L, _I, _P],
     "svl_l2norm_fwd": [_P, _L, _P, _P, _I, _L, _P, _L, _I, _F, _P],

@@ -94,10 +94,14 @@ def build_model(cfg):
         mmseg_cfg['model']['clip_encoder'] = clip_encoder_cfg['backbone']
     if 'model_args' in cfg:
         mmseg_cfg['model'].update(cfg['model_args'])
-    precise = bool(cfg.get('precise', False))
+    # extension: arithmetic mode per engine.  False = bf16 operands everywhere (throughput), True = split-bf16 x3 everywhere (parity),
+    # 'head' / 'encoder' = split operands in that engine only (the frozen clip_encoder follows the encoder)
+    pmode = cfg.get('precise', False)
+    if pmode not in (False, True, 'head', 'encoder'):
+        raise ValueError(f"cfg['precise'] must be False, True, 'head' or 'encoder', got {pmode!r}")
     for part in ('backbone', 'decode_head', 'clip_encoder'):
         if mmseg_cfg['model'].get(part) is not None:
-            mmseg_cfg['model'][part]['precise'] = precise
+            mmseg_cfg['model'][part]['precise'] = pmode is True or pmode == ('head' if part == 'decode_head' else 'encoder')
     model = build_segmentor(mmseg_cfg.model, train_cfg=mmseg_cfg.get('train_cfg'), test_cfg=mmseg_cfg.get('test_cfg'))
     model.disable_dropout = cfg['disable_dropout']
     model.fp_rate = cfg['fp_rate']

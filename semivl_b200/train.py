@@ -76,8 +76,10 @@ class OptimCfg:
 
 
 class Trainer:
-    def __init__(self, model, optim=None, hp=None):
+    def __init__(self, model, optim=None, hp=None, head_chunk_bytes=24e9):
         self.model = model
+        # activation budget of ONE gradient-tracked head pass of the SemiVL step (see _head_chunk); None = never split
+        self.head_chunk_bytes = head_chunk_bytes
         self.opt = optim or OptimCfg()
         self.hp = dict(conf_thresh=0.95, conf_mode="pixelwise", mcc_conf_thresh=0.9, mcc_loss_reduce="mean_all", mcc_lambda=0.1)
         if hp:
@@ -189,7 +191,6 @@ class Trainer:
         so the replayed graph keeps the exchange overlapped with the backward kernels."""
         key = (tuple(img.shape), tuple(mask.shape))
         if self._graph is None or self._graph_key != key:
-            assert img.shape[-1] % 16 == 0 and img.shape[-2] % 16 == 0, "crops that need the pos-embed resize run eagerly"
             self._g_img, self._g_mask = img.clone(), mask.clone()
             self._hyper = torch.zeros(4, device=img.device)
             self.supervised_step(self._g_img, self._g_mask, update=False)        # eager pass: frozen-weight operand cache, lazy attributes
@@ -254,10 +255,22 @@ class Trainer:
         return loss[0]
 
     # ------------------------------------------------------------------ SemiVL step (semivl.py:224-346)
+    def _head_chunk(self, N, hl, wl):
+        """Images per gradient-tracked head pass.  The head's saved activations are per (image, class) map -- ~16 MB per map at 128 x 128
+        output pixels in bf16 (twice that in the split-operand mode), i.e. 2.4 GB per image at N = 150 -- and no op of
+        the head mixes images (GroupNorm per map, class attention per image position), so the head batch can be cut into groups of images
+        that run forward -> loss -> backward one after the other with exactly the same result: the peak is one group's activations
+        instead of the whole 4b-image head batch (BASELINE configs 4 / 5: 124 GB at ADE b=8, 235 GB predicted at COCO b=16 unsplit)."""
+        if not self.head_chunk_bytes:
+            return 1 << 30
+        per_img = N * 16e6 * (hl * wl) / (128.0 * 128.0) * (2.0 if self.head.precise else 1.0)
+        return max(1, int(self.head_chunk_bytes // per_img))
+
     def semivl_step(self, batch, drop_masks=None, update=True):
-        """batch keys follow semivl.py:203-221.  One encoder pass over (img_x | img_w | img_s1 | img_s2), one head pass over
-        (x | w | w_fp | s1 | s2) -- the perturbed copy of the labelled images is never computed (the reference discards it,
-        semivl.py:247) -- a no-grad teacher pass on img_w_other and the frozen MaskCLIP pass on (img_w | img_w_other)."""
+        """batch keys follow semivl.py:203-221.  One encoder pass over (img_x | img_w | img_s1 | img_s2); a no-grad head pass over the
+        weak views (their prediction is detached, semivl.py:251: it only yields pseudo-labels) and gradient-tracked head passes over
+        (x | w_fp | s1 | s2), cut into image groups by _head_chunk -- the perturbed copy of the labelled images is never computed (the
+        reference discards it, semivl.py:247) --; a no-grad teacher pass on img_w_other and the frozen MaskCLIP pass on (img_w | img_w_other)."""
         m, hp = self.model, self.hp
         b = batch["img_x"].shape[0]
         H, W = batch["img_x"].shape[-2:]
@@ -276,12 +289,16 @@ class Trainer:
         L.call("svl_cutmix_img", batch["img_s2"], batch["img_s2_other"], batch["mix2"], img_s2, b, 3, H * W)
         # ---- teacher passes (no grad)
         fo, _, _ = self.vit.forward(m.renormalize_img_for_clip(batch["img_w_other"]), pb, need_grad=False, want_global=False)
-        low_o, _ = self.head.forward(fo, text, ph, need_grad=False)
-        del fo
-        N, hl, wl = low_o.shape[1:]
+        N, hl, wl = text.shape[0], 4 * fo[-1].shape[1], 4 * fo[-1].shape[2]
+        chunk = self._head_chunk(N, hl, wl)
         conf_o = torch.empty(b, H, W, device=dev)
         lab_o = torch.empty(b, H, W, device=dev, dtype=torch.int64)
-        L.call("svl_softmax_max", low_o, conf_o, lab_o, b, N, hl, wl, H, W, 1.0, 0.0)
+        for i0 in range(0, b, 4 * chunk):                           # nothing is saved in a no-grad pass: 4x larger groups
+            i1 = min(b, i0 + 4 * chunk)
+            low_o, _ = self.head.forward([f[i0:i1] for f in fo], text, ph, need_grad=False)
+            L.call("svl_softmax_max", low_o, conf_o[i0:i1], lab_o[i0:i1], i1 - i0, N, hl, wl, H, W, 1.0, 0.0)
+            del low_o
+        del fo
         mclip = mclip_o = None
         if lam != 0:
             mc = m.forward_maskclip(torch.cat((batch["img_w"], batch["img_w_other"])), hp["mcc_conf_thresh"])
@@ -295,13 +312,14 @@ class Trainer:
             drop_masks = [torch.bernoulli(torch.full((b, f.shape[-1]), 1.0 - m.fp_rate, device=dev)) for f in feats]
         scale = 1.0 / (1.0 - m.fp_rate)
         dm = [(dmk.reshape(b, 1, 1, -1).to(dev) * scale) for dmk in drop_masks]
-        # head batch: [x | w | w_fp | s1 | s2]
-        hf = [torch.cat((f[:2 * b], f[b:2 * b] * k, f[2 * b:])) for f, k in zip(feats, dm)]
-        low, hctx = self.head.forward(hf, text, ph, need_grad=True)
-        del hf
+        # pseudo-labels of the weak views (pred_w.detach().softmax.max, semivl.py:251-252): no gradient ever reaches these rows
         conf_w = torch.empty(b, H, W, device=dev)
         lab_w = torch.empty(b, H, W, device=dev, dtype=torch.int64)
-        L.call("svl_softmax_max", low[b:2 * b], conf_w, lab_w, b, N, hl, wl, H, W, 1.0, 0.0)
+        for i0 in range(0, b, 4 * chunk):                           # nothing is saved in a no-grad pass: 4x larger groups
+            i1 = min(b, i0 + 4 * chunk)
+            low_w, _ = self.head.forward([f[b + i0:b + i1] for f in feats], text, ph, need_grad=False)
+            L.call("svl_softmax_max", low_w, conf_w[i0:i1], lab_w[i0:i1], i1 - i0, N, hl, wl, H, W, 1.0, 0.0)
+            del low_w
         # ---- targets (cutmix of pseudo-labels, confidences, ignore masks; confidence weights per cfg['conf_mode'])
         npx = float(b * H * W)
         mode = CONF_MODES[hp["conf_mode"]]
@@ -352,40 +370,45 @@ class Trainer:
         _, w_fp, cf_fp, cnt_fp = conf_target(lab_w, conf_w, batch["ignore_mask"], None, 0.25, False)
         cnt_x = self._f(1)
         L.call("svl_count_valid", batch["mask_x"], batch["mask_x"].numel(), 255, cnt_x)
-        d_low = torch.zeros_like(low)
-        rows = lambda t, i: t[i * b:(i + 1) * b]
-        lx = self._f(3)
-        self._ce(rows(low, 0), rows(d_low, 0), b, N, hl, wl, H, W, [(batch["mask_x"], None, coef(cnt_x, 0.5))], lx)
-        lfp = self._f(3)
+        # loss groups: (encoder rows, feature scale, targets, loss accumulator); every coefficient is a full-batch quantity on the device
+        lx, lfp = self._f(3), self._f(3)
         t_fp = [(lab_w, w_fp, cf_fp)]
         if lam != 0:
             t_fp.append((mclip, None, mc_coef(mclip, cnt_fp, 0.5)))
-        self._ce(rows(low, 2), rows(d_low, 2), b, N, hl, wl, H, W, t_fp, lfp)
+        groups = [(0, None, [(batch["mask_x"], None, coef(cnt_x, 0.5))], lx), (b, dm, t_fp, lfp)]
         ls = {}
-        for i, key in ((3, "s1"), (4, "s2")):
+        for r0, key in ((2 * b, "s1"), (3 * b, "s2")):
             lab, wgt, cf, cnt, mcl = tgt[key]
             t = [(lab, wgt, cf)]
             if lam != 0:
                 t.append((mcl, None, mc_coef(mcl, cnt, 0.25)))
             ls[key] = self._f(3)
-            self._ce(rows(low, i), rows(d_low, i), b, N, hl, wl, H, W, t, ls[key])
+            groups.append((r0, None, t, ls[key]))
+        # ---- gradient-tracked head passes, one image group at a time: forward -> fused upsample + CE (loss and d_low) -> backward
+        dfe = [torch.zeros(4 * b, *f.shape[1:], device=dev, dtype=torch.float32) for f in feats]
+        sl = lambda t, i0, i1: None if t is None else t[i0:i1]
+        for r0, scale_k, targets, acc in groups:
+            for i0 in range(0, b, chunk):
+                i1 = min(b, i0 + chunk)
+                hf = [f[r0 + i0:r0 + i1] for f in feats]
+                if scale_k is not None:                     # feature perturbation of the weak views (builder.py:78-85)
+                    hf = [f * k[i0:i1] for f, k in zip(hf, scale_k)]
+                low, hctx = self.head.forward(hf, text, ph, need_grad=True)
+                del hf
+                d_low = torch.zeros_like(low)
+                self._ce(low, d_low, i1 - i0, N, hl, wl, H, W, [(sl(lb, i0, i1), sl(wg, i0, i1), cf) for lb, wg, cf in targets], acc)
+                dh = self.head.backward(hctx, d_low, ph, self.g_hd)
+                del hctx, low, d_low
+                for j, (g, d) in enumerate(zip(dfe, dh)):   # the clean weak views get no gradient: their rows carry the perturbed copy's
+                    g[r0 + i0:r0 + i1] = d if scale_k is None else d * scale_k[j][i0:i1]
+                del dh
         total = lx[0] + lfp[0] + lfp[1] + ls["s1"][0] + ls["s1"][1] + ls["s2"][0] + ls["s2"][1]
         terms = dict(loss_x=lx[0] * 2, loss_fp=lfp[0] * 4, loss_s1=ls["s1"][0] * 8, loss_s2=ls["s2"][0] * 8)
         if lam != 0:
             terms.update(loss_mc_fp=lfp[1] / (lam * 0.5), loss_mc_s1=ls["s1"][1] / (lam * 0.25), loss_mc_s2=ls["s2"][1] / (lam * 0.25))
-        # ---- backward
-        dhf = self.head.backward(hctx, d_low, ph, self.g_hd)
-        del hctx
+        # ---- encoder backward
         if update:
             self._head_grads_final()
-        dfe = []
-        for d, k in zip(dhf, dm):
-            g = torch.empty(4 * b, *d.shape[1:], device=dev, dtype=torch.float32)
-            g[:b] = d[:b]
-            g[b:2 * b] = d[b:2 * b] + d[2 * b:3 * b] * k
-            g[2 * b:] = d[3 * b:]
-            dfe.append(g)
-        del dhf
         self.vit.backward(vctx, dfe, pb, self.g_bb, on_layer_done=self._layer_grads_final if update else None)
         del vctx
         if update:

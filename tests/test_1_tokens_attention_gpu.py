@@ -131,7 +131,8 @@ def _attn_ref(qkv, b, L_, heads):
     return o.transpose(1, 2).reshape(b * L_, E), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("b,L_,heads", [(2, 197, 12), (1, 1025, 12), (3, 21, 4), (2, 64, 2), (1, 130, 1)])
+@pytest.mark.parametrize("b,L_,heads", [(2, 197, 12), (1, 1025, 12), (3, 21, 4), (2, 64, 2), (1, 130, 1), (2, 1682, 3), (1, 2602, 2), (2, 128, 2),
+                                        (1, 193, 2)])
 @pytest.mark.parametrize("precise", [False, True])
 def test_attention(ops, b, L_, heads, precise):
     from semivl_b200 import lib as L
@@ -155,3 +156,47 @@ def test_attention(ops, b, L_, heads, precise):
     da = ops.split_bf16(dout) if precise else dout.to(torch.bfloat16)
     dqkv = ops.attention_bwd(a, out, da, lse, b, L_, heads, precise, dv_add=dvadd, dv_add_dtype=L.F32)
     assert _rel(_val(dqkv, precise), ref_d) < (1e-4 if precise else 2e-2)
+
+
+@pytest.mark.parametrize("L_", [1025, 300])
+def test_attention_forward_rescales_when_the_running_maximum_grows(ops, L_):
+    """The tcgen05 forward keeps O in TMEM and moves a row's reference maximum only when the running maximum exceeds it by more than 8 (log2
+    units), rescaling O in place.  Keys whose scores GROW along the sequence (several crossings of the threshold per row, at different tiles
+    for different rows) against the fp32 reference; also rows whose scores shrink (never rescale after the first tile)."""
+    b, heads = 2, 3
+    E = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(L_ + 5)
+    qkv = torch.randn(b, L_, 3, heads, 64, device="cuda", generator=g)
+    ramp = torch.linspace(0.0, 1.0, L_, device="cuda").view(1, L_, 1, 1)
+    u = torch.randn(1, 1, heads, 64, device="cuda", generator=g)
+    u = u / u.norm(dim=-1, keepdim=True)
+    sign = torch.where(torch.arange(L_, device="cuda") % 3 == 0, -1.0, 1.0).view(1, L_, 1, 1)       # a third of the queries see shrinking scores
+    qkv[:, :, 0] = qkv[:, :, 0] * 0.3 + 12.0 * u * sign              # queries aligned (or anti-aligned) with u
+    qkv[:, :, 1] = qkv[:, :, 1] * 0.3 + 30.0 * u * ramp              # key component along u grows with the position: logits up to ~45
+    qkv = qkv.reshape(b * L_, 3 * E).to(torch.bfloat16)
+    ref, ref_lse = _attn_ref(qkv.float(), b, L_, heads)
+    out, lse = ops.attention_fwd(qkv, b, L_, heads, False)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert _rel(out, ref) < 1e-2
+    assert (lse - ref_lse).abs().max().item() < 2e-2              # absolute: lse reaches ~45 here (bf16 P rounding does not enter lse)
+
+
+@pytest.mark.parametrize("g,oh,ow", [(4, 5, 5), (50, 51, 51), (40, 41, 41), (14, 32, 32), (32, 14, 20)])
+def test_pos_resize_matches_torch_bicubic(ops, g, oh, ow):
+    """svl_pos_resize_fwd / _bwd against F.interpolate(mode='bicubic', align_corners=False) and its autograd on the position grid
+    (maskclip_vit.py:448-459,462-490): 50^2 -> 51^2 (801^2 crops), 40^2 -> 41^2 (641^2), the clip_encoder's 32^2 table on other crops."""
+    from semivl_b200 import lib as L
+    E = 768
+    gen = torch.Generator(device="cuda").manual_seed(g * 100 + oh)
+    pos = torch.randn(1, g * g + 1, E, device="cuda", generator=gen)
+    out = torch.empty(oh * ow + 1, E, device="cuda")
+    L.call("svl_pos_resize_fwd", pos, out, g, g, oh, ow, E)
+    src = pos.clone().requires_grad_(True)
+    grid = src[:, 1:].reshape(1, g, g, E).permute(0, 3, 1, 2)
+    ref = torch.cat((src[:, :1], F.interpolate(grid, size=(oh, ow), mode="bicubic", align_corners=False).flatten(2).transpose(1, 2)), dim=1)[0]
+    assert _rel(out, ref.detach()) < 2e-6
+    dout = torch.randn(oh * ow + 1, E, device="cuda", generator=gen)
+    ref.backward(dout)
+    dpos = torch.ones(1, g * g + 1, E, device="cuda")                 # accumulates into the parameter gradient
+    L.call("svl_pos_resize_bwd", dout, dpos, g, g, oh, ow, E)
+    assert _rel(dpos - 1.0, src.grad) < 1e-5

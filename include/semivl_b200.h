@@ -225,6 +225,41 @@ int svl_conv_out1_bwd(const float* dout, const void* x, int x_dtype, int64_t ldx
                       float* dw, float* dbias, int64_t maps, int h, int w, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Conv encoder of the Cityscapes skr04 model: mmseg ResNetV1c(depth=101, num_stages=1) = deep stem + layer1 with SyncBN
+ * (configs/_base_/models/vlm-vlg-aspp-s2p4-skr04-ftap-mcvitb.py:50-60, model/vlm.py:50-52,120-121).  The convolutions run on
+ * svl_gemm / svl_wgrad; these are the HBM-bound pieces around them.  NHWC activations, rows = B*H*W.
+ * ---------------------------------------------------------------------------------------------- */
+/* im2col of the 3x3 / stride 2 / pad 1 stem convolution on the f32 NCHW image: out[(b,oy,ox), c*9 + ky*3 + kx], columns 27..31 zero
+ * (out_dtype BF16 or BF16X2; the [32, 27] flattened weight padded to K = 32 is the matching operand) */
+int svl_stem_im2col(const float* img, void* out, int out_dtype, int64_t ldo, int B, int H, int W, int Ho, int Wo, void* stream);
+/* max-pool 3x3 / stride 2 / pad 1; widx [B*Ho*Wo, C] bytes = window position of the (first) maximum, consumed by the backward gather */
+int svl_maxpool3s2_fwd(const void* x, int dtype, int64_t ldx, void* out, int out_dtype, int64_t ldo, uint8_t* widx, int B, int H, int W, int C,
+                       int Ho, int Wo, void* stream);
+int svl_maxpool3s2_bwd(const void* dy, int dy_dtype, int64_t lddy, const uint8_t* widx, void* dx, int dx_dtype, int64_t lddx, int B, int H, int W,
+                       int C, int Ho, int Wo, void* stream);
+/* BatchNorm in training mode, split so that the host can all-reduce the statistics over the ranks (SyncBN):
+ *   svl_bn_stats     sums[0..C) = sum_rows x, sums[C..2C) = sum_rows x^2 (two fixed-order stages, no atomics; ws: svl_bn_workspace floats)
+ *   [all-reduce sums and the row count over NCCL]
+ *   svl_bn_finalize  mean / rstd of the (global) batch (biased variance), running statistics updated with `momentum` (unbiased variance;
+ *                    running_* may be NULL)
+ *   svl_bn_apply     out = [relu]((x - mean) * rstd * gamma + beta [+ res])      (eval mode: mean = running_mean, rstd = rsqrt(running_var + eps))
+ *   svl_bn_bwd_stats sums = [sum g | sum g * xhat], g = dy * [y > 0] (y = saved block output, NULL: no ReLU); dgamma = sums[C..), dbeta = sums[0..C)
+ *   [all-reduce sums]
+ *   svl_bn_bwd_apply dx = gamma * rstd * (g - S1/N - xhat * S2/N) with the global sums / row count; dres = g when non-NULL (residual branch) */
+size_t svl_bn_workspace(int64_t rows, int C);
+int svl_bn_stats(const void* x, int x_dtype, int64_t ldx, int64_t rows, int C, float* ws, float* sums, void* stream);
+int svl_bn_finalize(const float* sums, float count, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                    float* running_var, int C, void* stream);
+int svl_bn_apply(const void* x, int x_dtype, int64_t ldx, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 const void* res, int res_dtype, int64_t ldres, void* out, int out_dtype, int64_t ldo, int relu, int64_t rows, int C,
+                 void* stream);
+int svl_bn_bwd_stats(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const void* y, int y_dtype,
+                     int64_t ldy, const float* mean, const float* rstd, int64_t rows, int C, float* ws, float* sums, void* stream);
+int svl_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const void* y, int y_dtype,
+                     int64_t ldy, const float* mean, const float* rstd, const float* gamma, const float* sums, float count, void* dx,
+                     int dx_dtype, int64_t lddx, void* dres, int dres_dtype, int64_t lddres, int64_t rows, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Logit-side kernels.  `low` are the head's 4x-resolution class maps [R, N, hl, wl] f32; full-resolution logits
  * [R, N, H, W] = bilinear(low, align_corners=False) (vlg_head.py:247-248; the second resize of builder.py:93-97 is the identity).
  * ---------------------------------------------------------------------------------------------- */

@@ -264,14 +264,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 //   * K and V travel through separate rings (K is released by the score product, two tiles ahead of V);
 //   * the tail: key columns >= L are neither exponentiated nor counted, warps whose 32 query rows are all >= L only keep the barrier
 //     protocol going (L = 1025 = 8 * 128 + 1 leaves one valid row in the 9th query tile and one valid key in the 17th key tile);
-//   * EIGHT softmax warps: two threads per query row (warps w and w + 4 share a TMEM lane quarter), 32 of the tile's 64 keys each.  With one
-//     thread per row the XU pipe was 50 % busy -- two softmax warps per scheduler cannot cover each other's TMEM-load, maximum, pack and
-//     store phases.  The two threads of a row exchange their partial row maxima through shared memory (one 64-thread named barrier per
-//     tile) so that both take the same rescale decision; sums stay per thread and are combined once at the end.
-// Ordering relies on tcgen05.mma instructions of one thread executing in issue order: S_{j+2} (which overwrites score buffer j & 1 and
-// the P_j stored inside it) is issued after P_j V_j.
+//   (a variant with EIGHT softmax warps -- two threads per row exchanging partial row maxima through shared memory and a named barrier per
+//    tile -- was measured slower, 111.5 vs 102.5 us per layer: the forward is not short of warps; profiles/r02_attention.md.)
+// S_{j+2} overwrites score buffer j & 1 and the P_j stored inside it: the MMA warp issues it only after the commit of P_j V_j has arrived
+// (issue order alone does not protect a TMEM A operand against a later accumulator write).
 constexpr int TK2 = 64, KST = 4;
-constexpr int kThreads8 = 320;                 // producer warp + MMA warp + EIGHT softmax warps (two threads per row)
 constexpr uint32_t kHalfTile = 64 * 128;       // bytes of a 64-row x 64-bf16 tile
 constexpr float kRescaleThreshold = 8.f;       // log2 units
 
@@ -304,7 +301,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-__global__ void __launch_bounds__(kThreads8, 2)
+__global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -320,18 +317,18 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   auto p_full = [&](int s) { return bar + 8u * (5 + 4 * KST + s); };
   const uint32_t tmem_ptr_addr = bar + 8u * (7 + 4 * KST);
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - raw));
-  float* xchg = (float*)(smem_raw + (tmem_ptr_addr + 8 - raw));        // [2 tiles][4 quarters][2 halves][32 lanes] partial row maxima / sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const int E = p.heads * D;
   const int nt = (p.L + TK2 - 1) / TK2;
 
-  if (warp == 0 && lane == 0) {
+  constexpr int kProducerWarp = 4, kMmaWarp = 5;       // softmax warps 0..3 (TMEM lane quarter = warp id); the issue warps get the highest ids
+  if (warp == kProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
     ptx::mbar_init(q_full, 1);
-    ptx::mbar_init(q_tmem, 8);
+    ptx::mbar_init(q_tmem, 4);
     ptx::mbar_init(o_done, 1);
     for (int s = 0; s < KST; ++s) {
       ptx::mbar_init(k_full(s), 1);
@@ -341,11 +338,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(s_full(s), 1);
-      ptx::mbar_init(p_full(s), 8);
+      ptx::mbar_init(p_full(s), 4);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc(tmem_ptr_addr, 256);
     ptx::tmem_relinquish();
   }
@@ -354,7 +351,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;            // S / P [2]: columns [0,64) [64,128); O: [128,192); Q (packed bf16): [192,224)
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // two producer lanes: the K ring runs two tiles ahead of the V ring and must not wait behind it
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(q_full, kTile);
@@ -373,7 +370,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ptx::tma_load_3d(sV + st * kHalfTile, &tmKV, v_full(st), 2 * E + h * D, j * TK2, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     const bool leader = ptx::elect_one();
     const uint32_t idesc_s = ptx::make_idesc_bf16(128, 64, 0, 0);
     const uint32_t idesc_pv = ptx::make_idesc_bf16(128, 64, 0, 1);
@@ -403,8 +400,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(tmem_base + 128u, tmem_base + (uint32_t)(sb * 64 + (kk >> 1) * 32 + (kk & 1) * 8), vb + (uint64_t)(kk * 128), idesc_pv,
-                       (j > 0 || kk > 0) ? 1u : 0u);      // keys 32.. of P_j start at column 32 of the buffer (each thread packs over its own score columns)
+          umma_bf16_ts(tmem_base + 128u, tmem_base + (uint32_t)(sb * 64 + kk * 8), vb + (uint64_t)(kk * 128), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         ptx::umma_commit(v_empty(st));
         ptx::umma_commit(o_done);
       }
@@ -414,26 +410,30 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (nt > 1) issue_s(1);
     for (int j = 0; j < nt; ++j) {
       issue_pv(j);
-      if (j + 2 < nt) issue_s(j + 2);        // overwrites score buffer j & 1 (and P_j inside it): issued after P_j V_j, executes after it
+      if (j + 2 < nt) {
+        // S_{j+2} overwrites score buffer j & 1 and the P_j stored inside it.  Issue order is NOT enough: the tensor pipe does not track a
+        // later D write against an earlier TMEM A-operand read (run-to-run differences at 16 x 12 x 1025 proved it), so wait for P_j V_j.
+        ptx::mbar_wait(o_done, (uint32_t)(j & 1));
+        issue_s(j + 2);
+      }
     }
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;              // TMEM lane quarter (= warp % 4), key half of the 64-key tile
+    const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = p.scale * kLog2e;
-    const bool warp_valid = q0 + q * 32 < p.L;            // warp-uniform (and equal for both halves): none of the quarter's query rows exists otherwise
-    const int bar_id = 1 + q;                             // named barrier of the two warps of this quarter (0 is __syncthreads)
+    const bool warp_valid = q0 + q * 32 < p.L;            // warp-uniform: none of this warp's query rows exists otherwise
     {
-      // this thread's half of the Q row -> TMEM (the K-major SWIZZLE_128B tile holds row r at r * 128, 16-byte chunk c at (c ^ (r & 7)) * 16)
+      // Q row -> TMEM (the K-major SWIZZLE_128B tile holds row r at r * 128, 16-byte chunk c at (c ^ (r & 7)) * 16)
       ptx::mbar_wait(q_full, 0);
       const uint8_t* qrow = smem_raw + (sQ - raw) + r * 128;
-      uint32_t qv[16];
+      uint32_t qv[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 t = *(const uint4*)(qrow + (((half * 4 + c) ^ (r & 7)) << 4));
+      for (int c = 0; c < 8; ++c) {
+        const uint4 t = *(const uint4*)(qrow + ((c ^ (r & 7)) << 4));
         qv[c * 4] = t.x; qv[c * 4 + 1] = t.y; qv[c * 4 + 2] = t.z; qv[c * 4 + 3] = t.w;
       }
-      tmem_st16(tl + 192u + (uint32_t)(half * 16), qv);
+      ptx::tmem_st_32x32(tl + 192u, qv);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -444,49 +444,47 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int sb = j & 1;
       ptx::mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1));
       ptx::tc_fence_after();
-      const int nvalid = p.L - j * TK2 - half * 32;       // >= 32 except on the last tile (may be <= 0 for the second half)
+      const int nvalid = p.L - j * TK2;                   // >= 64 except on the last tile
       if (warp_valid) {
-        uint32_t v[32];
-        tmem_ld32(tl + (uint32_t)(sb * 64 + half * 32), v);
-        float m0 = -INFINITY, m1 = -INFINITY;
-        if (nvalid >= 32) {
+        uint32_t v[64];
+        tmem_ld64(tl + (uint32_t)(sb * 64), v);
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        if (nvalid >= 64) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < 64; i += 8) {
             m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
             m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            m2 = fmax3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            m3 = fmax3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (i < nvalid) m0 = fmaxf(m0, __uint_as_float(v[i]));
+          for (int i = 0; i < 64; ++i) if (i < nvalid) m0 = fmaxf(m0, __uint_as_float(v[i]));
         }
-        // row maximum over both halves: exchange through shared memory (slot j & 1: the partner read slot (j - 2) & 1 before it reached
-        // the barrier of tile j - 1)
-        float* slot = xchg + (sb * 4 + q) * 64;
-        slot[half * 32 + lane] = fmaxf(m0, m1);
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        const float ms = fmaxf(slot[lane], slot[32 + lane]) * sl2;
-        const bool need = ms > m_ref + kRescaleThreshold;           // first tile: m_ref = -inf.  Same inputs, same decision in both threads of the row
+        const float ms = fmax3(m0, m1, fmaxf(m2, m3)) * sl2;
+        const bool need = ms > m_ref + kRescaleThreshold;           // first tile: m_ref = -inf
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? ms : m_ref;
           const float corr = ex2(m_ref - m_new);                    // rows that keep their reference: ex2(0) = 1
           l *= corr;
-          if (j > 0) {                                              // O holds the tiles before j: wait for P_{j-1} V_{j-1}, rescale this thread's 32 columns
+          if (j > 0) {                                              // O holds the tiles before j: wait for P_{j-1} V_{j-1}, rescale in place
             ptx::mbar_wait(o_done, (uint32_t)((j - 1) & 1));
             ptx::tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(tl + 128u + (uint32_t)(half * 32), o);
+            uint32_t o[64];
+            tmem_ld64(tl + 128u, o);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            ptx::tmem_st_32x32(tl + 128u + (uint32_t)(half * 32), o);
+            for (int i = 0; i < 64; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            ptx::tmem_st_32x32(tl + 128u, o);
+            ptx::tmem_st_32x32(tl + 160u, o + 32);
           }
           m_ref = m_new;
         }
-        // P = exp2(s * scale - m_ref) as packed bf16 over the first 16 of the 32 score columns this thread has just read
-        uint32_t pk[16];
+        // P = exp2(s * scale - m_ref) as packed bf16 over the first 32 columns of the score buffer just read
+        uint32_t pk[32];
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        if (nvalid >= 32) {
+        if (nvalid >= 64) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 8; ++g) {
             float pv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) pv[i] = ex2(fmaf(__uint_as_float(v[g * 8 + i]), sl2, -m_ref));
@@ -496,7 +494,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 8; ++g) {
             float pv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) pv[i] = 0.f;
@@ -514,7 +512,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         l += (s0 + s1) + (s2 + s3);
-        tmem_st16(tl + (uint32_t)(sb * 64 + half * 32), pk);
+        ptx::tmem_st_32x32(tl + (uint32_t)(sb * 64), pk);
         ptx::tmem_st_wait();
       }
       ptx::tc_fence_before();
@@ -525,29 +523,24 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     ptx::tc_fence_after();
     const int row = q0 + r;
     if (warp_valid) {
-      // total row sum = both halves (the reference maxima are identical by construction)
-      float* slot = xchg + (nt & 1) * 256 + q * 64;
-      slot[half * 32 + lane] = l;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      l = slot[lane] + slot[32 + lane];
-      uint32_t o[32];
-      tmem_ld32(tl + 128u + (uint32_t)(half * 32), o);
+      uint32_t o[64];
+      tmem_ld64(tl + 128u, o);
       if (row < p.L) {
         const float inv = 1.f / l;
-        float f[32];
+        float f[64];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv;
-        __nv_bfloat16* dst = p.out + ((int64_t)b * p.L + row) * p.ldo + h * D + half * 32;
+        for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(o[i]) * inv;
+        __nv_bfloat16* dst = p.out + ((int64_t)b * p.L + row) * p.ldo + h * D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *(uint4*)(dst + i * 8) = f32_to_bf16x8(f + i * 8);
-        if (p.lse && half == 0) p.lse[((int64_t)b * p.heads + h) * p.L + row] = (m_ref + log2f(l)) / kLog2e;
+        for (int i = 0; i < D / 8; ++i) *(uint4*)(dst + i * 8) = f32_to_bf16x8(f + i * 8);
+        if (p.lse) p.lse[((int64_t)b * p.heads + h) * p.L + row] = (m_ref + log2f(l)) / kLog2e;
       }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 256);
   }
@@ -642,9 +635,8 @@ __device__ __forceinline__ void st_row64(uint8_t* row_base, int r, const float* 
 //   over the first 32 columns of the S^T / dP^T buffers the thread has just read -> dV += P^T dO, dK += dS^T Q with the A operand in
 //   TENSOR MEMORY (TMEM accumulators over all query tiles; Q / dO tiles are re-read MN-major from the same smem bytes).
 // Round 2: the operand tiles used to go through shared memory (2 x 16 KB written, 2 x 16 KB read per query tile: 144 KB of shared-memory
-// traffic per tile at 128 B/clk against 512 clk of tensor pipe -- the kernel was shared-memory-bandwidth bound); now 80 KB.  The score
-// products of tile j+1 overwrite P^T_j / dS^T_j, so they are issued after the accumulate products of tile j (tcgen05.mma executes in
-// issue order); the second CTA of the SM fills the gap.
+// traffic per tile at 128 B/clk against 512 clk of tensor pipe); now 80 KB.  The score products of tile j+1 overwrite P^T_j / dS^T_j, so
+// they are issued only after the accumulate products of tile j have completed; the second CTA of the SM fills the gap.
 // Backward kernels: EIGHT softmax warps (two threads per row, 32 of the tile's 64 columns each -- P and dS are element-wise given the saved
 // lse / delta, so the split needs no exchange): four warps per scheduler over the SM's two CTAs instead of two hide the TMEM-load and MUFU
 // latencies the one-thread-per-row version exposed (XU pipe 30 % busy, long-scoreboard stalls dominant; profiles/r02_ncu_attention.md).
@@ -750,6 +742,9 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       __syncwarp();
     };
     for (int j = 0; j < nt; ++j) {
+      // the score products overwrite P^T_{j-1} / dS^T_{j-1}: wait until the accumulate products that read them have completed
+      // (their commit on q_empty; issue order alone does not protect a TMEM A operand against a later accumulator write)
+      if (j > 0) ptx::mbar_wait(q_empty((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
       scores(j);
       accumulate(j);
     }
@@ -1060,14 +1055,14 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int h
     uint32_t box64[3] = {64u, 64u, 1u};
     if (int rc = tma_encode_bf16(&tmKV, qkv, 3, dims, strides, box64)) return rc;
     p.s_first = 1;
-    const size_t smem2 = kTile + 2 * KST * kHalfTile + 8 * (8 + 4 * KST) + 16 + 2 * 4 * 64 * sizeof(float);
+    const size_t smem2 = kTile + 2 * KST * kHalfTile + 8 * (8 + 4 * KST) + 16;
     static bool attr2 = false;
     if (!attr2) {
       SVL_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       attr2 = true;
     }
     dim3 grid2((L + TQ - 1) / TQ, heads, b);
-    attn_fwd_tc2_kernel<<<grid2, kThreads8, smem2, stream>>>(tm, tmKV, p);
+    attn_fwd_tc2_kernel<<<grid2, kThreads, smem2, stream>>>(tm, tmKV, p);
     SVL_LAUNCH_CHECK();
     return SVL_OK;
   }

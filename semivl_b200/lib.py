@@ -68,6 +68,8 @@ _lib.svl_attention_bwd_workspace.restype = C.c_size_t
 _lib.svl_attention_bwd_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
 _lib.svl_gn_workspace.restype = C.c_size_t
 _lib.svl_gn_workspace.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
+_lib.svl_bn_workspace.restype = C.c_size_t
+_lib.svl_bn_workspace.argtypes = [C.c_int64, C.c_int]
 _lib.svl_wgrad.restype = C.c_int
 _lib.svl_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
 
@@ -87,6 +89,14 @@ _PROTOS = {
     "svl_axpy": [_P, _P, _F, _L, _P],
     "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _F, _P],
     "svl_gn_relu_bwd": [_P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P],
+    "svl_stem_im2col": [_P, _P, _I, _L, _I, _I, _I, _I, _I, _P],
+    "svl_maxpool3s2_fwd": [_P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _I, _P],
+    "svl_maxpool3s2_bwd": [_P, _I, _L, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
+    "svl_bn_stats": [_P, _I, _L, _L, _I, _P, _P, _P],
+    "svl_bn_finalize": [_P, _F, _F, _F, _P, _P, _P, _P, _I, _P],
+    "svl_bn_apply": [_P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _I, _L, _I, _L, _I, _P],
+    "svl_bn_bwd_stats": [_P, _I, _L, _P, _I, _L, _P, _I, _L, _P, _P, _L, _I, _P, _P, _P],
+    "svl_bn_bwd_apply": [_P, _I, _L, _P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _F, _P, _I, _L, _P, _I, _L, _L, _I, _P],
     "svl_sim_im2col": [_P, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "svl_sim_col2im": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _P],
     "svl_map_sum": [_P, _I, _L, _P, _L, _I, _I, _F, _P],

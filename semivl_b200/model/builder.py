@@ -6,7 +6,7 @@ import torch
 from torch.nn import functional as F
 
 from ..registry import Config, build_segmentor
-from . import maskclip_vit, vlg_head, vlm  # noqa: F401  (register the types)
+from . import maskclip_vit, resnet, vlg_head, vlm  # noqa: F401  (register the types)
 from .vlg_head import upsample_bilinear
 from .vlm import VLM
 
@@ -36,12 +36,17 @@ def forward_wrapper(self, img, gt=None, need_fp=False, only_fp=False, forward_mo
         return F.dropout2d(f, self.fp_rate)
 
     x = self.extract_feat(img)
+    nf = len(x[0][0])
     if only_fp:
         x[0][0] = [drop(f, i) for i, f in enumerate(x[0][0])]
+        if x[2] is not None:                                          # conv-encoder features are perturbed too (builder.py:69-71)
+            x[2] = [drop(f, nf + i) for i, f in enumerate(x[2])]
     elif need_fp:
         x[0][0] = [torch.cat((f, drop(f, i))) for i, f in enumerate(x[0][0])]
         if x[0][1] is not None:
             x[0][1] = torch.cat((x[0][1], x[0][1]))
+        if x[2] is not None:                                          # builder.py:83-85
+            x[2] = [torch.cat((f, drop(f, nf + i))) for i, f in enumerate(x[2])]
     out = self._decode_head_forward_test(x, img_metas=None)
     if tuple(out.shape[2:]) != tuple(img.shape[2:]):           # identity resize otherwise (builder.py:93-97)
         out = upsample_bilinear(out, img.shape[2:])
@@ -58,7 +63,10 @@ def forward_lowres(self, img, need_fp=False, drop_masks=None):
             if drop_masks is not None:
                 return f * (drop_masks[i].to(f.device) / (1.0 - self.fp_rate))
             return F.dropout2d(f, self.fp_rate)
+        nf = len(x[0][0])
         x[0][0] = [torch.cat((f, drop(f, i))) for i, f in enumerate(x[0][0])]
+        if x[2] is not None:
+            x[2] = [torch.cat((f, drop(f, nf + i))) for i, f in enumerate(x[2])]
     return self.decode_head.forward_lowres(x)
 
 
@@ -99,9 +107,11 @@ def build_model(cfg):
     pmode = cfg.get('precise', False)
     if pmode not in (False, True, 'head', 'encoder'):
         raise ValueError(f"cfg['precise'] must be False, True, 'head' or 'encoder', got {pmode!r}")
-    for part in ('backbone', 'decode_head', 'clip_encoder'):
+    for part in ('backbone', 'decode_head', 'clip_encoder', 'conv_encoder'):
         if mmseg_cfg['model'].get(part) is not None:
             mmseg_cfg['model'][part]['precise'] = pmode is True or pmode == ('head' if part == 'decode_head' else 'encoder')
+    if 'conv_encoder_args' in cfg and mmseg_cfg['model'].get('conv_encoder') is not None:      # extension: e.g. dict(pretrained=None)
+        mmseg_cfg['model']['conv_encoder'].update(cfg['conv_encoder_args'])
     model = build_segmentor(mmseg_cfg.model, train_cfg=mmseg_cfg.get('train_cfg'), test_cfg=mmseg_cfg.get('test_cfg'))
     model.disable_dropout = cfg['disable_dropout']
     model.fp_rate = cfg['fp_rate']

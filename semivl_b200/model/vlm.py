@@ -31,7 +31,6 @@ class VLM(nn.Module):
         super().__init__()
         assert load_text_embedding == load_pl_text_embedding
         assert maskclip_class_filter is None and maskclip_trust_head is None and neck is None and auxiliary_head is None
-        assert conv_encoder is None, "conv_encoder (Cityscapes skr04) is not implemented yet (SURVEY.md §8f-1)"
         backbone = dict(backbone)
         if pretrained is not None:                        # mmseg EncoderDecoder pushes `pretrained` into the backbone cfg
             backbone["pretrained"] = pretrained
@@ -42,7 +41,7 @@ class VLM(nn.Module):
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.local_iter = 0
         self.clip_encoder = build_backbone(clip_encoder) if clip_encoder is not None else None
-        self.conv_encoder = None
+        self.conv_encoder = build_backbone(conv_encoder) if conv_encoder is not None else None          # model/vlm.py:50-52
         self.load_text_embedding = load_text_embedding
         self.decode_head.load_text_embedding = load_text_embedding
         self.load_mcc_text_embedding = load_mcc_text_embedding
@@ -56,12 +55,12 @@ class VLM(nn.Module):
 
     # ------------------------------------------------------------------ reference surface
     def init_weights(self):
-        for m in (self.backbone, self.decode_head, self.clip_encoder):
+        for m in (self.backbone, self.decode_head, self.clip_encoder, self.conv_encoder):
             if m is not None:
                 m.init_weights()
 
     def set_precise(self, precise):
-        for m in (self.backbone, self.decode_head, self.clip_encoder):
+        for m in (self.backbone, self.decode_head, self.clip_encoder, self.conv_encoder):
             if m is not None:
                 m.set_precise(precise)
 
@@ -88,10 +87,14 @@ class VLM(nn.Module):
         return self._text_cache[key]
 
     def extract_feat(self, img):
+        orig_img = img
         img = self.renormalize_img_for_clip(img)
         visual_feat = self.backbone(img)
         self.decode_head.load_text_embedding = self.load_text_embedding
-        return [visual_feat, self._text(img.device), None]
+        conv_feat = None
+        if self.conv_encoder is not None:                       # the conv encoder sees the ImageNet-normalised image (model/vlm.py:113,120-121)
+            conv_feat = list(self.conv_encoder(orig_img))
+        return [visual_feat, self._text(img.device), conv_feat]
 
     def _decode_head_forward_test(self, x, img_metas):
         return self.decode_head.forward(x, force_output_pred_masks=True)["pred_masks"]

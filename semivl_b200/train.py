@@ -69,10 +69,16 @@ CONF_MODES = {"pixelwise": 0, "pixelratio": 1, "pixelavg": 2}
 
 
 class OptimCfg:
+    """experiments.py:246-255: AdamW, one learning-rate class per key of `paramwise_cfg.custom_keys` that reaches a trainable tensor
+    (backbone, head, conv_encoder), uniform weight decay; poly decay over `scheduler_max_iters` (default: total_iters) after an optional
+    linear warm-up (semivl.py:338-345); `total_iters` also drives the MaskCLIP-lambda ramp (semivl.py:312-316)."""
+
     def __init__(self, lr=1e-4, weight_decay=0.01, backbone_lr_mult=0.01, head_lr_mult=10.0, betas=(0.9, 0.999), eps=1e-8,
-                 total_iters=1000, power=0.9):
-        self.lr, self.wd, self.bb_mult, self.head_mult = lr, weight_decay, backbone_lr_mult, head_lr_mult
+                 total_iters=1000, power=0.9, conv_encoder_lr_mult=0.1, warmup_iters=0, warmup_ratio=1e-6, scheduler_max_iters=None):
+        self.lr, self.wd, self.bb_mult, self.head_mult, self.ce_mult = lr, weight_decay, backbone_lr_mult, head_lr_mult, conv_encoder_lr_mult
         self.betas, self.eps, self.total_iters, self.power = betas, eps, total_iters, power
+        self.warmup_iters, self.warmup_ratio = warmup_iters, warmup_ratio
+        self.scheduler_max_iters = scheduler_max_iters if scheduler_max_iters is not None else total_iters
 
 
 class Trainer:
@@ -89,17 +95,20 @@ class Trainer:
         self.iters = 0
         bb = [(n, p) for n, p in model.backbone.named_parameters() if p.requires_grad]
         hd = [(n, p) for n, p in model.decode_head.named_parameters() if p.requires_grad]
+        conv = getattr(model, "conv_encoder", None)
+        ce = [(n, p) for n, p in conv.named_parameters() if p.requires_grad] if conv is not None else []
         self.n_bb = sum(p.numel() for _, p in bb)
         self.n_hd = sum(p.numel() for _, p in hd)
+        self.n_ce = sum(p.numel() for _, p in ce)
         dev = next(model.parameters()).device
-        n = self.n_bb + self.n_hd
+        n = self.n_bb + self.n_hd + self.n_ce
         self.p_flat = torch.empty(n, device=dev, dtype=torch.float32)
         self.g_flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m_flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v_flat = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.g_bb, self.g_hd = {}, {}
+        self.g_bb, self.g_hd, self.g_ce = {}, {}, {}
         off = 0
-        for group, gd in ((bb, self.g_bb), (hd, self.g_hd)):
+        for group, gd in ((bb, self.g_bb), (hd, self.g_hd), (ce, self.g_ce)):
             for name, p in group:
                 k = p.numel()
                 self.p_flat[off:off + k].copy_(p.data.reshape(-1))
@@ -111,8 +120,11 @@ class Trainer:
             # whatever each rank's RNG produced for the randomly initialised head; the Adam moments are zeros on every rank already
             dist.broadcast(self.p_flat, src=0)
         self.vit, self.head = model.backbone.engine, model.decode_head.engine
+        self.ce = conv.engine if conv is not None else None
         self.vit.cache.volatile = set(self.g_bb)
         self.head.cache.volatile = set(self.g_hd)
+        if self.ce is not None:
+            self.ce.cache.volatile = set(self.g_ce)
         self.world = _world()
         self._capturing, self._graph, self._graph_key, self._hyper = False, None, None, None
         self.exchange = GradExchange(self.g_flat)
@@ -141,15 +153,31 @@ class Trainer:
     def _ph(self):
         return {n: p.data for n, p in self.model.decode_head.named_parameters()}
 
+    def _pc(self):
+        """conv-encoder parameters and BatchNorm buffers (running statistics are updated in place by training-mode passes)"""
+        c = self.model.conv_encoder
+        d = {n: p.data for n, p in c.named_parameters()}
+        d.update({n: b for n, b in c.named_buffers() if "num_batches_tracked" not in n})
+        return d
+
     def lr_at(self, it):
-        """Base learning rate used BY optimizer step number `it` (1-based).  semivl.py:338-345 rewrites the rate after each
-        optimizer.step() from the 0-based iteration index of the step just taken: step 1 and step 2 run at the initial rate, step
-        `it` at lr * (1 - (it - 2) / total) ** 0.9."""
+        """Base learning-rate FACTOR times lr used BY optimizer step number `it` (1-based).  semivl.py:338-345 rewrites the rate after each
+        optimizer.step() from the 0-based index i of the iteration just run -- linear warm-up `1 - (1 - i / warmup_iters) * (1 - warmup_ratio)`
+        while i < warmup_iters, else poly `(1 - i / scheduler_max_iters) ** 0.9` -- so step 1 runs at the initial rate and step `it` >= 2 at
+        the rate written after iteration i = it - 2."""
         o = self.opt
-        return o.lr * (1.0 - max(it - 2, 0) / o.total_iters) ** o.power
+        if it <= 1:
+            return o.lr
+        i = it - 2
+        if i < o.warmup_iters:
+            return o.lr * (1.0 - (1.0 - i / o.warmup_iters) * (1.0 - o.warmup_ratio))
+        return o.lr * (1.0 - i / o.scheduler_max_iters) ** o.power
 
     def _head_grads_final(self):
         self.exchange.reduce(self.n_bb, self.n_bb + self.n_hd)
+
+    def _conv_grads_final(self):
+        self.exchange.reduce(self.n_bb + self.n_hd, self.n_bb + self.n_hd + self.n_ce)
 
     def _layer_grads_final(self, i):
         """called by the encoder backward after layer i's weight gradients are complete (layers run 11 -> 0)"""
@@ -158,29 +186,36 @@ class Trainer:
             self._bucket_hi = self.layer_lo[i]
 
     def _step_scalars(self, it):
-        """(lr of the backbone class, lr of the head class, 1 - beta1^t, sqrt(1 - beta2^t)) of optimizer step number `it` (1-based)."""
+        """(lr of the backbone class, lr of the head class, 1 - beta1^t, sqrt(1 - beta2^t), lr of the conv-encoder class) of optimizer step
+        number `it` (1-based) -- the device vector svl_adamw_dev reads (lr_index 0, 1 and 4)."""
         o = self.opt
         base = self.lr_at(it)
-        return base * o.bb_mult, base * o.head_mult, 1.0 - o.betas[0] ** it, (1.0 - o.betas[1] ** it) ** 0.5
+        return base * o.bb_mult, base * o.head_mult, 1.0 - o.betas[0] ** it, (1.0 - o.betas[1] ** it) ** 0.5, base * o.ce_mult
 
     def optimizer_step(self):
         self.exchange.finish()                                        # sum over ranks; the mean is folded into gscale below
         self._bucket_hi = self._layers_end
         o, gs, nb = self.opt, 1.0 / self.world, self.n_bb
+        classes = [(0, nb, 0, o.bb_mult), (nb, self.n_hd, 1, o.head_mult)]          # (offset, length, lr_index of svl_adamw_dev, lr multiplier)
+        if self.n_ce:
+            classes.append((nb + self.n_hd, self.n_ce, 4, o.ce_mult))
         if self._capturing:
             # inside a CUDA-graph capture: per-step scalars come from device memory (self._hyper), host counters move at replay time
-            for lo, k, idx in ((0, nb, 0), (nb, self.n_hd, 1)):
+            for lo, k, idx, _ in classes:
                 L.call("svl_adamw_dev", self.p_flat[lo:], self.g_flat[lo:], self.m_flat[lo:], self.v_flat[lo:], k, self._hyper, idx, o.betas[0],
                        o.betas[1], o.eps, o.wd, gs)
             return
         self.iters += 1
         lr = self.lr_at(self.iters)
-        L.call("svl_adamw", self.p_flat, self.g_flat, self.m_flat, self.v_flat, nb, lr * o.bb_mult, o.betas[0], o.betas[1], o.eps, o.wd,
-               self.iters, gs)
-        L.call("svl_adamw", self.p_flat[nb:], self.g_flat[nb:], self.m_flat[nb:], self.v_flat[nb:], self.n_hd, lr * o.head_mult, o.betas[0],
-               o.betas[1], o.eps, o.wd, self.iters, gs)
-        self.vit.cache.bump()
-        self.head.cache.bump()
+        for lo, k, _, mult in classes:
+            L.call("svl_adamw", self.p_flat[lo:], self.g_flat[lo:], self.m_flat[lo:], self.v_flat[lo:], k, lr * mult, o.betas[0], o.betas[1],
+                   o.eps, o.wd, self.iters, gs)
+        self._bump_caches()
+
+    def _bump_caches(self):
+        for e in (self.vit, self.head, self.ce):
+            if e is not None:
+                e.cache.bump()
 
     # ------------------------------------------------------------------ CUDA-graph replay of the supervised step
     def graphed_supervised_step(self, img, mask):
@@ -192,10 +227,9 @@ class Trainer:
         key = (tuple(img.shape), tuple(mask.shape))
         if self._graph is None or self._graph_key != key:
             self._g_img, self._g_mask = img.clone(), mask.clone()
-            self._hyper = torch.zeros(4, device=img.device)
+            self._hyper = torch.zeros(5, device=img.device)
             self.supervised_step(self._g_img, self._g_mask, update=False)        # eager pass: frozen-weight operand cache, lazy attributes
-            self.vit.cache.bump()                                                 # trainable-weight casts must be part of the graph
-            self.head.cache.bump()
+            self._bump_caches()                                                   # trainable-weight casts must be part of the graph
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             self._capturing, l0 = True, L.launches
@@ -212,8 +246,7 @@ class Trainer:
         self._graph.replay()
         L.launches += self._graph_launches
         self.iters += 1
-        self.vit.cache.bump()                       # the cached operand copies now belong to the graph: eager calls must re-cast
-        self.head.cache.bump()
+        self._bump_caches()                         # the cached operand copies now belong to the graph: eager calls must re-cast
         return self._g_loss
 
     @staticmethod
@@ -237,7 +270,12 @@ class Trainer:
         self.exchange.begin()
         pb, ph = self._pb(), self._ph()
         feats, _, vctx = self.vit.forward(m.renormalize_img_for_clip(img), pb, need_grad=True, want_global=False)
-        low, hctx = self.head.forward(feats, text, ph, need_grad=True)
+        conv_feats = cctx = None
+        if self.ce is not None:                    # skr04: the conv encoder sees the ImageNet-normalised image (model/vlm.py:113,120-121)
+            pc, csync = self._pc(), m.conv_encoder.sync
+            cf, cctx = self.ce.forward(img, pc, training=True, need_grad=True, sync=csync)
+            conv_feats = [cf]
+        low, hctx = self.head.forward(feats, text, ph, need_grad=True, conv_feats=conv_feats)
         R, N, hl, wl = low.shape
         cnt, coef, loss = self._f(1), self._f(1), self._f(3)
         L.call("svl_count_valid", mask, mask.numel(), 255, cnt)
@@ -248,6 +286,12 @@ class Trainer:
         del hctx
         if update:
             self._head_grads_final()
+        if cctx is not None:                       # [taps..., embedding, conv feature]: the conv encoder's backward does not depend on the ViT's
+            self.ce.backward(cctx, dfe[len(feats)], pc, self.g_ce, sync=csync)
+            del cctx
+            if update:
+                self._conv_grads_final()
+            dfe = dfe[:len(feats)]
         self.vit.backward(vctx, dfe, pb, self.g_bb, on_layer_done=self._layer_grads_final if update else None)
         del vctx
         if update:
@@ -289,16 +333,20 @@ class Trainer:
         L.call("svl_cutmix_img", batch["img_s2"], batch["img_s2_other"], batch["mix2"], img_s2, b, 3, H * W)
         # ---- teacher passes (no grad)
         fo, _, _ = self.vit.forward(m.renormalize_img_for_clip(batch["img_w_other"]), pb, need_grad=False, want_global=False)
+        cf_o = None
+        if self.ce is not None:                    # model.eval() for the teacher pass (semivl.py:228-232): running BatchNorm statistics
+            pc, csync = self._pc(), m.conv_encoder.sync
+            cf_o, _ = self.ce.forward(batch["img_w_other"], pc, training=False, need_grad=False)
         N, hl, wl = text.shape[0], 4 * fo[-1].shape[1], 4 * fo[-1].shape[2]
         chunk = self._head_chunk(N, hl, wl)
         conf_o = torch.empty(b, H, W, device=dev)
         lab_o = torch.empty(b, H, W, device=dev, dtype=torch.int64)
         for i0 in range(0, b, 4 * chunk):                           # nothing is saved in a no-grad pass: 4x larger groups
             i1 = min(b, i0 + 4 * chunk)
-            low_o, _ = self.head.forward([f[i0:i1] for f in fo], text, ph, need_grad=False)
+            low_o, _ = self.head.forward([f[i0:i1] for f in fo], text, ph, need_grad=False, conv_feats=None if cf_o is None else [cf_o[i0:i1]])
             L.call("svl_softmax_max", low_o, conf_o[i0:i1], lab_o[i0:i1], i1 - i0, N, hl, wl, H, W, 1.0, 0.0)
             del low_o
-        del fo
+        del fo, cf_o
         mclip = mclip_o = None
         if lam != 0:
             mc = m.forward_maskclip(torch.cat((batch["img_w"], batch["img_w_other"])), hp["mcc_conf_thresh"])
@@ -308,8 +356,18 @@ class Trainer:
         # ---- student passes
         imgs = torch.cat((batch["img_x"], batch["img_w"], img_s1, img_s2))
         feats, _, vctx = self.vit.forward(m.renormalize_img_for_clip(imgs), pb, need_grad=True, want_global=False)
+        cf = cctx = None
+        if self.ce is not None:
+            # two training-mode calls like the reference's two student forwards (semivl.py:245-249): the BatchNorm statistics of (x | w) and
+            # of (s1 | s2) are separate batches (and the running statistics move twice per step)
+            cfa, ctx_a = self.ce.forward(imgs[:2 * b], pc, training=True, need_grad=True, sync=csync)
+            cfb, ctx_b = self.ce.forward(imgs[2 * b:], pc, training=True, need_grad=True, sync=csync)
+            cf, cctx = torch.cat((cfa, cfb)), (ctx_a, ctx_b)
+            del cfa, cfb
+        nfe = len(feats)
+        pert = list(feats) + ([cf] if cf is not None else [])          # every feature the perturbed pass drops channels of (builder.py:78-85)
         if drop_masks is None:
-            drop_masks = [torch.bernoulli(torch.full((b, f.shape[-1]), 1.0 - m.fp_rate, device=dev)) for f in feats]
+            drop_masks = [torch.bernoulli(torch.full((b, f.shape[-1]), 1.0 - m.fp_rate, device=dev)) for f in pert]
         scale = 1.0 / (1.0 - m.fp_rate)
         dm = [(dmk.reshape(b, 1, 1, -1).to(dev) * scale) for dmk in drop_masks]
         # pseudo-labels of the weak views (pred_w.detach().softmax.max, semivl.py:251-252): no gradient ever reaches these rows
@@ -317,7 +375,8 @@ class Trainer:
         lab_w = torch.empty(b, H, W, device=dev, dtype=torch.int64)
         for i0 in range(0, b, 4 * chunk):                           # nothing is saved in a no-grad pass: 4x larger groups
             i1 = min(b, i0 + 4 * chunk)
-            low_w, _ = self.head.forward([f[b + i0:b + i1] for f in feats], text, ph, need_grad=False)
+            low_w, _ = self.head.forward([f[b + i0:b + i1] for f in feats], text, ph, need_grad=False,
+                                         conv_feats=None if cf is None else [cf[b + i0:b + i1]])
             L.call("svl_softmax_max", low_w, conf_w[i0:i1], lab_w[i0:i1], i1 - i0, N, hl, wl, H, W, 1.0, 0.0)
             del low_w
         # ---- targets (cutmix of pseudo-labels, confidences, ignore masks; confidence weights per cfg['conf_mode'])
@@ -385,15 +444,15 @@ class Trainer:
             ls[key] = self._f(3)
             groups.append((r0, None, t, ls[key]))
         # ---- gradient-tracked head passes, one image group at a time: forward -> fused upsample + CE (loss and d_low) -> backward
-        dfe = [torch.zeros(4 * b, *f.shape[1:], device=dev, dtype=torch.float32) for f in feats]
+        dfe = [torch.zeros(4 * b, *f.shape[1:], device=dev, dtype=torch.float32) for f in pert]
         sl = lambda t, i0, i1: None if t is None else t[i0:i1]
         for r0, scale_k, targets, acc in groups:
             for i0 in range(0, b, chunk):
                 i1 = min(b, i0 + chunk)
-                hf = [f[r0 + i0:r0 + i1] for f in feats]
+                hf = [f[r0 + i0:r0 + i1] for f in pert]
                 if scale_k is not None:                     # feature perturbation of the weak views (builder.py:78-85)
                     hf = [f * k[i0:i1] for f, k in zip(hf, scale_k)]
-                low, hctx = self.head.forward(hf, text, ph, need_grad=True)
+                low, hctx = self.head.forward(hf[:nfe], text, ph, need_grad=True, conv_feats=hf[nfe:] or None)
                 del hf
                 d_low = torch.zeros_like(low)
                 self._ce(low, d_low, i1 - i0, N, hl, wl, H, W, [(sl(lb, i0, i1), sl(wg, i0, i1), cf) for lb, wg, cf in targets], acc)
@@ -409,6 +468,13 @@ class Trainer:
         # ---- encoder backward
         if update:
             self._head_grads_final()
+        if cctx is not None:
+            d_cf = dfe.pop()
+            self.ce.backward(cctx[0], d_cf[:2 * b], pc, self.g_ce, sync=csync)
+            self.ce.backward(cctx[1], d_cf[2 * b:], pc, self.g_ce, sync=csync)
+            del cctx, d_cf
+            if update:
+                self._conv_grads_final()
         self.vit.backward(vctx, dfe, pb, self.g_bb, on_layer_done=self._layer_grads_final if update else None)
         del vctx
         if update:

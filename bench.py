@@ -29,13 +29,14 @@ sys.path.insert(0, ROOT)
 # images, which the reference computes and discards, semivl.py:247: 12 631 - 1 485.9 and 14 180 - 1 312.4)
 CONFIGS = {
     2: dict(name="VOC 21-class synthetic 512x512", dataset="pascal", nclass=21, crop=512, batch=16, workload="supervised", gf_per_img=831.5),
-    3: dict(name="Cityscapes 19-class synthetic 801x801", dataset="cityscapes", nclass=19, crop=801, batch=2, workload="supervised", gf_per_img=2487.5),
+    # config 3 runs the reference's real Cityscapes model (skr04: + ResNetV1c stem / layer1 conv encoder with SyncBN, 26.4 GF forward at 801^2)
+    3: dict(name="Cityscapes 19-class synthetic 801x801", dataset="cityscapes", nclass=19, crop=801, batch=2, workload="supervised", gf_per_img=2487.5 + 79.0),
     4: dict(name="ADE20K 150-class synthetic 512x512", dataset="ade", nclass=150, crop=512, batch=8, workload="semivl", gf_per_img=11145.1),
     5: dict(name="COCO 81-class synthetic 641x641", dataset="coco", nclass=81, crop=641, batch=16, workload="semivl", gf_per_img=12867.6),
 }
 GF_PER_UNIT_SEMIVL_VOC = 4542.0 - 208.7
 DATASET_OF = {21: "pascal", 19: "cityscapes", 150: "ade", 81: "coco"}
-TEXT_OF = {"pascal": "voc12_wbg_single", "cityscapes": "cityscapes_single", "ade": "ade_single", "coco": "coco_single"}
+TEXT_OF = {"pascal": "voc12_wbg_single", "cityscapes": "cityscapes_conceptavg3_single", "ade": "ade_single", "coco": "coco_single"}
 
 
 def parse():
@@ -72,6 +73,11 @@ def parse():
 
 
 def model_cfg(args, precise):
+    if args.dataset == "cityscapes":      # experiments.py:428-456: skr04 model, concept-averaged text table, CLIP re-normalisation
+        return dict(model='mmseg.vlm-vlg-aspp-s2p4-skr04-ftap-mcvitb', nclass=args.nclass, crop_size=args.crop, dataset=args.dataset,
+                    text_embedding_variant='conceptavg3_single', mcc_text='concept3_single', pl_text='conceptavg3_single', clip_encoder='mcvit16',
+                    disable_dropout=True, fp_rate=0.5, model_args=dict(pretrained=None, renorm_clip_img=True),
+                    clip_encoder_args=dict(pretrained=None), conv_encoder_args=dict(pretrained=None), precise=precise)
     return dict(model='mmseg.vlm-vlg-aspp-s2p4-sk04-ftap-mcvitb', nclass=args.nclass, crop_size=args.crop, dataset=args.dataset,
                 text_embedding_variant='single', mcc_text='single', pl_text='single', clip_encoder='mcvit16', disable_dropout=True,
                 fp_rate=0.5, model_args=dict(pretrained=None), clip_encoder_args=dict(pretrained=None), precise=precise)
@@ -248,18 +254,36 @@ def parity_block(torch, args, model, label):
     own init_weights leaves the random head so close to class-degenerate that an arg-max comparison says nothing."""
     import numpy as np
     from oracle import semivl_oracle as O
-    mc = O.ModelCfg(img_size=args.crop, num_classes=args.nclass)
-    sd = O.fixture_state_dict(O.param_shapes(mc, with_clip_encoder=False), seed=0)
+    skr04 = getattr(model, "conv_encoder", None) is not None
+    mc = O.ModelCfg(img_size=args.crop, num_classes=args.nclass, **(dict(out_indices=(4, 12), skip_channels=(32, 32)) if skr04 else {}))
+    shapes = O.param_shapes(mc, with_clip_encoder=False)
+    if skr04:
+        from oracle import resnetv1c_oracle as R
+        shapes["decode_head.skip_proj.1.0.weight"] = (32, 256, 3, 3)
+    sd = O.fixture_state_dict(shapes, seed=0)
+    if skr04:
+        sd.update(R.fixture_params(2, pre="conv_encoder."))
     model.load_state_dict(sd, strict=False)
-    for part in (model.backbone, model.decode_head):
-        part.engine.cache.clear()
+    for part in (model.backbone, model.decode_head, getattr(model, "conv_encoder", None)):
+        if part is not None:
+            part.engine.cache.clear()
+    model.eval()                                  # BatchNorm of the conv encoder: running statistics on both sides
     text = torch.from_numpy(np.load(os.path.join(ROOT, "semivl_b200", "configs", "_base_", "datasets", "text_embedding", TEXT_OF[args.dataset] + ".npy")))
     img = synth_batch(torch, 1, args.crop, args.nclass, 4321, "cpu", False)["img_x"]
     torch.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     with torch.no_grad():
-        ref = O.model_forward(img, sd, text, mc)
+        if skr04:
+            import torch.nn.functional as F
+            t = lambda v: torch.tensor(v).view(1, -1, 1, 1)
+            clip_img = (img * t([0.229, 0.224, 0.225]) + t([0.485, 0.456, 0.406]) - t([0.48145466, 0.4578275, 0.40821073])) / t([0.26862954, 0.26130258, 0.27577711])
+            feats, _ = O.vit_forward(clip_img, sd, mc)
+            low = O.vlg_head_forward(feats, text, sd, mc, conv_feats=R.conv_encoder_forward(img, sd, training=False))
+            ref = F.interpolate(low, size=img.shape[2:], mode="bilinear", align_corners=False)
+        else:
+            ref = O.model_forward(img, sd, text, mc)
         y = model(img.cuda()).float().cpu()
+    model.train()
     err = (y - ref).abs().max().item()
     top2 = ref.topk(2, dim=1).values
     dec = (top2[:, 0] - top2[:, 1]) > 2 * err

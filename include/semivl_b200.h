@@ -328,7 +328,8 @@ int svl_crop_flip_mask(const uint8_t* src, int sh, int sw, int64_t* dst, int64_t
                        void* stream);
 int svl_cutmix_box(float* box, int size, int bx, int by, int bw, int bh, void* stream);
 
-/* svl_adamw with the per-step scalars in DEVICE memory: hyper = {lr of class 0, lr of class 1, 1 - beta1^t, sqrt(1 - beta2^t)};
+/* svl_adamw with the per-step scalars in DEVICE memory: hyper = {lr of class 0, lr of class 1, 1 - beta1^t, sqrt(1 - beta2^t), lr of class 4, ...}
+ * (lr_index 0, 1 or >= 4: further learning-rate classes follow the two bias corrections, e.g. the conv_encoder class of the skr04 model);
  * lets a captured CUDA graph of the whole training step be replayed under the poly LR schedule (semivl.py:338-345). */
 int svl_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int lr_index, float beta1, float beta2,
                   float eps, float wd, float gscale, void* stream);

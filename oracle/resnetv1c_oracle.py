@@ -75,3 +75,22 @@ def param_shapes(pre="conv_encoder.", blocks=3):
             for leaf in ("weight", "bias", "running_mean", "running_var"):
                 s[b + "downsample.1." + leaf] = (256,)
     return s
+
+
+def fixture_params(seed=0, pre=""):
+    """Seeded test weights: He-scaled convolutions, BatchNorm gains around 1, non-trivial running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+    for k, s in param_shapes(pre=pre).items():
+        if k.endswith("running_var"):
+            p[k] = torch.rand(s, generator=g) + 0.5
+        elif k.endswith("running_mean"):
+            p[k] = torch.randn(s, generator=g) * 0.1
+        elif len(s) == 1 and k.endswith("weight"):
+            p[k] = 1.0 + 0.2 * torch.randn(s, generator=g)
+        elif len(s) == 1:
+            p[k] = 0.2 * torch.randn(s, generator=g)
+        else:
+            fan = s[1] * s[2] * s[3]
+            p[k] = torch.randn(s, generator=g) * (2.0 / fan) ** 0.5
+    return p

@@ -483,7 +483,7 @@ __global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict_
 }
 extern "C" int svl_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int lr_index, float beta1,
                              float beta2, float eps, float wd, float gscale, void* stream) {
-  SVL_CHECK_ARG(p && g && m && v && hyper && (lr_index == 0 || lr_index == 1), "svl_adamw_dev: bad arguments");
+  SVL_CHECK_ARG(p && g && m && v && hyper && (lr_index == 0 || lr_index == 1 || lr_index >= 4), "svl_adamw_dev: bad arguments");
   if (n == 0) return SVL_OK;
   adamw_dev_kernel<<<ew_grid(n), 256, 0, ST>>>(p, g, m, v, n, hyper, lr_index, beta1, beta2, eps, wd, gscale == 0.f ? 1.f : gscale);
   SVL_LAUNCH_CHECK();

@@ -21,7 +21,7 @@ def sync_sums(t, count):
     returns the global row count.  One process: identity."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return count
-    buf = torch.cat((t.reshape(-1), torch.tensor([float(count)], device=t.device, dtype=t.dtype)))
+    buf = torch.cat((t.reshape(-1), torch.full((1,), float(count), device=t.device, dtype=t.dtype)))     # a fill kernel: capturable in a CUDA graph
     dist.all_reduce(buf)
     t.copy_(buf[:-1].view_as(t))
     return float(buf[-1].item()) if t.device.type == "cpu" else _count_of(buf, count)

@@ -65,11 +65,17 @@ class VLM(nn.Module):
                 m.set_precise(precise)
 
     def renormalize_img_for_clip(self, img):
+        """model/vlm.py:69-78: undo the ImageNet normalisation, apply CLIP's.  The six constants live on the device (cached per device on
+        first use, so that a captured CUDA graph of the step contains no host -> device copy)."""
         if not self.renorm_clip_img:
             return img
-        t = lambda v: torch.tensor(v, device=img.device).view(1, -1, 1, 1)
-        return (img * t([0.229, 0.224, 0.225]) + t([0.485, 0.456, 0.406]) - t([0.48145466, 0.4578275, 0.40821073])) / \
-            t([0.26862954, 0.26130258, 0.27577711])
+        key = ("renorm", str(img.device))
+        if key not in self._text_cache:
+            t = lambda v: torch.tensor(v, device=img.device).view(1, -1, 1, 1)
+            self._text_cache[key] = tuple(t(v) for v in ([0.229, 0.224, 0.225], [0.485, 0.456, 0.406], [0.48145466, 0.4578275, 0.40821073],
+                                                        [0.26862954, 0.26130258, 0.27577711]))
+        s_in, m_in, m_clip, s_clip = self._text_cache[key]
+        return (img * s_in + m_in - m_clip) / s_clip
 
     def freeze(self, model, exclude_keys=None):
         for n, m in model.named_parameters():

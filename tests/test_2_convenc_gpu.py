@@ -15,21 +15,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 
 def _params(seed=0):
     from oracle import resnetv1c_oracle as R
-    g = torch.Generator().manual_seed(seed)
-    p = {}
-    for k, s in R.param_shapes(pre="").items():
-        if k.endswith("running_var"):
-            p[k] = torch.rand(s, generator=g) + 0.5
-        elif k.endswith("running_mean"):
-            p[k] = torch.randn(s, generator=g) * 0.1
-        elif len(s) == 1 and k.endswith("weight"):
-            p[k] = 1.0 + 0.2 * torch.randn(s, generator=g)
-        elif len(s) == 1:
-            p[k] = 0.2 * torch.randn(s, generator=g)
-        else:
-            fan = s[1] * s[2] * s[3]
-            p[k] = torch.randn(s, generator=g) * (2.0 / fan) ** 0.5
-    return p
+    return R.fixture_params(seed)
 
 
 def _rel(a, b):
@@ -139,3 +125,120 @@ def test_skr04_model_matches_oracle(text_dir, precise):
                 nr = gr.norm().item()
                 if nr > 1e-9:
                     assert abs(gv.double().norm().item() - nr) <= 5e-2 * nr, (k, gv.norm().item(), nr)
+
+
+def _skr04(crop, nclass, precise, b_seed=0):
+    from oracle import semivl_oracle as O
+    from semivl_b200.model import build_model
+    cfg = dict(model='mmseg.vlm-vlg-aspp-s2p4-skr04-ftap-mcvitb', nclass=nclass, crop_size=crop, dataset='cityscapes', text_embedding_variant='conceptavg3_single',
+               mcc_text='concept3_single', pl_text='conceptavg3_single', clip_encoder='mcvit16', disable_dropout=True, fp_rate=0.5,
+               model_args=dict(pretrained=None, renorm_clip_img=True), clip_encoder_args=dict(pretrained=None), conv_encoder_args=dict(pretrained=None),
+               precise=precise)
+    m = build_model(cfg)
+    mc = O.ModelCfg(img_size=crop, num_classes=nclass, out_indices=(4, 12), skip_channels=(32, 32))
+    shapes = O.param_shapes(mc)
+    shapes["decode_head.skip_proj.1.0.weight"] = (32, 256, 3, 3)
+    sd = O.fixture_state_dict(shapes, seed=0)
+    sd.update({"conv_encoder." + k: v for k, v in _params(2).items()})
+    m.load_state_dict(sd, strict=False)
+    return m.cuda(), mc, sd
+
+
+def test_trainer_steps_with_conv_encoder():
+    """The fused training steps of the skr04 model (Trainer: flat buffer with a third learning-rate class for conv_encoder.*, conv-encoder
+    passes scheduled around the head) against the same loss composed from the public modules + torch autograd (an independent schedule over
+    the same kernels): supervised step and the full SemiVL step (two training-mode conv-encoder calls, (x | w) and (s1 | s2), like the
+    reference's two student forwards; eval-mode teacher pass), precise mode."""
+    import torch.nn.functional as F
+    from oracle.make_golden import synth_batch
+    from semivl_b200.train import OptimCfg, Trainer
+    crop, nclass, b = 64, 19, 2
+    m, mc, sd = _skr04(crop, nclass, True)
+    m.train()
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(b, 3, crop, crop, generator=g).cuda()
+    lab = torch.randint(0, nclass, (b, crop, crop), generator=g).cuda()
+    lab[:, :7, :9] = 255
+    # ---- supervised step
+    rm0 = m.conv_encoder.stem[1].running_mean.clone()
+    loss_ref = F.cross_entropy(m(img), lab, ignore_index=255)
+    loss_ref.backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert any(k.startswith("conv_encoder.") for k in ref)
+    assert not torch.equal(m.conv_encoder.stem[1].running_mean, rm0)            # training-mode pass moved the running statistics
+    tr = Trainer(m, OptimCfg(lr=5e-5, backbone_lr_mult=0.1, conv_encoder_lr_mult=0.1))
+    assert tr.n_ce == sum(p.numel() for p in m.conv_encoder.parameters())
+    loss = tr.supervised_step(img, lab, update=False)
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * loss_ref.item()
+    for prefix, gd in (("backbone.", tr.g_bb), ("decode_head.", tr.g_hd), ("conv_encoder.", tr.g_ce)):
+        for k, gv in gd.items():
+            gr = ref[prefix + k]
+            assert (gv - gr).norm().item() <= 1e-3 * gr.norm().item() + 1e-6, (prefix + k, gv.norm().item(), gr.norm().item())
+    # one optimizer step: the conv-encoder class moves at lr * 0.1
+    before = tr.p_flat.clone()
+    tr.supervised_step(img, lab, update=True)
+    lo = tr.n_bb + tr.n_hd
+    d_ce = (tr.p_flat[lo:] - before[lo:]).abs().max().item()
+    assert 0.5 * 5e-6 < d_ce < 1.5 * 5e-6 + 1e-2 * 5e-6 * before[lo:].abs().max().item()
+    # ---- SemiVL step vs the module composition (semivl.py:224-323 driven on the public API, injected dropout2d masks)
+    batch = {k: v.cuda() for k, v in synth_batch(b, crop, nclass, 31).items()}
+    gm = torch.Generator().manual_seed(32)
+    masks = [(torch.rand(b, c, generator=gm) >= 0.5).float().cuda() for c in (768, 512, 256)]
+    hp = dict(conf_thresh=1.0 / nclass + 2e-3, conf_mode="pixelavg", mcc_conf_thresh=1.0 / nclass + 1e-3, mcc_loss_reduce="mean_all", mcc_lambda=0.0)
+    tr = Trainer(m, OptimCfg(), hp=hp)
+    buffers = {n: b_.clone() for n, b_ in m.conv_encoder.named_buffers()}       # the teacher pass reads the running statistics: same start for both
+    total, terms = tr.semivl_step(batch, drop_masks=masks, update=False)
+    got = {n: v.clone() for d, pre in ((tr.g_bb, "backbone."), (tr.g_hd, "decode_head."), (tr.g_ce, "conv_encoder.")) for n, v in ((pre + k, t) for k, t in d.items())}
+    # reference composition
+    from semivl_b200.model.builder import forward_wrapper
+    for p_ in m.parameters():
+        p_.grad = None
+    after = {n: b_.clone() for n, b_ in m.conv_encoder.named_buffers()}
+    for n, b_ in m.conv_encoder.named_buffers():
+        b_.copy_(buffers[n])
+    bt = {k: v.clone() for k, v in batch.items()}
+    box1, box2 = bt["mix1"].bool(), bt["mix2"].bool()
+    bt["img_s1"][box1.unsqueeze(1).expand_as(bt["img_s1"])] = bt["img_s1_other"][box1.unsqueeze(1).expand_as(bt["img_s1"])]
+    bt["img_s2"][box2.unsqueeze(1).expand_as(bt["img_s2"])] = bt["img_s2_other"][box2.unsqueeze(1).expand_as(bt["img_s2"])]
+    with torch.no_grad():
+        m.eval()
+        conf_o, mask_o = m(bt["img_w_other"]).softmax(1).max(1)
+    m.train()
+    # keep masks of the perturbed copy of (x | w): the labelled half is discarded by the loss (semivl.py:247), the weak half gets `masks`
+    preds, preds_fp = m(torch.cat((bt["img_x"], bt["img_w"])), need_fp=True,
+                        drop_masks=[torch.cat((torch.ones_like(q), q)).view(2 * b, -1, 1, 1) for q in masks])
+    pred_x, pred_w = preds.chunk(2)
+    _, pred_w_fp = preds_fp.chunk(2)
+    pred_s1, pred_s2 = m(torch.cat((bt["img_s1"], bt["img_s2"]))).chunk(2)
+    conf_w, mask_w = pred_w.detach().softmax(1).max(1)
+    mix = lambda a, o, bx: torch.where(bx, o, a)
+    mm1, mm2 = mix(mask_w, mask_o, box1), mix(mask_w, mask_o, box2)
+    cm1, cm2 = mix(conf_w, conf_o, box1), mix(conf_w, conf_o, box2)
+    im1, im2 = mix(bt["ignore_mask"], bt["ignore_mask_other"], box1), mix(bt["ignore_mask"], bt["ignore_mask_other"], box2)
+
+    def cw(loss, conf, ign):                                   # confidence_weighted_loss, conf_mode='pixelavg' (utils/train_utils.py:43-46)
+        valid = ign != 255
+        avg_conf = (conf * valid).sum(dim=(1, 2), keepdim=True) / valid.sum(dim=(1, 2), keepdim=True)
+        return (loss.sum() * avg_conf).sum() / valid.sum()
+    ce = lambda pr, tg: F.cross_entropy(pr, tg, reduction="none")
+    l_x = F.cross_entropy(pred_x, bt["mask_x"], ignore_index=255)
+    l_s1, l_s2 = cw(ce(pred_s1, mm1), cm1, im1), cw(ce(pred_s2, mm2), cm2, im2)
+    l_fp = cw(ce(pred_w_fp, mask_w), conf_w, bt["ignore_mask"])
+    loss_ref = (l_x + 0.25 * l_s1 + 0.25 * l_s2 + 0.5 * l_fp) / 2.0
+    loss_ref.backward()
+    print("semivl skr04: fused", total.item(), "module composition", loss_ref.item())
+    for n, b_ in m.conv_encoder.named_buffers():                # two training-mode conv-encoder calls in both schedules: same running statistics
+        if "num_batches" not in n:
+            assert torch.allclose(b_, after[n], rtol=1e-4, atol=1e-6), n
+    assert abs(total.item() - loss_ref.item()) < 2e-4 * loss_ref.item()
+    worst = 0.0
+    for n, p_ in m.named_parameters():
+        if p_.grad is not None and n in got:
+            gr = p_.grad
+            if gr.norm().item() < 1e-5:            # e.g. head.bias: one bias shared by all class maps, softmax gradients sum to zero over the classes
+                assert (got[n] - gr).norm().item() < 1e-5, n
+                continue
+            e = (got[n] - gr).norm().item() / gr.norm().item()
+            worst = max(worst, e)
+            assert e < 2e-2, (n, e)
+    print("semivl skr04: worst relative gradient difference fused vs module composition", worst)

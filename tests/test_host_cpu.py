@@ -164,7 +164,8 @@ def test_poly_lr_schedule_matches_reference_order(built):
         seen.append(lr)
         lr = O.poly_lr(1e-4, i, 50)
     assert np.allclose([tr.lr_at(it) for it in range(1, 11)], seen, rtol=1e-12)
-    a, b_, bc1, bc2s = tr._step_scalars(3)
+    a, b_, bc1, bc2s, c_ = tr._step_scalars(3)
+    assert np.isclose(c_, seen[2] * 0.1)
     assert np.isclose(a, seen[2] * 0.01) and np.isclose(b_, seen[2] * 10.0)
     assert np.isclose(bc1, 1 - 0.9 ** 3) and np.isclose(bc2s, (1 - 0.999 ** 3) ** 0.5)
 
@@ -359,3 +360,49 @@ def test_trainer_broadcasts_initial_parameters_gloo_world2(built):
     assert res[0][0] != res[1][0], "the two ranks were meant to start from different random heads"
     assert res[0][1] == res[1][1]                 # sampled entries + sums of the flat parameter buffer
     assert res[0][2] == res[1][2]                 # the module parameters are views of the (broadcast) flat buffer
+
+
+def _syncbn_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from semivl_b200.model.resnet import sync_sums
+    sums = torch.arange(2 * 8, dtype=torch.float32).view(2, 8) * (rank + 1)
+    count = sync_sums(sums, 100 * (rank + 1))
+    q.put((rank, sums.tolist(), count))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_syncbn_statistics_exchange_gloo_world2(built):
+    """SyncBN hook of the conv encoder (semivl.py:136 convert_sync_batchnorm): the per-channel sums of every BatchNorm and the
+    row count are SUM all-reduced over the ranks before mean / rstd are formed."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: rest for r, *rest in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+    want = (torch.arange(2 * 8, dtype=torch.float32).view(2, 8) * 3).tolist()
+    assert res[0][0] == want and res[1][0] == want
+    assert res[0][1] == 300.0 and res[1][1] == 300.0
+
+
+def test_lr_warmup_and_scheduler_max_iters(built):
+    """semivl.py:186,338-345: linear warm-up `lr * (1 - (1 - i / warmup_iters) * (1 - warmup_ratio))` while i < warmup_iters, then poly over
+    scheduler_max_iters (which may exceed total_iters), rewritten AFTER the optimizer step of iteration i."""
+    from semivl_b200.train import OptimCfg, Trainer
+    tr = Trainer.__new__(Trainer)
+    tr.opt = OptimCfg(lr=2e-4, total_iters=40, warmup_iters=5, warmup_ratio=1e-3, scheduler_max_iters=80)
+    lr, seen = 2e-4, []
+    for i in range(12):                     # the reference loop: step with the current rate, then rewrite it from index i
+        seen.append(lr)
+        if i < 5:
+            lr = 2e-4 * (1 - (1 - i / 5) * (1 - 1e-3))
+        else:
+            lr = 2e-4 * (1 - i / 80) ** 0.9
+    assert np.allclose([tr.lr_at(it) for it in range(1, 13)], seen, rtol=1e-12)

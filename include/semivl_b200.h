@@ -327,6 +327,20 @@ int svl_crop_flip_normalize(const uint8_t* src_hwc, int sh, int sw, float* dst_c
 int svl_crop_flip_mask(const uint8_t* src, int sh, int sw, int64_t* dst, int64_t* ignore_mask, int size, int x0, int y0, int flip, int pad_value,
                        void* stream);
 int svl_cutmix_box(float* box, int size, int bx, int by, int bw, int bh, void* stream);
+/* Scale / strong augmentations of the unlabelled stream on uint8 HWC images (transform.py:43-64 resize, blur; semi.py:84-93 ColorJitter,
+ * RandomGrayscale), integer-exact counterparts of the Pillow / torchvision code paths the reference calls:
+ *   svl_resample_pass_u8   one pass of Image.resize(BILINEAR) along x (axis 1) or y (axis 0): kk [out, ksize] 22-bit fixed-point coefficients
+ *                          and bounds [out, 2] = (first source index, taps) are DEVICE tables built on the host (Resample.c precompute_coeffs)
+ *   svl_gather_nearest_u8  Image.resize(NEAREST) of a label map through host-built index tables ys [oh], xs [ow] (ImagingScaleAffine)
+ *   svl_color_op_u8        in place: mode 0 brightness, 1 contrast, 2 saturation (ImageEnhance blends), 3 grayscale, 4 hue shift (`shift` =
+ *                          uint8(hue_factor * 255)); scratch = one device uint64 (the gray sum of mode 1)
+ *   svl_box_blur_pass_u8   one extended box blur pass of ImageFilter.GaussianBlur (3 along x, then 3 along y; BoxBlur.c): integer radius and
+ *                          the 8.24 fixed-point weights ww / fw come from the host */
+int svl_resample_pass_u8(const uint8_t* src, uint8_t* dst, const int* kk, const int* bounds, int ksize, int h, int w, int c, int out_size,
+                         int axis, void* stream);
+int svl_gather_nearest_u8(const uint8_t* src, uint8_t* dst, const int* ys, const int* xs, int w, int oh, int ow, void* stream);
+int svl_color_op_u8(uint8_t* img, int64_t npix, int mode, float factor, int shift, unsigned long long* scratch, void* stream);
+int svl_box_blur_pass_u8(const uint8_t* src, uint8_t* dst, int h, int w, int c, int axis, int radius, unsigned ww, unsigned fw, void* stream);
 
 /* svl_adamw with the per-step scalars in DEVICE memory: hyper = {lr of class 0, lr of class 1, 1 - beta1^t, sqrt(1 - beta2^t), lr of class 4, ...}
  * (lr_index 0, 1 or >= 4: further learning-rate classes follow the two bias corrections, e.g. the conv_encoder class of the skr04 model);

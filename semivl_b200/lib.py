@@ -132,6 +132,10 @@ _PROTOS = {
     "svl_crop_flip_normalize": [_P, _I, _I, _P, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
     "svl_crop_flip_mask": [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "svl_cutmix_box": [_P, _I, _I, _I, _I, _I, _P],
+    "svl_resample_pass_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "svl_gather_nearest_u8": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "svl_color_op_u8": [_P, _L, _I, _F, _I, _P, _P],
+    "svl_box_blur_pass_u8": [_P, _P, _I, _I, _I, _I, _I, C.c_uint, C.c_uint, _P],
     "svl_attention_fwd": [_P, _I, _P, _P, _I, _I, _I, _F, _P],
     "svl_attention_bwd": [_P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _I, _I, _I, _F, _P],
 }

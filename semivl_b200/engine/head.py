@@ -378,7 +378,7 @@ class HeadEngine:
             d_cur, d_cur_dtype = d_prev, L.F32
         # text projection (weights only; the text embeddings are frozen inputs)
         d_t_pre = d_t * (ctx["t"] > 0)
-        ops.wgrad(ops.to_act(_pad_cols(d_t_pre, 8), pr), ctx["txt_act"], grads["text_proj.0.weight"], m=c.Ct, n=c.in_dim, precise=pr)
+        ops.wgrad(ops.to_act(d_t_pre.contiguous(), pr), ctx["txt_act"], grads["text_proj.0.weight"], m=c.Ct, n=c.in_dim, precise=pr)
         grads["text_proj.0.bias"].add_(d_t_pre.sum(0))
         # ASPP
         d_x1 = d_cur                                          # f32 accumulator: the residual x + aspp(x) passes the gradient through
@@ -426,8 +426,3 @@ class HeadEngine:
         d_emb = torch.empty(B, h, w, c.in_dim, **f32)
         ops.l2norm_bwd(d_img_n, gdt, ctx["img_n"], ctx["inv_img"], d_emb.view(B * hw, c.in_dim))
         return d_taps + [d_emb] + d_conv
-
-
-def _pad_cols(x, mult):
-    """f32 [rows, c] -> [rows_padded_to_mult... unchanged rows, c] (rows unchanged); kept for API symmetry."""
-    return x.contiguous()

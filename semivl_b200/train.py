@@ -217,6 +217,31 @@ class Trainer:
             if e is not None:
                 e.cache.bump()
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Optimizer-side state for checkpoint / resume: the flat parameter, first- and second-moment buffers and the step counter (the
+        reference saves `optimizer.state_dict()` next to the model, semivl.py:423-433)."""
+        return dict(p_flat=self.p_flat.clone(), m_flat=self.m_flat.clone(), v_flat=self.v_flat.clone(), iters=self.iters,
+                    layout=dict(n_bb=self.n_bb, n_hd=self.n_hd, n_ce=self.n_ce))
+
+    def load_state_dict(self, sd):
+        lay = sd["layout"]
+        assert (lay["n_bb"], lay["n_hd"], lay["n_ce"]) == (self.n_bb, self.n_hd, self.n_ce), "checkpoint belongs to a different trainable-parameter layout"
+        self.p_flat.copy_(sd["p_flat"])
+        self.m_flat.copy_(sd["m_flat"])
+        self.v_flat.copy_(sd["v_flat"])
+        self.iters = int(sd["iters"])
+        self.invalidate_weights()
+
+    def invalidate_weights(self):
+        """Call after ANY in-place edit of the model's weights that did not go through this trainer (model.load_state_dict, manual surgery):
+        the parameters are `.data` views of the flat buffer, whose version counter never moves, so the engines' cached bf16 operand copies
+        -- of frozen tensors too -- must be dropped by hand; a captured CUDA graph holds casts of the old values and is dropped as well."""
+        for e in (self.vit, self.head, self.ce):
+            if e is not None:
+                e.cache.clear()
+        self._graph, self._graph_key = None, None
+
     # ------------------------------------------------------------------ CUDA-graph replay of the supervised step
     def graphed_supervised_step(self, img, mask):
         """`supervised_step(img, mask)` as ONE CUDA-graph launch (~690 kernel launches and their host-side descriptor set-up

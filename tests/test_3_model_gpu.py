@@ -458,3 +458,43 @@ def test_semivl_step_head_groups_are_exact(golden_dir):
     print(f"one image per head group vs unsplit: loss {l2:.7f} vs {l0:.7f}, gradient rel {err:.3e} (unsplit run-to-run floor {floor:.3e})")
     assert abs(l2 - l0) <= 2e-6 * abs(l0) and np.abs(t2 - t0).max() <= 2e-6 * np.abs(t0).max()
     assert err <= max(3 * floor, 2e-5)
+
+
+def test_trainer_checkpoint_resume_and_weight_reload(text_dir):
+    """Trainer.state_dict / load_state_dict (flat parameters, Adam moments, step counter) resume a run exactly, and a model.load_state_dict
+    after the trainer has run is honoured once invalidate_weights() drops the cached operand copies (the parameters are .data views
+    whose version counter never moves)."""
+    from semivl_b200.train import OptimCfg, Trainer
+    crop, b = 64, 2
+    g = torch.Generator().manual_seed(21)
+    imgs = [torch.randn(b, 3, crop, crop, generator=g).cuda() for _ in range(4)]
+    masks = [torch.randint(0, 21, (b, crop, crop), generator=g).cuda() for _ in range(4)]
+    m, mc, sd = _build(crop, True)
+    tr = Trainer(m, OptimCfg(lr=1e-4, total_iters=10))
+    for i in range(2):
+        tr.supervised_step(imgs[i], masks[i])
+    ck = tr.state_dict()
+    ref = [tr.supervised_step(imgs[i], masks[i]).item() for i in (2, 3)]
+    p_ref = tr.p_flat.clone()
+    m2, _, _ = _build(crop, True)
+    tr2 = Trainer(m2, OptimCfg(lr=1e-4, total_iters=10))
+    tr2.supervised_step(imgs[0], masks[0])                       # warms the operand caches with OTHER weights
+    tr2.load_state_dict(ck)
+    assert tr2.iters == 2
+    got = [tr2.supervised_step(imgs[i], masks[i]).item() for i in (2, 3)]
+    assert np.allclose(got, ref, rtol=2e-5), (got, ref)
+    # the two runs take the same two steps from the same state; they differ by the fp32 reduction order of the weight gradients, which Adam's
+    # m / sqrt(v) turns into up to ~lr per element where a gradient is near zero: compare with the distance the two steps moved the weights
+    moved = (p_ref - ck["p_flat"]).norm().item()
+    assert (tr2.p_flat - p_ref).norm().item() <= 0.05 * moved, ((tr2.p_flat - p_ref).norm().item(), moved)
+    # a weight reload behind the trainer's back: frozen tensors included
+    sd_b = {k: (v * 1.5 if k == "backbone.layers.3.ffn.layers.0.0.weight" else v) for k, v in sd.items()}
+    l_old = tr2.supervised_step(imgs[0], masks[0], update=False).item()
+    m2.load_state_dict(sd_b)
+    tr2.invalidate_weights()
+    l_new = tr2.supervised_step(imgs[0], masks[0], update=False).item()
+    m3, _, _ = _build(crop, True)
+    m3.load_state_dict(sd_b)
+    m3 = m3.cuda()
+    l_want = Trainer(m3, OptimCfg()).supervised_step(imgs[0], masks[0], update=False).item()
+    assert abs(l_new - l_want) < 1e-5 * abs(l_want) and abs(l_new - l_old) > 1e-6

@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SVL_NVCC_EXTRA", "").split(), "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, pr in procs:
         out, _ = pr.communicate()

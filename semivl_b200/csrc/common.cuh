@@ -225,37 +225,36 @@ __device__ __forceinline__ void ld16(const void* p, int dtype, int64_t off, int6
   }
 }
 
-// Fast exact-erf GELU for the bf16 throughput-mode epilogues: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. fp32-level),
-// one MUFU.RCP + one MUFU.EX2 instead of erff's branchy polynomial; the same exponential also gives the Gaussian of gelu'.
-__device__ __forceinline__ void erf_exp_fast(float u, float& erf_u, float& exp_mu2) {
-  const float a = fabsf(u);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.f)));      // MUFU.RCP, no IEEE fix-up branch
-  const float e = __expf(-a * a);
-  float pl = fmaf(1.061405429f, t, -1.453152027f);
-  pl = fmaf(pl, t, 1.421413741f);
-  pl = fmaf(pl, t, -0.284496736f);
-  pl = fmaf(pl, t, 0.254829592f);
-  const float r = 1.f - pl * t * e;
-  erf_u = copysignf(r, u);
-  exp_mu2 = e;
+// Fast GELU for the bf16 throughput-mode epilogues (the epilogue of the FFN1 GEMM is bound by its ALU work: every instruction counts).
+// Phi(x) = 1 - erfc(x / sqrt 2) / 2 with Abramowitz-Stegun 7.1.25: erfc(u) = (a1 t + a2 t^2 + a3 t^3) exp(-u^2), t = 1 / (1 + p u), u >= 0,
+// |error| <= 2.5e-5 (1.25e-5 on Phi: 1/300 of a bf16 rounding step); one MUFU.RCP + one MUFU.EX2 (ftz forms: no range fix-ups), constants
+// folded so that everything starts from x; the same exponential is the Gaussian of gelu'.  The precise mode uses erff (gelu_exact).
+__device__ __forceinline__ void phi_exp_fast(float x, float& cdf, float& gauss) {
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.47047f * 0.70710678118654752f, 1.f)));
+  const float w = x * 0.84932180028801904f;                       // sqrt(log2(e) / 2): 2^(-w^2) = exp(-x^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(w * -w));
+  float pl = fmaf(0.5f * 0.7478556f, t, 0.5f * -0.0958798f);
+  pl = fmaf(pl, t, 0.5f * 0.3480242f);
+  const float h = pl * t * e;                                     // erfc(|x| / sqrt 2) / 2
+  cdf = x >= 0.f ? 1.f - h : h;
+  gauss = e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  float er, ex;
-  erf_exp_fast(x * 0.70710678118654752f, er, ex);
-  return 0.5f * x * (1.f + er);
+  float cdf, e;
+  phi_exp_fast(x, cdf, e);
+  return x * cdf;
 }
 __device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& dg) {
-  float er, ex;
-  erf_exp_fast(x * 0.70710678118654752f, er, ex);
-  const float cdf = fmaf(0.5f, er, 0.5f);
+  float cdf, e;
+  phi_exp_fast(x, cdf, e);
   g = x * cdf;
-  dg = fmaf(x * 0.3989422804014327f, ex, cdf);
+  dg = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  float er, ex;
-  erf_exp_fast(x * 0.70710678118654752f, er, ex);      // ex = exp(-x^2 / 2)
-  return 0.5f * (1.f + er) + x * 0.3989422804014327f * ex;
+  float cdf, e;
+  phi_exp_fast(x, cdf, e);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 }  // namespace svl

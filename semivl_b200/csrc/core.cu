@@ -25,8 +25,8 @@ static int g_checked = 0;   // 0 = not yet, 1 = ok, <0 = error code
 
 int num_sms() { return g_sms > 0 ? g_sms : 148; }
 
-int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+int tma_encode(CUtensorMap* map, const void* base, int dtype, int swizzle_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
   if (!g_encode) {
     set_error("tma_encode: driver entry point not resolved (svl_check_device not called?)");
     return SVL_ERR_CUDA;
@@ -35,8 +35,10 @@ int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(map, dtype == SVL_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                        const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u stride0 %llu)", (int)r, rank,
@@ -45,6 +47,11 @@ int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
     return SVL_ERR_CUDA;
   }
   return SVL_OK;
+}
+
+int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  return tma_encode(map, base, SVL_BF16, 128, rank, dims, strides_bytes, box);
 }
 
 }  // namespace svl

@@ -23,6 +23,25 @@
 namespace svl {
 namespace {
 
+#ifdef SVL_GEMM_DIAG
+#define SVL_DBG(bit) (p.dbg & (bit))
+#define SVL_TRACE(seq, slot) do { if (p.trace && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define SVL_DBG(bit) false
+#define SVL_TRACE(seq, slot) do {} while (0)
+#endif
+
+#ifdef SVL_GEMM_DIAG
+__device__ __forceinline__ void st16_cs(void* p, int64_t off, const float* f) {      // diag: streaming (evict-first) 32-byte bf16 store
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]); r[i] = *(uint32_t*)&h; }
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"((__nv_bfloat16*)p + off), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+#else
+__device__ __forceinline__ void st16_cs(void*, int64_t, const float*) {}
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiGroups = 4;          // epilogue warps per TMEM lane quarter (each takes every kEpiGroups-th 32-column chunk)
@@ -40,7 +59,7 @@ struct GemmParams {
   int tiles_x, tiles_y;            // conv tiles per image row / column-of-tiles
   int num_m_tiles, num_n_tiles;
   int n_fastest;                   // tile order (see the note at the top)
-  int tma_store;                   // 1: bf16 output tiles are staged in shared memory and written by TMA (full 128-byte lines)
+  int staged;                      // staged epilogue (EXT 5 / 6): per-quartet smem buffers, side tile loaded and output tile stored by TMA
   int cluster;                     // 1: CTA pairs (cluster of 2 along M) share every B tile through TMA multicast;
                                    // 2: CTA pairs run ONE cta_group::2 UMMA (M = 256), each CTA holds half of the B tile
   int n, block_n, k_per_tap, num_taps;
@@ -54,6 +73,8 @@ struct GemmParams {
   const void* dact_src; int dact_dtype; int dact_kind; int64_t ld_dact;
   const void* residual; int res_dtype; int64_t ldres;
   int accumulate;
+  long long* trace;                // diag: per-tile clock64 log of CTA 0 ([tile][16] slots)
+  int dbg;                         // -DSVL_GEMM_DIAG builds only (SVL_GEMM_DBG bits: 1 no global stores, 2 no epilogue body, 4 no side loads)
   // row-strip convolution mode (tile = 128 pixels of one image row, k_per_tap <= 64, one N tile): the taps of a filter row share one
   // A strip of (128 + span) pixels, read by each tap at its own row offset; all tap weights stay resident in shared memory
   int strip, ng;
@@ -118,22 +139,24 @@ __device__ __forceinline__ void transpose_cells_8x4(float* o, int lane) {
 template <int OUT, int ACT, int PRE, int DACT, int RES, int EXT, bool GEN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmParams p) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A][stages x B][barriers][tmem ptr]
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + p.stages * p.a_stage_bytes;
   // strip mode: smem_b holds the resident weights of all taps (num_taps tiles), the A ring holds strips
-  // TMA-store mode: four 128-row x 64-column bf16 boxes (SWIZZLE_128B, 16 KB each) staged after the operand ring
+  // staged epilogue: one buffer per epilogue quartet (the 4 warps that cover the 128 rows of one 32-column chunk): 128 rows x 32 columns,
+  // f32 (16 KB, SWIZZLE_128B) or bf16 (8 KB, SWIZZLE_64B), after the operand ring
   const uint32_t smem_c = smem_b + (p.strip ? (uint32_t)p.num_taps * p.b_tile_bytes : p.stages * p.b_stage_bytes);   // 1024-aligned
-  const uint32_t bar_base = smem_c + (p.tma_store ? 4u * 16384u : 0u);
+  const uint32_t bar_base = smem_c + (uint32_t)p.staged * kEpiGroups;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + s); };
   const uint32_t wbar = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc);
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc + 1);
+  auto side_bar = [&](int g) { return bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc + 2 + g); };
   volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,6 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_init(tempty_bar(s), (pair ? 2 : 1) * 4 * (p.block_n < kEpiGroups * 32 ? (p.block_n + 31) / 32 : kEpiGroups));
     }
     ptx::mbar_init(wbar, 1);
+    for (int g = 0; g < kEpiGroups; ++g) ptx::mbar_init(side_bar(g), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -278,14 +302,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     } else {
-      for (int tile = (pair && crank != 0) ? num_tiles : tile0; tile < num_tiles; tile += tstride) {      // pair mode: the leader issues for both SMs
+      int tseq = 0;
+      for (int tile = (pair && crank != 0) ? num_tiles : tile0; tile < num_tiles; tile += tstride, ++tseq) {      // pair mode: the leader issues for both SMs
+        if (leader) SVL_TRACE(tseq, 0);
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
+        if (leader) SVL_TRACE(tseq, 1);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
         uint32_t accum = 0;
+#ifdef SVL_GEMM_DIAG
+        long long waited = 0;
+#endif
         for (int t = 0; t < p.num_taps; ++t) {
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+#ifdef SVL_GEMM_DIAG
+            const long long w0 = clock64();
+#endif
             ptx::mbar_wait(full_bar(stage), phase);
+#ifdef SVL_GEMM_DIAG
+            waited += clock64() - w0;
+#endif
             ptx::tc_fence_after();
             const uint64_t adesc = tmpl + (uint64_t)((smem_a + stage * p.a_stage_bytes) >> 4);
             const uint64_t bdesc = tmpl + (uint64_t)((smem_b + stage * p.b_stage_bytes) >> 4);
@@ -310,6 +346,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (leader) {
           if (pair) ptx::umma_commit_pair(tfull_bar(as), (uint16_t)3);      // both CTAs' epilogue warps read their half of the accumulator
           else ptx::umma_commit(tfull_bar(as));
+          SVL_TRACE(tseq, 2);
+#ifdef SVL_GEMM_DIAG
+          if (p.trace && blockIdx.x == 0 && tseq < 32) p.trace[tseq * 16 + 15] = waited;
+#endif
         }
         __syncwarp();
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
@@ -328,7 +368,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // column groups without a 32-column chunk of this block_n (narrow conv outputs) take no part: the accumulator-free barrier counts
     // only the active groups
     const bool active = cgrp * 32 < p.block_n;
+    // staged epilogue (EXT 5: f32 out + f32 residual; EXT 6: bf16 out, optional act' side tile / second output): the quartet = the four
+    // warps (one per TMEM lane quarter) that share a 32-column chunk; its buffer holds that chunk for all 128 rows of the tile
+    constexpr bool STAGED = !GEN && (EXT == 5 || EXT == 6);
+    constexpr bool ST_F32 = EXT == 5;
+    constexpr bool ST_SIDE = STAGED && (ST_F32 || DACT >= 1);
+    constexpr uint32_t kStBuf = ST_F32 ? 16384u : 8192u, kStRow = ST_F32 ? 128u : 64u;
+    const uint32_t st_buf = smem_c + (uint32_t)cgrp * kStBuf;
+    uint8_t* const st_row = smem_raw + (st_buf - ptx::smem_u32(smem_raw)) + (uint32_t)r * kStRow;
+    const uint32_t st_sw = ST_F32 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);      // SWIZZLE_128B / SWIZZLE_64B chunk XOR of this row
+    const bool qlead = q == 0 && lane == 0;                                          // the quartet's TMA thread
+    uint32_t sphase = 0;
+    auto quartet_bar = [&]() { __syncwarp(); asm volatile("bar.sync %0, 128;" ::"r"(1 + cgrp) : "memory"); };
+    int tseq = -1;
+    const int tslot = warp == 2 ? 4 : warp == 9 ? 8 : warp == 17 ? 12 : 100;
     for (int tile = active ? (p.strip ? (int)blockIdx.x : tile0) : num_tiles; tile < num_tiles; tile += (p.strip ? (int)gridDim.x : tstride)) {
+      ++tseq;
+      if (lane == 0 && tslot < 16) SVL_TRACE(tseq, tslot);
       const int n_tile = p.n_fastest ? tile % p.num_n_tiles : tile / m_slots, m_slot = p.n_fastest ? tile / p.num_n_tiles : tile % m_slots;
       const int m_tile = p.cluster ? 2 * m_slot + crank : m_slot;
       const int n0 = n_tile * p.block_n;
@@ -344,7 +400,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // tile's MMAs are still running.  act' source: both 32-column chunks of this thread into registers (raw bf16);
       // residual (fp32, 128 B per chunk): an L2 prefetch of the line.
       uint4 sraw[2][4];
-      if (!GEN && DACT >= 1 && grow >= 0) {
+      if (!GEN && EXT < 5 && DACT >= 1 && grow >= 0 && !SVL_DBG(4)) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int c0 = (cgrp + j * kEpiGroups) * 32;
@@ -355,7 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
-      if (!GEN && RES == SVL_F32 && grow >= 0) {
+      if (!GEN && EXT < 5 && RES == SVL_F32 && grow >= 0 && !SVL_DBG(4)) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int c0 = (cgrp + j * kEpiGroups) * 32;
@@ -363,8 +419,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             asm volatile("prefetch.global.L2 [%0];" ::"l"((const float*)p.residual + grow * p.ldres + n0 + c0));
         }
       }
+      if (ST_SIDE && qlead && n0 + cgrp * 32 < p.n) {
+        // side tile of the quartet's first chunk: the buffer is free once this thread's earlier stores have read it
+        ptx::bulk_wait_group_read0();
+        ptx::mbar_arrive_expect_tx(side_bar(cgrp), kStBuf);
+        ptx::tma_load_2d(st_buf, &tmD, side_bar(cgrp), n0 + cgrp * 32, m_tile * BM);
+        // the side tiles come from HBM (saved activations / the residual stream): 3-4k cycles of load latency per chunk sat on the quartet's
+        // critical path; pull the NEXT tile's two chunks into L2 now (profiles/r02_gemm_epilogue.md)
+        const int nt = tile + tstride;
+        if (nt < num_tiles && !SVL_DBG(128)) {
+          const int nn = p.n_fastest ? nt % p.num_n_tiles : nt / m_slots, ns = p.n_fastest ? nt / p.num_n_tiles : nt % m_slots;
+          const int nm = p.cluster ? 2 * ns + crank : ns;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int cc = (cgrp + jj * kEpiGroups) * 32;
+            if (cc < p.block_n && nn * p.block_n + cc < p.n) ptx::tma_prefetch_2d(&tmD, nn * p.block_n + cc, nm * BM);
+          }
+        }
+      }
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
+      if (lane == 0 && tslot < 16) SVL_TRACE(tseq, tslot + 1);
       if (GEN)
       for (int c0 = cgrp * 32; c0 < p.block_n; c0 += kEpiGroups * 32) {
         if (n0 + c0 >= p.n) break;
@@ -442,14 +517,116 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // (unreachable: the specialised kernels use the slab loop below)
         }
       }
-      if (!GEN) {
+      bool released = false;
+      auto release_acc = [&]() {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (pair && crank != 0) ptx::mbar_arrive_cluster(ptx::cluster_map(tempty_bar(as), 0));
+          else ptx::mbar_arrive(tempty_bar(as));
+        }
+        released = true;
+      };
+      if (STAGED) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c0 = (cgrp + j * kEpiGroups) * 32;
+          if (c0 >= p.block_n || n0 + c0 >= p.n) break;
+          const int c1 = c0 + kEpiGroups * 32;
+          const bool last = j == 1 || c1 >= p.block_n || n0 + c1 >= p.n;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
+          if (ST_SIDE) {
+            ptx::mbar_wait(side_bar(cgrp), sphase);                  // the side tile has landed (and with it: the buffer was free)
+            sphase ^= 1u;
+          } else {
+            if (qlead) ptx::bulk_wait_group_read0();                 // the previous store has read the buffer
+            quartet_bar();
+          }
+          ptx::tmem_ld_wait();
+          if (warp == 2 && lane == 0) SVL_TRACE(tseq, j == 0 ? 3 : 11);
+          if (last) release_acc();                                   // the accumulator is in registers: the MMA warp may overwrite it now
+          uint4 second[4];                                           // GELU_DSAVE: gelu' of the chunk, packed, stored after the first output
+          if (ST_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4* cell = (float4*)(st_row + (((uint32_t)i ^ st_sw) << 4));
+              float4 o = *cell;                                      // residual
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bb = __ldg((const float4*)(p.bias + n0 + c0) + i);
+              o.x += fmaf(__uint_as_float(v[4 * i]), alpha, bb.x);
+              o.y += fmaf(__uint_as_float(v[4 * i + 1]), alpha, bb.y);
+              o.z += fmaf(__uint_as_float(v[4 * i + 2]), alpha, bb.z);
+              o.w += fmaf(__uint_as_float(v[4 * i + 3]), alpha, bb.w);
+              *cell = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4* cell = (uint4*)(st_row + (((uint32_t)i ^ st_sw) << 4));
+              float f[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * i + k]);
+              if (alpha != 1.f) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] *= alpha;
+              }
+              if (p.bias) {
+                const float4 b0 = __ldg((const float4*)(p.bias + n0 + c0) + 2 * i), b1 = __ldg((const float4*)(p.bias + n0 + c0) + 2 * i + 1);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (ACT == SVL_ACT_GELU_DSAVE) {
+                float dg[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gelu_and_grad_fast(f[k], f[k], dg[k]);
+                second[i] = f32_to_bf16x8(dg);
+              } else if (ACT == SVL_ACT_GELU) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = gelu_fast(f[k]);
+              }
+              if (DACT >= 1) {
+                const uint4 sd = *cell;
+                const uint32_t w[4] = {sd.x, sd.y, sd.z, sd.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float s0 = __uint_as_float(w[k] << 16), s1 = __uint_as_float(w[k] & 0xffff0000u);
+                  f[2 * k] *= DACT == 1 ? gelu_grad_fast(s0) : s0;
+                  f[2 * k + 1] *= DACT == 1 ? gelu_grad_fast(s1) : s1;
+                }
+              }
+              if (!SVL_DBG(64)) *cell = f32_to_bf16x8(f);
+            }
+          }
+          ptx::fence_proxy_async();                                  // generic-proxy writes of the buffer -> visible to the TMA engine
+          quartet_bar();
+          if (warp == 2 && lane == 0 && j == 0) SVL_TRACE(tseq, 7);
+          if (qlead && !SVL_DBG(1)) {
+            ptx::tma_store_2d(&tmC, st_buf, n0 + c0, m_tile * BM);   // rows >= M are clipped by the tensor map
+            ptx::bulk_commit_group();
+          }
+          if (ACT == SVL_ACT_GELU_DSAVE) {
+            if (qlead) ptx::bulk_wait_group_read0();
+            quartet_bar();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (!SVL_DBG(64)) *(uint4*)(st_row + (((uint32_t)i ^ st_sw) << 4)) = second[i];
+            ptx::fence_proxy_async();
+            quartet_bar();
+            if (qlead && !SVL_DBG(1)) {
+              ptx::tma_store_2d(&tmD, st_buf, n0 + c0, m_tile * BM);
+              ptx::bulk_commit_group();
+            }
+          }
+          if (ST_SIDE && !last && qlead) {                           // side tile of the quartet's second chunk
+            ptx::bulk_wait_group_read0();
+            ptx::mbar_arrive_expect_tx(side_bar(cgrp), kStBuf);
+            ptx::tma_load_2d(st_buf, &tmD, side_bar(cgrp), n0 + c1, m_tile * BM);
+          }
+        }
+        __syncwarp();
+      }
+      if (!GEN && !STAGED && !SVL_DBG(2)) {
         // specialised epilogue: 32-column chunks, one output row per thread, 32-byte vector accesses (full sectors);
         // bias / act / act' / residual fused in registers
-        if (OUT == SVL_BF16 && p.tma_store) {
-          // the previous tile's TMA stores must have finished READING the staging boxes before anyone overwrites them
-          if (threadIdx.x == 64) ptx::bulk_wait_group_read0();
-          asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiGroups) : "memory");
-        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                  // block_n <= 256: at most two chunks per warp
           const int c0 = (cgrp + j * kEpiGroups) * 32;
@@ -465,9 +642,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               growT[jj] = __shfl_sync(0xffffffffu, grow, jj * 4 + (lane & 3));
-              resT[jj] = growT[jj] >= 0 ? *(const float4*)((const float*)p.residual + growT[jj] * p.ldres + colT) : make_float4(0.f, 0.f, 0.f, 0.f);
+              resT[jj] = growT[jj] >= 0 && !SVL_DBG(4) ? *(const float4*)((const float*)p.residual + growT[jj] * p.ldres + colT) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             ptx::tmem_ld_wait();
+            if (j == 0 && warp == 2 && lane == 0) SVL_TRACE(tseq, 3);
             float o[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]) * alpha;
@@ -479,16 +657,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             transpose_cells_8x4(o, lane);
+            if (j == 0 && warp == 2 && lane == 0) SVL_TRACE(tseq, 7);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              if (growT[jj] >= 0)
+              if (growT[jj] >= 0 && !SVL_DBG(1))
                 *(float4*)((float*)p.out + growT[jj] * p.ldc + colT) =
                     make_float4(o[4 * jj] + resT[jj].x, o[4 * jj + 1] + resT[jj].y, o[4 * jj + 2] + resT[jj].z, o[4 * jj + 3] + resT[jj].w);
             }
+            if (warp == 2 && lane == 0) SVL_TRACE(tseq, j == 0 ? 11 : 15);
             continue;
           }
           float side[2][16];
-          if (RES >= 0 && grow >= 0) {
+          if (RES >= 0 && grow >= 0 && !SVL_DBG(4)) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int col = n0 + c0 + g * 16;
@@ -540,7 +720,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float dg[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) gelu_and_grad_fast(f[i], f[i], dg[i]);
-              st16(p.preact_out, PRE, grow * p.ld_preact + col, 0, cnt, dg);
+              if (!SVL_DBG(1)) { if (SVL_DBG(16)) st16_cs(p.preact_out, (SVL_DBG(8) ? (grow & 1023) : grow) * p.ld_preact + col, dg); else st16(p.preact_out, PRE, (SVL_DBG(8) ? (grow & 1023) : grow) * p.ld_preact + col, 0, cnt, dg); }
             } else if (PRE >= 0) st16(p.preact_out, PRE, grow * p.ld_preact + col, 0, cnt, f);
             if (ACT == SVL_ACT_GELU) {
 #pragma unroll
@@ -560,7 +740,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] += side[g][i];
             }
-            int64_t off = grow * p.ldc + col;
+            int64_t off = (SVL_DBG(8) ? (grow & 1023) : grow) * p.ldc + col;
+            if (SVL_DBG(32)) off = ((((int64_t)tile * 2 + j) * 2 + g) * 16 + (warp - 2)) * 512 + lane * 16;      // diag: every store instruction covers 1 KB contiguous
             if (EXT == 1) {                                  // cq % 16 == 0 is checked by the launcher for this variant
               const int qq = col / cq, cc = col % cq;
               off = ct_base + ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
@@ -571,40 +752,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] += sv[i];
             }
-            if (OUT == SVL_BF16 && p.tma_store) {
-              // stage the 16 values (32 bytes) in the SWIZZLE_128B box of their 64-column group: row r, 16-byte chunks XOR-swizzled by r % 8
-              const int tc = c0 + g * 16;                       // column inside the tile
-              uint8_t* rowp = smem_raw + (smem_c - ptx::smem_u32(smem_raw)) + (uint32_t)(tc >> 6) * 16384u + (uint32_t)r * 128u;
-              const int k0 = (tc & 63) >> 3;
-              *(uint4*)(rowp + (((k0) ^ (r & 7)) << 4)) = f32_to_bf16x8(f);
-              *(uint4*)(rowp + (((k0 + 1) ^ (r & 7)) << 4)) = f32_to_bf16x8(f + 8);
-            } else {
+            if (!SVL_DBG(1)) {
+              if (OUT == SVL_BF16 && SVL_DBG(16)) st16_cs(p.out, off, f); else
               st16(p.out, OUT, off, p.ldc / 2, cnt, f);
             }
           }
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (pair && crank != 0) ptx::mbar_arrive_cluster(ptx::cluster_map(tempty_bar(as), 0));
-        else ptx::mbar_arrive(tempty_bar(as));
-      }
-      if (!GEN && OUT == SVL_BF16 && p.tma_store) {
-        ptx::fence_proxy_async();                                // generic-proxy writes of the staging boxes -> visible to the TMA engine
-        asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiGroups) : "memory");
-        if (threadIdx.x == 64) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            if (b * 64 < p.block_n && n0 + b * 64 < p.n) ptx::tma_store_2d(&tmC, smem_c + (uint32_t)b * 16384u, n0 + b * 64, m_tile * BM);
-          ptx::bulk_commit_group();                              // rows >= M / columns >= N are clipped by the tensor map
-        }
-      }
+      if (lane == 0 && tslot < 16) SVL_TRACE(tseq, tslot + 2);
+      if (!released) release_acc();
       if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
     }
   }
 
-  if (p.tma_store && threadIdx.x == 64) ptx::bulk_wait_group0();      // the last tile's stores are complete before the CTA retires
+  if (p.staged && warp >= 2 && (warp & 3) == 0 && lane == 0) ptx::bulk_wait_group0();      // the quartet leaders' last stores are complete before the CTA retires
   ptx::tc_fence_before();
   __syncthreads();
   if (p.cluster) ptx::cluster_sync();          // no CTA leaves while its peer may still signal into its shared memory
@@ -647,7 +808,6 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   if (int rc = svl_check_device()) return rc;
 
   GemmParams p;
-  p.tma_store = 0;
   p.cluster = 0;
   memset(&p, 0, sizeof(p));
   p.a_conv = d->a_conv;
@@ -665,7 +825,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.n_fastest = p.num_n_tiles > 1 && !d->a_conv && (int64_t)d->m * d->k_per_tap * d->num_taps * 2 > (48ll << 20);
   const int64_t a_cols = d->a_cols > 0 ? d->a_cols : d->lda;
 
-  CUtensorMap tmA, tmB, tmBh, tmC;
+  CUtensorMap tmA, tmB, tmBh, tmC, tmD;
   if (d->a_conv) {
     SVL_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0 && (int64_t)d->nb * d->h * d->w == d->m, "svl_gemm: conv geometry does not match m");
     p.nb = d->nb; p.h = d->h; p.w = d->w;
@@ -729,6 +889,28 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
     if (int rc = tma_encode_bf16(&tmA, d->a, 2, dims, strides, box)) return rc;
   }
+  // ---- staged epilogue (EXT 5 / 6)?  Plain GEMMs whose epilogue moves a second tile: fp32 output + fp32 residual (out-proj, FFN2), bf16 output
+  // times a saved bf16 act' tile (FFN2 dgrad), bf16 output + saved gelu' (FFN1).  SVL_GEMM_STAGED: bit 0 f32 + residual, bit 1 act' side tile,
+  // bit 2 GELU_DSAVE, bit 3 every other plain bf16 output.
+  static int staged_mask = -1;
+  if (staged_mask < 0) { const char* e = getenv("SVL_GEMM_STAGED"); staged_mask = e ? atoi(e) : 7; }
+  int staged_kind = 0;                                   // 5 / 6 = EXT of the staged variants
+  {
+    const bool base_ok = !d->a_conv && d->out_mode == SVL_OUT_LINEAR && !d->row_bias && !d->accumulate && d->n % 32 == 0 &&
+                         ((uintptr_t)d->out & 15) == 0 && (!d->bias || ((uintptr_t)d->bias & 15) == 0) && p.block_n % 32 == 0;
+    if (base_ok && d->out_dtype == SVL_F32 && d->residual && d->res_dtype == SVL_F32 && !d->preact_out && !d->dact_src && d->act == SVL_ACT_NONE &&
+        d->ldc % 4 == 0 && d->ldres % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && (staged_mask & 1))
+      staged_kind = 5;
+    else if (base_ok && d->out_dtype == SVL_BF16 && !d->residual && d->ldc % 8 == 0) {
+      const bool side = d->dact_src && (d->dact_kind == SVL_ACT_GELU || d->dact_kind == SVL_ACT_SAVED) && d->dact_dtype == SVL_BF16 &&
+                        d->ld_dact % 8 == 0 && ((uintptr_t)d->dact_src & 15) == 0 && !d->preact_out && d->act == SVL_ACT_NONE;
+      const bool dsave = d->act == SVL_ACT_GELU_DSAVE && !d->dact_src && d->preact_dtype == SVL_BF16 && d->ld_preact % 8 == 0 &&
+                         ((uintptr_t)d->preact_out & 15) == 0;
+      const bool plain_out = !d->dact_src && !d->preact_out && (d->act == SVL_ACT_NONE || d->act == SVL_ACT_GELU);
+      if ((side && (staged_mask & 2)) || (dsave && (staged_mask & 4)) || (plain_out && (staged_mask & 8))) staged_kind = 6;
+    }
+  }
+  p.staged = staged_kind == 5 ? 16384 : staged_kind == 6 ? 8192 : 0;
   {
     uint64_t dims[2] = {(uint64_t)d->ldb, (uint64_t)d->b_rows};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
@@ -741,7 +923,8 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     if (cluster_on < 0) { const char* e = getenv("SVL_GEMM_CLUSTER"); cluster_on = e ? atoi(e) : 3; }
     const bool eligible = !d->a_conv && p.num_m_tiles >= 2 && p.block_n % 32 == 0;
     p.cluster = !eligible ? 0 : (cluster_on == 1 || cluster_on == 2) ? cluster_on
-              : (cluster_on == 3 && (int64_t)d->k_per_tap * d->num_taps >= 2048 && d->num_taps == 1) ? 2 : 0;
+              : (cluster_on == 3 && (((int64_t)d->k_per_tap * d->num_taps >= 2048 && d->num_taps == 1) || staged_kind == 5)) ? 2 : 0;
+    // (fp32 staging buffers take 64 KB: only the pair mode's 32 KB stages leave room for a deep enough operand ring)
     if (p.cluster) {                                        // half-height box: the B half a CTA loads (multicast to both, or kept, in pair mode)
       uint32_t boxh[2] = {(uint32_t)BK, (uint32_t)(p.block_n / 2)};
       if (int rc = tma_encode_bf16(&tmBh, d->b, 2, dims, strides, boxh)) return rc;
@@ -770,27 +953,27 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
       p.g_nmma[g] = nm;
     }
   } else {
-    // TMA-store epilogue: single bf16 output of a plain GEMM, full-width tiles (all 16 epilogue warps take part in its barriers)
-    static int tma_store_on = -1;
-    if (tma_store_on < 0) { const char* e = getenv("SVL_GEMM_TMA_STORE"); tma_store_on = e ? atoi(e) : 0; }
-    p.tma_store = tma_store_on && !d->a_conv && d->out_dtype == SVL_BF16 && d->out_mode == SVL_OUT_LINEAR && !d->preact_out && !d->row_bias &&
-                  !d->accumulate && !d->residual && p.block_n == 256 && d->ldc % 8 == 0 && ((uintptr_t)d->out & 15) == 0 &&
-                  (d->act == SVL_ACT_NONE || d->act == SVL_ACT_GELU) &&
-                  (!d->dact_src || ((d->dact_kind == SVL_ACT_GELU || d->dact_kind == SVL_ACT_SAVED) && d->dact_dtype == SVL_BF16 && d->n % 32 == 0 &&
-                                    d->ld_dact % 8 == 0 && ((uintptr_t)d->dact_src & 15) == 0));
-    const size_t stage_c = p.tma_store ? 4 * 16384 : 0;
-    const size_t budget = p.tma_store ? (size_t)(227 * 1024 - 2048) : (size_t)kSmemBudget;       // operand ring + staging boxes fill the SM
+    const size_t stage_c = (size_t)p.staged * kEpiGroups;
+    const size_t budget = p.staged ? (size_t)(227 * 1024 - 1024 - 512) : (size_t)kSmemBudget;       // operand ring + staging buffers fill the SM
     p.stages = (int)((budget - stage_c) / (p.a_stage_bytes + p.b_stage_bytes));
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     smem_data = (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + stage_c;
-    if (p.tma_store) {
+    if (p.staged) {
+      const int dt = staged_kind == 5 ? SVL_F32 : SVL_BF16, es = staged_kind == 5 ? 4 : 2, sw = staged_kind == 5 ? 128 : 64;
+      uint32_t boxc[2] = {32u, (uint32_t)BM};
       uint64_t dimsc[2] = {(uint64_t)d->n, (uint64_t)d->m};
-      uint64_t stridesc[1] = {(uint64_t)d->ldc * 2};
-      uint32_t boxc[2] = {64u, (uint32_t)BM};
-      if (int rc = tma_encode_bf16(&tmC, d->out, 2, dimsc, stridesc, boxc)) return rc;
+      uint64_t stridesc[1] = {(uint64_t)d->ldc * es};
+      if (int rc = tma_encode(&tmC, d->out, dt, sw, 2, dimsc, stridesc, boxc)) return rc;
+      const void* second = staged_kind == 5 ? d->residual : d->dact_src ? d->dact_src : d->preact_out;
+      const int64_t ld2 = staged_kind == 5 ? d->ldres : d->dact_src ? d->ld_dact : d->ld_preact;
+      if (second) {
+        uint64_t stridesd[1] = {(uint64_t)ld2 * es};
+        if (int rc = tma_encode(&tmD, second, dt, sw, 2, dimsc, stridesd, boxc)) return rc;
+      }
     }
   }
-  if (!p.tma_store) tmC = tmA;
+  if (!p.staged) tmC = tmA;
+  if (!p.staged || (staged_kind == 6 && !d->dact_src && !d->preact_out)) tmD = tmA;
   p.acc_stages = 512 / p.block_n < kMaxAcc ? 512 / p.block_n : kMaxAcc;
   if (const char* e = getenv("SVL_ACC_STAGES")) { int v = atoi(e); if (v >= 1 && v <= p.acc_stages) p.acc_stages = v; }
   p.tmem_cols = pow2ceil(p.acc_stages * p.block_n < 32 ? 32 : p.acc_stages * p.block_n);
@@ -802,8 +985,12 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   p.dact_src = d->dact_src; p.dact_dtype = d->dact_dtype; p.dact_kind = d->dact_kind; p.ld_dact = d->ld_dact;
   p.residual = d->residual; p.res_dtype = d->res_dtype; p.ldres = d->ldres;
   p.accumulate = d->accumulate;
+#ifdef SVL_GEMM_DIAG
+  { const char* e = getenv("SVL_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("SVL_GEMM_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 10) : nullptr; }
+#endif
 
-  const size_t smem = 1024 + smem_data + 8 * (2 * kMaxStages + 2 * kMaxAcc + 2) + 16;
+  const size_t smem = 1024 + smem_data + 8 * (2 * kMaxStages + 2 * kMaxAcc + 2 + kEpiGroups) + 16;
   if (p.strip) p.cluster = 0;
   const int num_tiles = (p.cluster ? (p.num_m_tiles + 1) / 2 * 2 : p.num_m_tiles) * p.num_n_tiles;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
@@ -824,9 +1011,9 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
       at[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                                 \
       cfg.attrs = at; cfg.numAttrs = 1;                                                                                   \
-      SVL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<__VA_ARGS__, PAIRV>, tmA, tmB, tmBh, tmC, p));                              \
+      SVL_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<__VA_ARGS__, PAIRV>, tmA, tmB, tmBh, tmC, tmD, p));                              \
     } else {                                                                                                              \
-      gemm_kernel<__VA_ARGS__, PAIRV><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmBh, tmC, p);            \
+      gemm_kernel<__VA_ARGS__, PAIRV><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmBh, tmC, tmD, p);          \
     }                                                                                                                     \
   } while (0)
 #define SVL_LAUNCH_GEMM(...)                                          \
@@ -834,7 +1021,15 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     if (p.cluster == 2) SVL_LAUNCH_GEMM_AS(true, __VA_ARGS__);        \
     else SVL_LAUNCH_GEMM_AS(false, __VA_ARGS__);                      \
   } while (0)
-  if (plain && no_extra && p.out_dtype == SVL_BF16) {
+  if (staged_kind == 5) {
+    SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, SVL_F32, 5, false);
+  } else if (staged_kind == 6) {
+    if (p.dact_src && p.dact_kind == SVL_ACT_GELU) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 1, -1, 6, false);
+    else if (p.dact_src) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 2, -1, 6, false);
+    else if (p.act == SVL_ACT_GELU_DSAVE) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU_DSAVE, SVL_BF16, 0, -1, 6, false);
+    else if (p.act == SVL_ACT_GELU) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU, -1, 0, -1, 6, false);
+    else SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 6, false);
+  } else if (plain && no_extra && p.out_dtype == SVL_BF16) {
     SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_NONE, -1, 0, -1, 0, false);
   } else if (plain && no_extra && p.out_dtype == SVL_F32) {
     SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, -1, 0, false);

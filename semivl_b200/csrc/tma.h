@@ -10,6 +10,9 @@ namespace svl {
 // dims[0] is the contiguous dimension; strides_bytes has rank-1 entries (dimension 1..rank-1).
 int tma_encode_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
+// general form: dtype = SVL_F32 / SVL_BF16, swizzle_bytes = 0 / 32 / 64 / 128
+int tma_encode(CUtensorMap* map, const void* base, int dtype, int swizzle_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box);
 int num_sms();
 // tcgen05 flash attention (attention_tc.cu), bf16 throughput mode only
 size_t attention_bwd_tc_workspace(int b, int L, int heads);

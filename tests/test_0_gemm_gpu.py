@@ -242,12 +242,13 @@ def test_throughput_report(ops):
         print(f"wgrad {rows}x{m}x{n}: {ms * 1e3:.1f} us  {2 * m * n * rows / ms / 1e9:.1f} TFLOP/s")
 
 
-@pytest.mark.parametrize("env", [dict(SVL_GEMM_CLUSTER="1"), dict(SVL_GEMM_CLUSTER="2"), dict(SVL_GEMM_TMA_STORE="1"),
-                                 dict(SVL_GEMM_CLUSTER="2", SVL_GEMM_TMA_STORE="1")])
+@pytest.mark.parametrize("env", [dict(SVL_GEMM_CLUSTER="1"), dict(SVL_GEMM_CLUSTER="2"), dict(SVL_GEMM_STAGED="0"), dict(SVL_GEMM_STAGED="15"),
+                                 dict(SVL_GEMM_CLUSTER="2", SVL_GEMM_STAGED="15"), dict(SVL_GEMM_CLUSTER="0", SVL_GEMM_STAGED="15")])
 def test_optin_launch_modes_subprocess(env):
-    """Opt-in launch modes of the contraction engine, read once per process, exercised in a child process on the plain / epilogue GEMM tests:
+    """Launch modes of the contraction engine, read once per process, exercised in a child process on the plain / epilogue GEMM tests:
     SVL_GEMM_CLUSTER=1 (2-CTA clusters, B tile TMA-multicast, 2-arrival stage barriers), =2 (CTA pairs running one cta_group::2 UMMA with
-    M = 256, half of B per CTA, leader-side barriers), SVL_GEMM_TMA_STORE=1 (bf16 tiles staged in shared memory and written by TMA)."""
+    M = 256, half of B per CTA, leader-side barriers), =0 (never); SVL_GEMM_STAGED = bit mask of the epilogues that go through the per-quartet
+    shared-memory buffers and TMA (0: none, the register / direct-store epilogues; 15: all, including every plain bf16 output)."""
     import os
     import subprocess
     import sys

@@ -156,6 +156,12 @@ int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* y, c
  * element b*batch_stride (dropping / re-inserting the cls token row of [b, L, c] token tensors, maskclip_vit.py:543-546) */
 int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t src_batch_stride, void* dst, int dst_dtype, int64_t ld_dst,
              int64_t dst_batch_stride, int batch, int64_t rows, int cols, float scale, void* stream);
+/* Batched parameter jobs, one launch.  mode 0: refresh the GEMM-operand copies of the trainable weights after the optimizer step
+ * (dst[i] = cast(src[idx[i]]), idx < 0 = zero padding; replaces the per-tensor reshape / permute / cast launches the reference's optimizer.step
+ * + autocast would do, semivl.py:326-328).  mode 1: scatter staged weight gradients into the parameter layout (dst[idx[i]] += src[i]; src[i] = 0).
+ * jobs: device int64 [njobs][5] = {src, dst, idx (int32*), n, flags (bit 0: f32 dst)}; block_start: device int32 [njobs + 1], first
+ * 1024-element block of each job. */
+int svl_param_jobs(const void* jobs, const void* block_start, int njobs, int total_blocks, int mode, void* stream);
 /* out[col] += sum_rows x[row, col]  (bias gradients) */
 int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
 /* out[i] (+)= sum_b x[b, i]  (pos_embed gradient, maskclip_vit.py:500) */

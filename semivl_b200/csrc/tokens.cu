@@ -647,6 +647,55 @@ extern "C" int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
   return SVL_OK;
 }
 
+// Batched parameter jobs: ONE launch refreshes every GEMM-operand copy of the trainable weights after the optimizer step (dst[i] =
+// cast(src[idx[i]]), idx < 0 = zero padding: any operand layout is a gather of the parameter) or scatters every staged weight gradient
+// back into the parameter layout (dst[idx[i]] += src[i]; src[i] = 0: the index maps are injective, no atomics).  A job row is
+// {src, dst, idx, n, flags} (flags bit 0: dst is f32 instead of bf16); block_start[j] = first 1024-element block of job j.
+__global__ void __launch_bounds__(256) param_jobs_kernel(const long long* __restrict__ jobs, const int* __restrict__ block_start, int njobs, int mode) {
+  int lo = 0, hi = njobs;                                   // last job whose first block is <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (block_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const long long* J = jobs + 5 * lo;
+  const long long n = J[3];
+  const int* __restrict__ idx = (const int*)J[2];
+  const long long base = (long long)((int)blockIdx.x - block_start[lo]) * 1024;
+  if (mode == 0) {
+    const float* __restrict__ src = (const float*)J[0];
+    const bool f32 = J[4] & 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + k * 256 + threadIdx.x;
+      if (i < n) {
+        const int s = idx[i];
+        const float v = s >= 0 ? src[s] : 0.f;
+        if (f32) ((float*)J[1])[i] = v;
+        else ((__nv_bfloat16*)J[1])[i] = __float2bfloat16(v);
+      }
+    }
+  } else {
+    float* __restrict__ src = (float*)J[0];
+    float* __restrict__ dst = (float*)J[1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + k * 256 + threadIdx.x;
+      if (i < n) {
+        const int s = idx[i];
+        if (s >= 0) dst[s] += src[i];
+        src[i] = 0.f;
+      }
+    }
+  }
+}
+
+extern "C" int svl_param_jobs(const void* jobs, const void* block_start, int njobs, int total_blocks, int mode, void* stream) {
+  SVL_CHECK_ARG(jobs && block_start && njobs >= 1 && total_blocks >= 1 && (mode == 0 || mode == 1), "svl_param_jobs: bad arguments");
+  param_jobs_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const long long*)jobs, (const int*)block_start, njobs, mode);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+
 extern "C" int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t src_batch_stride, void* dst, int dst_dtype, int64_t ld_dst,
                         int64_t dst_batch_stride, int batch, int64_t rows, int cols, float scale, void* stream) {
   SVL_CHECK_ARG(src && dst && batch >= 1, "svl_cast: bad arguments");

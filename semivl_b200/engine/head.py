@@ -33,43 +33,44 @@ class HeadEngine:
         self.cache = WeightCache()
 
     # ------------------------------------------------------------------ weight operands
-    def _prep(self, p, name, kind):
-        pr = self.precise
+    @staticmethod
+    def _layout(kind):
+        """operand layout of a parameter as a pure gather of its elements (reshape / permute / slice / zero padding)"""
+        def pad_cols(t):                   # conv1 [C,1,ks,ks] -> [C, 64]
+            w = t.new_zeros(t.shape[0], 64)
+            w[:, : t.shape[2] * t.shape[3]] = t.reshape(t.shape[0], -1)
+            return w
 
-        def make(t):
-            t = t.float()
-            if kind == "lin":
-                w = t.reshape(t.shape[0], -1)
-            elif kind == "lin_t":
-                w = t.reshape(t.shape[0], -1).t()
-            elif kind == "conv":           # [Co,Ci,kh,kw] -> [(tap, co), ci]
-                w = t.permute(2, 3, 0, 1).reshape(-1, t.shape[1])
-            elif kind == "conv_t":         # -> [(tap, ci), co]
-                w = t.permute(2, 3, 1, 0).reshape(-1, t.shape[0])
-            elif kind == "convT":          # ConvTranspose [Ci,Co,2,2] -> [(q, co), ci]
-                w = t.permute(2, 3, 1, 0).reshape(-1, t.shape[0])
-            elif kind == "convT_t":        # -> [(q, ci), co]
-                w = t.permute(2, 3, 0, 1).reshape(-1, t.shape[1])
-            elif kind == "conv1":          # [C,1,ks,ks] -> [C, kpad]
-                w = torch.zeros(t.shape[0], 64, device=t.device)
-                w[:, : t.shape[2] * t.shape[3]] = t.reshape(t.shape[0], -1)
-            elif kind == "conv1_t":
-                w = torch.zeros(64, t.shape[0], device=t.device)
-                w[: t.shape[2] * t.shape[3]] = t.reshape(t.shape[0], -1).t()
-            elif kind == "projA":          # aspp.project [C, 5C,1,1] -> first 4C input channels
-                w = t.reshape(t.shape[0], -1)[:, : 4 * t.shape[0]]
-            elif kind == "projA_t":
-                w = t.reshape(t.shape[0], -1)[:, : 4 * t.shape[0]].t()
-            elif kind == "projB":
-                w = t.reshape(t.shape[0], -1)[:, 4 * t.shape[0]:]
-            elif kind == "projB_t":
-                w = t.reshape(t.shape[0], -1)[:, 4 * t.shape[0]:].t()
-            elif kind == "out1":           # head [1,C,3,3] -> f32 [9*C]
-                return t[0].permute(1, 2, 0).reshape(-1).contiguous()
-            else:
-                raise ValueError(kind)
-            return ops.prep_weight(w.contiguous(), pr)
-        return self.cache.get((name, kind, pr), p[name], make)
+        def pad_rows(t):                   # -> [64, C]
+            w = t.new_zeros(64, t.shape[0])
+            w[: t.shape[2] * t.shape[3]] = t.reshape(t.shape[0], -1).t()
+            return w
+        return {
+            "lin": lambda t: t.reshape(t.shape[0], -1),
+            "lin_t": lambda t: t.reshape(t.shape[0], -1).t(),
+            "conv": lambda t: t.permute(2, 3, 0, 1).reshape(-1, t.shape[1]),            # [Co,Ci,kh,kw] -> [(tap, co), ci]
+            "conv_t": lambda t: t.permute(2, 3, 1, 0).reshape(-1, t.shape[0]),          # -> [(tap, ci), co]
+            "convT": lambda t: t.permute(2, 3, 1, 0).reshape(-1, t.shape[0]),           # ConvTranspose [Ci,Co,2,2] -> [(q, co), ci]
+            "convT_t": lambda t: t.permute(2, 3, 0, 1).reshape(-1, t.shape[1]),         # -> [(q, ci), co]
+            "conv1": pad_cols,
+            "conv1_t": pad_rows,
+            "projA": lambda t: t.reshape(t.shape[0], -1)[:, : 4 * t.shape[0]],          # aspp.project [C, 5C,1,1] -> first 4C input channels
+            "projA_t": lambda t: t.reshape(t.shape[0], -1)[:, : 4 * t.shape[0]].t(),
+            "projB": lambda t: t.reshape(t.shape[0], -1)[:, 4 * t.shape[0]:],
+            "projB_t": lambda t: t.reshape(t.shape[0], -1)[:, 4 * t.shape[0]:].t(),
+            "out1": lambda t: t[0].permute(1, 2, 0).reshape(-1),                        # head [1,C,3,3] -> f32 [9*C]
+        }[kind]
+
+    def _prep(self, p, name, kind):
+        return self.cache.get_layout((name, kind, self.precise), p[name], self._layout(kind), self.precise, raw_f32=kind == "out1")
+
+    def _wgrad_buf(self, grads, name, kind, shape):
+        """(buffer the weight-gradient kernel accumulates into in operand layout `kind`, staged?): the persistent staging buffer of the
+        batched mode (moved by cache.scatter_grads() at the end of backward) or a fresh zero tensor the caller adds into grads[name]"""
+        st = self.cache.grad_staging((name, kind), grads[name], self._layout(kind))
+        if st is not None:
+            return st.view(shape), True
+        return torch.zeros(shape, device=grads[name].device, dtype=torch.float32), False
 
     # ------------------------------------------------------------------ helpers
     def _conv_gn(self, x_act, nb, h, w, cin, wname, gname, G, p, dil, out_act, out_col0, need_grad, res=None):
@@ -93,9 +94,10 @@ class HeadEngine:
         d_raw = ops.new_act(nb * h * w, cout, pr, x_act.device)
         ops.gn_relu_bwd(dy, dy_dtype, S["raw"], L.dtype_of(S["raw"]), p[gname + ".weight"], p[gname + ".bias"], S["mean"], S["rstd"], d_raw,
                         ops.act_dtype(pr), grads[gname + ".weight"], grads[gname + ".bias"], nb, h * w, cout, G, dy_col0=dy_col0)
-        dw = torch.zeros(len(filt), cout, cin, device=x_act.device, dtype=torch.float32)
+        dw, staged = self._wgrad_buf(grads, wname, "conv", (len(filt), cout, cin))
         ops.wgrad(d_raw, x_act, dw, m=cout, n=cin, precise=pr, conv=(nb, h, w), filt=filt)
-        grads[wname].add_(dw.view(ks, ks, cout, cin).permute(2, 3, 0, 1))
+        if not staged:
+            grads[wname].add_(dw.view(ks, ks, cout, cin).permute(2, 3, 0, 1))
         if dx_out is not None:
             ops.gemm(d_raw, self._prep(p, wname, "conv_t"), dx_out, n=cin, k=cout, precise=pr, conv=(nb, h, w), filt=[(-a, -b) for a, b in filt],
                      b_row_stride=cin, out_dtype=dx_dtype, accumulate=accumulate)
@@ -208,10 +210,11 @@ class HeadEngine:
         # transposed conv: bias, weight and data gradients; d_cat is read as [nb, h, 2w', 2*ldp] (pixel (2y+qy, 2x+qx) -> x' = qy*w + x, column block qx)
         ops.colsum(d_cat, adt, nb * H2 * W2, cup, grads[name + "up.bias"], ld=ldp)
         taps_w = [(0, qy * w, 0, qx * ldp, qy * 2 + qx) for qy in range(2) for qx in range(2)]
-        dwq = torch.zeros(4, cin, cup, device=dev, dtype=torch.float32)
+        dwq, staged = self._wgrad_buf(grads, name + "up.weight", "convT_t", (4, cin, cup))
         ops.wgrad(S["x"], d_cat, dwq, m=cin, n=cup, precise=pr, conv=(nb, h, w), taps=taps_w, ld_x=2 * ldp, x_map_w=2 * w, x_lo=ccat,
                   slot_stride=cin * cup, ld_dw=cup)
-        grads[name + "up.weight"].add_(dwq.view(2, 2, cin, cup).permute(2, 3, 0, 1))
+        if not staged:
+            grads[name + "up.weight"].add_(dwq.view(2, 2, cin, cup).permute(2, 3, 0, 1))
         dx = torch.empty(nb * h * w, cin, device=dev, dtype=gtorch)
         taps_d = [(0, qy * w, qx * ldp, (qy * 2 + qx) * cin, 0) for qy in range(2) for qx in range(2)]
         ops.gemm(d_cat, self._prep(p, name + "up.weight", "convT_t"), dx, n=cin, k=cup, precise=pr, conv=(nb, h, w), taps=taps_d, lda=2 * ldp,
@@ -328,10 +331,11 @@ class HeadEngine:
         # output conv
         u2 = ctx["u2"]
         d_u2 = torch.empty(nb * 16 * hw, c.up[1], device=dev, dtype=gtorch)
-        dw9 = torch.zeros(9 * c.up[1], **f32)
+        dw9, staged = self._wgrad_buf(grads, "head.weight", "out1", (9 * c.up[1],))
         L.call("svl_conv_out1_bwd", d_low, u2, adt, u2.shape[-1], self._prep(p, "head.weight", "out1"), d_u2, gdt, d_u2.shape[-1], dw9,
                grads["head.bias"], nb, 4 * h, 4 * w, c.up[1], n_launch=2)
-        grads["head.weight"].add_(dw9.view(3, 3, c.up[1]).permute(2, 0, 1)[None])
+        if not staged:
+            grads["head.weight"].add_(dw9.view(3, 3, c.up[1]).permute(2, 0, 1)[None])
         # decoder
         d_u1, d_sk1 = self._up_bwd(ctx["Su2"], d_u2, gdt, nb, B, N, 2 * h, 2 * w, c.up[0], "up2.", c.up[1] // 16, p, grads)
         del d_u2
@@ -343,9 +347,10 @@ class HeadEngine:
             cs = c.skip[j]
             sh, sw, cin = ctx["geo"][j]
             name = f"skip_proj.{j}.0."
-            dw = torch.zeros(9, cs, cin, **f32)
+            dw, staged = self._wgrad_buf(grads, name + "weight", "conv", (9, cs, cin))
             ops.wgrad(d_sk, ctx["fa"][j], dw, m=cs, n=cin, precise=pr, conv=(B, sh, sw), filt=_f3(1))
-            grads[name + "weight"].add_(dw.view(3, 3, cs, cin).permute(2, 3, 0, 1))
+            if not staged:
+                grads[name + "weight"].add_(dw.view(3, 3, cs, cin).permute(2, 3, 0, 1))
             ops.colsum(d_sk, adt, B * sh * sw, cs, grads[name + "bias"])
             if need_feat_grads:
                 d_f = torch.empty(B, sh, sw, cin, **f32)
@@ -407,10 +412,12 @@ class HeadEngine:
         L.call("svl_map_bcast_add", d_x1, d_gap, L.F32, C, nb, hw, C, 1.0 / hw)
         # conv1
         d_x1_act = ops.to_act(d_x1, pr)
-        dw1 = torch.zeros(C, 64, **f32)
+        dw1, staged = self._wgrad_buf(grads, "conv1.weight", "conv1", (C, 64))
         ops.wgrad(d_x1_act, ctx["col"], dw1, m=C, n=64, precise=pr)
-        grads["conv1.weight"].add_(dw1[:, : c.ks * c.ks].reshape(C, 1, c.ks, c.ks))
+        if not staged:
+            grads["conv1.weight"].add_(dw1[:, : c.ks * c.ks].reshape(C, 1, c.ks, c.ks))
         ops.colsum(d_x1, L.F32, nb * hw, C, grads["conv1.bias"])
+        self.cache.scatter_grads()                                 # every staged weight gradient of this pass -> grads (one launch)
         if not need_feat_grads:
             return d_taps + [None] + d_conv
         d_col = torch.empty(nb * hw, 64, device=dev, dtype=gtorch)

@@ -84,6 +84,7 @@ _PROTOS = {
     "svl_l2norm_fwd": [_P, _L, _P, _P, _I, _L, _P, _L, _I, _F, _P],
     "svl_l2norm_bwd": [_P, _I, _L, _P, _P, _P, _L, _I, _L, _I, _P],
     "svl_cast": [_P, _I, _L, _L, _P, _I, _L, _L, _I, _L, _I, _F, _P],
+    "svl_param_jobs": [_P, _P, _I, _I, _I, _P],
     "svl_colsum": [_P, _I, _L, _L, _I, _P, _P],
     "svl_batch_sum": [_P, _P, _I, _L, _I, _P],
     "svl_axpy": [_P, _P, _F, _L, _P],

@@ -125,6 +125,8 @@ class Trainer:
         self.head.cache.volatile = set(self.g_hd)
         if self.ce is not None:
             self.ce.cache.volatile = set(self.g_ce)
+        for e in (self.vit, self.head):
+            e.cache.batched = not e.precise       # throughput mode: operand copies / staged weight gradients move in one launch per step
         self.world = _world()
         self._capturing, self._graph, self._graph_key, self._hyper = False, None, None, None
         self.exchange = GradExchange(self.g_flat)
@@ -204,6 +206,7 @@ class Trainer:
             for lo, k, idx, _ in classes:
                 L.call("svl_adamw_dev", self.p_flat[lo:], self.g_flat[lo:], self.m_flat[lo:], self.v_flat[lo:], k, self._hyper, idx, o.betas[0],
                        o.betas[1], o.eps, o.wd, gs)
+            self._refresh_operands()
             return
         self.iters += 1
         lr = self.lr_at(self.iters)
@@ -211,6 +214,11 @@ class Trainer:
             L.call("svl_adamw", self.p_flat[lo:], self.g_flat[lo:], self.m_flat[lo:], self.v_flat[lo:], k, lr * mult, o.betas[0], o.betas[1],
                    o.eps, o.wd, self.iters, gs)
         self._bump_caches()
+        self._refresh_operands()
+
+    def _refresh_operands(self):
+        for e in (self.vit, self.head):
+            e.cache.refresh()
 
     def _bump_caches(self):
         for e in (self.vit, self.head, self.ce):
@@ -255,6 +263,7 @@ class Trainer:
             self._hyper = torch.zeros(5, device=img.device)
             self.supervised_step(self._g_img, self._g_mask, update=False)        # eager pass: frozen-weight operand cache, lazy attributes
             self._bump_caches()                                                   # trainable-weight casts must be part of the graph
+            self._refresh_operands()                                              # batched mode: job tables built (host -> device copies) before capture
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             self._capturing, l0 = True, L.launches

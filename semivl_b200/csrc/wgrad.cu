@@ -507,6 +507,193 @@ int try_launch_strip(const svl_wgrad_desc* d, int block_n, cudaStream_t stream) 
   return 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Row-stacked variant for 3 x 3 (dilation 1) convolutions with 32 output channels -- the 32-channel `Up` convolutions of the decode head on
+// 128-pixel-wide maps, whose weight gradients ran at 12.5 % useful tensor work in the strip kernel (one CTA group per filter row, each
+// loading dy and x again) and 5x over their HBM time.  Here ONE step = 64 pixels of one x row r against the dy rows r-1, r, r+1:
+//   A (M = 128) = two 64-element MN-major chunks = two dy rows; a 32-channel row fills the first 64 bytes of each 128-byte operand line (TMA
+//                 pads a 64-byte inner box to the swizzle span; the other half is stale shared memory and only feeds accumulator lanes
+//                 32..63 / 96..127, which nobody reads).  MMA 1: rows r-1 | r (filter rows +1 | 0), MMA 2: row r+1 | unused (filter row -1)
+//   B (N = 192) = three dx taps: the x strip (66 pixels) read 0 / 1 / 2 pixels further (LBO = 128 bytes), 64 channels per chunk
+// so x is loaded once (not once per filter row and CTA group), dy three times from L2, all nine taps come out of two MMAs per 16 pixels, and the
+// whole problem is one output tile split over K (pixels) across the SMs.  Rows / pixels outside the image are TMA zero fill.
+// (A [row a | row b] packing of two 32-channel rows into one operand line is not reachable with TMA: measured, a 64-byte inner box lands
+// on a 128-byte pitch; scratch/wgrad_dump.py.)
+struct RowstackParams {
+  int nb, h, w, tiles_x, cin;
+  int64_t num_steps;
+  int dy_koff, x_koff, splits, stages;
+  uint32_t strip_stride, stage_bytes;
+  int slot[3][3];                  // dW slot of filter position (dy + 1, dx + 1)
+  float* dw; int64_t ld_dw, slot_stride;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_rowstack_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ RowstackParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + p.stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 1);
+  volatile uint32_t* tmem_ptr_gen = (volatile uint32_t*)(smem_raw + (tmem_ptr_addr - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t per = (p.num_steps + p.splits - 1) / p.splits;
+  const int64_t s0 = (int64_t)blockIdx.x * per;
+  const int64_t s1 = s0 + per < p.num_steps ? s0 + per : p.num_steps;
+  const bool has_work = s1 > s0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDY);
+    ptx::prefetch_tmap(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tfull_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, 512u);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (has_work) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = 3u * 64u * 64u + 66u * (uint32_t)p.cin * 2u;      // bytes the four boxes really transfer
+        int tix = (int)(s0 % p.tiles_x), r = (int)((s0 / p.tiles_x) % p.h), img = (int)(s0 / ((int64_t)p.tiles_x * p.h));
+        for (int64_t s = s0; s < s1; ++s) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = smem_base + stage * p.stage_bytes, sb = sa + 4 * kBoxBytes;
+          const int cx = tix * 64, cr = r, ci = img;
+          if (++tix == p.tiles_x) { tix = 0; if (++r == p.h) { r = 0; ++img; } }
+          for (int c = 0; c < 3; ++c) ptx::tma_load_4d(sa + c * kBoxBytes, &tmDY, full_bar(stage), p.dy_koff, cx, cr - 1 + c, ci);
+          ptx::tma_load_4d(sb, &tmX, full_bar(stage), p.x_koff, cx - 1, cr, ci);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = ptx::make_idesc_bf16(BM, 192, 1, 1);
+      const bool leader = ptx::elect_one();
+      const uint64_t tmpl_a = ptx::make_smem_desc(0, kBoxBytes, 1024);     // M chunks (dy rows) one box apart
+      const uint64_t tmpl_b = ptx::make_smem_desc(0, 128, 1024);           // N chunk t = the strip read t pixels (128-byte K rows) further
+      int stage = 0;
+      uint32_t phase = 0, accum = 0;
+      for (int64_t s = s0; s < s1; ++s) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_base + stage * p.stage_bytes, sb = sa + 4 * kBoxBytes;
+        if (leader) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 16; ++kk)
+              ptx::umma_bf16(tmem_base + (uint32_t)a * 256u, tmpl_a + (uint64_t)((sa + a * 2 * kBoxBytes + kk * 2048) >> 4),
+                             tmpl_b + (uint64_t)((sb + kk * 2048) >> 4), idesc, kk > 0 ? 1u : accum);
+          }
+          ptx::umma_commit(empty_bar(stage));
+        }
+        accum = 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) ptx::umma_commit(tfull_bar);
+      __syncwarp();
+    } else {
+      const int q = warp & 3;                            // TMEM lane quarter: 0 = first dy row of an MMA (channels 0..31), 2 = its second row
+      ptx::mbar_wait(tfull_bar, 0);
+      ptx::tc_fence_after();
+      if (q == 0 || q == 2) {
+        for (int a = 0; a < (q == 0 ? 2 : 1); ++a) {
+          const int t = a == 0 ? (q == 0 ? 1 : 0) : -1;  // filter row: MMA 1 = dy rows r-1 | r -> +1 | 0, MMA 2 = dy row r+1 -> -1
+          for (int dxi = 0; dxi < 3; ++dxi)
+            for (int c0 = 0; c0 < p.cin; c0 += 32) {
+              uint32_t v[32];
+              ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + dxi * 64 + c0), v);
+              ptx::tmem_ld_wait();
+              float* dst = p.dw + (int64_t)p.slot[t + 1][dxi] * p.slot_stride + (int64_t)lane * p.ld_dw + c0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                red_add_v4(dst + g * 4, __uint_as_float(v[g * 4]) * p.alpha, __uint_as_float(v[g * 4 + 1]) * p.alpha,
+                           __uint_as_float(v[g * 4 + 2]) * p.alpha, __uint_as_float(v[g * 4 + 3]) * p.alpha);
+            }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// Returns 1 when the row-stacked kernel was launched, 0 when the problem does not qualify, < 0 on error.
+int try_launch_rowstack(const svl_wgrad_desc* d, cudaStream_t stream) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SVL_WGRAD_ROWSTACK"); on = e ? atoi(e) : 1; }
+  if (!on || !d->conv || d->num_taps != 9 || d->m != 32 || (d->n != 32 && d->n != 64) || d->x_map_w != 0 || d->w < 64) return 0;
+  if (((uintptr_t)d->dw & 15) != 0 || d->ld_dw % 4 != 0 || d->slot_stride % 4 != 0) return 0;
+  RowstackParams p;
+  memset(&p, 0, sizeof(p));
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) p.slot[a][b] = -1;
+  for (int t = 0; t < 9; ++t) {
+    const int fy = d->tap_dy[t], fx = d->tap_dx[t];
+    if (fy < -1 || fy > 1 || fx < -1 || fx > 1 || d->tap_dy_koff[t] != d->tap_dy_koff[0] || d->tap_x_koff[t] != d->tap_x_koff[0]) return 0;
+    p.slot[fy + 1][fx + 1] = d->tap_slot[t];
+  }
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) if (p.slot[a][b] < 0) return 0;
+  p.nb = d->nb; p.h = d->h; p.w = d->w; p.cin = d->n;
+  p.tiles_x = (d->w + 63) / 64;
+  p.num_steps = (int64_t)d->nb * d->h * p.tiles_x;
+  p.dy_koff = d->tap_dy_koff[0]; p.x_koff = d->tap_x_koff[0];
+  p.strip_stride = (66u * 128u + 1023u) & ~1023u;
+  p.stage_bytes = 4 * kBoxBytes + p.strip_stride;
+  p.stages = (int)(kSmemBudget / p.stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.dw = d->dw; p.ld_dw = d->ld_dw; p.slot_stride = d->slot_stride;
+  p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  const int64_t dy_cols = d->dy_cols > 0 ? d->dy_cols : d->ld_dy;
+  const int64_t x_cols = d->x_cols > 0 ? d->x_cols : d->ld_x;
+  CUtensorMap tmDY, tmX;
+  {
+    uint64_t dims[4] = {(uint64_t)dy_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t st[3] = {(uint64_t)d->ld_dy * 2, (uint64_t)d->ld_dy * 2 * d->w, (uint64_t)d->ld_dy * 2 * d->w * d->h};
+    uint32_t box[4] = {32u, 64u, 1u, 1u};
+    if (int rc = tma_encode_bf16(&tmDY, d->dy, 4, dims, st, box)) return rc;
+    uint64_t dimsx[4] = {(uint64_t)x_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t stx[3] = {(uint64_t)d->ld_x * 2, (uint64_t)d->ld_x * 2 * d->w, (uint64_t)d->ld_x * 2 * d->w * d->h};
+    uint32_t boxx[4] = {(uint32_t)p.cin, 66u, 1u, 1u};
+    if (int rc = tma_encode_bf16(&tmX, d->x, 4, dimsx, stx, boxx)) return rc;
+  }
+  int splits = d->splits > 0 ? d->splits : num_sms();
+  if (splits > p.num_steps) splits = (int)p.num_steps;
+  p.splits = splits;
+  const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 8 * (2 * kMaxStages + 2) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVL_CUDA(cudaFuncSetAttribute(wgrad_rowstack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  wgrad_rowstack_kernel<<<(unsigned)splits, kThreads, smem, stream>>>(tmDY, tmX, p);
+  SVL_LAUNCH_CHECK();
+  return 1;
+}
+
 }  // namespace
 }  // namespace svl
 
@@ -548,7 +735,9 @@ extern "C" int svl_wgrad(const svl_wgrad_desc* d, void* stream) {
     p.block_n = best;
   }
   {
-    int rc = try_launch_strip(d, p.block_n, (cudaStream_t)stream);
+    int rc = try_launch_rowstack(d, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : SVL_OK;
+    rc = try_launch_strip(d, p.block_n, (cudaStream_t)stream);
     if (rc != 0) return rc < 0 ? rc : SVL_OK;
   }
   p.num_m_tiles = (d->m + BM - 1) / BM;

@@ -189,7 +189,7 @@ def test_wgrad_linear(ops, rows, m, n, precise):
                                                      (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
                                                      (4, 8, 8, 256, 64, 1, 1), (2, 128, 128, 64, 32, 3, 1), (3, 64, 64, 96, 64, 3, 1),
                                                      (2, 32, 32, 256, 128, 3, 1), (2, 164, 164, 32, 32, 3, 1), (3, 82, 82, 64, 64, 3, 1),
-                                                     (2, 204, 204, 64, 32, 3, 1), (2, 100, 70, 128, 64, 3, 1)])
+                                                     (2, 204, 204, 64, 32, 3, 1), (2, 100, 70, 128, 64, 3, 1), (3, 67, 130, 32, 32, 3, 1), (1, 65, 64, 64, 32, 3, 1)])
 @pytest.mark.parametrize("precise", [False, True])
 def test_wgrad_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
     g = torch.Generator(device="cuda").manual_seed(nb * h + cin + cout)

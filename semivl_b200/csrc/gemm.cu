@@ -789,6 +789,10 @@ int auto_block_n(int n) {
 }  // namespace
 }  // namespace svl
 
+namespace svl {
+int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream);      // conv_roll.cu: 3 x 3 convolutions with 32 / 64 output channels
+}
+
 using namespace svl;
 
 extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
@@ -806,6 +810,10 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   SVL_CHECK_ARG(d->act != SVL_ACT_GELU_DSAVE || d->preact_out, "svl_gemm: SVL_ACT_GELU_DSAVE needs preact_out (it receives gelu')");
   SVL_CHECK_ARG(d->act != SVL_ACT_SAVED && d->dact_kind != SVL_ACT_GELU_DSAVE, "svl_gemm: SVL_ACT_SAVED is a dact_kind, SVL_ACT_GELU_DSAVE an act");
   if (int rc = svl_check_device()) return rc;
+  if (d->a_conv) {
+    const int rc = try_launch_conv_roll(d, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : SVL_OK;
+  }
 
   GemmParams p;
   p.cluster = 0;

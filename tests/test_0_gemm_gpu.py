@@ -129,7 +129,9 @@ def test_ffn_epilogues_bf16(ops, m, n, k):
 
 @pytest.mark.parametrize("nb,h,w,cin,cout,ks,dil", [(5, 12, 12, 64, 48, 3, 2), (7, 32, 32, 128, 128, 3, 6), (3, 64, 64, 128, 64, 3, 1),
                                                      (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
-                                                     (2, 128, 128, 32, 1, 3, 1), (4, 8, 8, 256, 64, 1, 1)])
+                                                     (2, 128, 128, 32, 1, 3, 1), (4, 8, 8, 256, 64, 1, 1), (3, 37, 128, 64, 32, 3, 1),
+                                                     (2, 21, 164, 32, 64, 3, 1), (5, 1, 130, 32, 32, 3, 1), (150, 16, 128, 32, 32, 3, 1),
+                                                     (2, 40, 204, 64, 64, 3, 1)])
 @pytest.mark.parametrize("precise", [False, True])
 def test_implicit_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
     g = torch.Generator(device="cuda").manual_seed(nb * h + cin + cout)
@@ -147,6 +149,14 @@ def test_implicit_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
     out = torch.full((nb, h, w, cout), float("nan"), device="cuda")
     ops.gemm(a, b, out, n=cout, k=cin, precise=precise, conv=(nb, h, w), filt=filt, b_row_stride=cout, bias=bias)
     assert _rel(out, ref) < (3e-5 if precise else 1e-4)
+    if not precise:
+        # bf16 output (+ ReLU): the 3 x 3 / 32-64 channel / >= 96-pixel-wide cases take the rolling-accumulator kernel (conv_roll.cu)
+        from semivl_b200 import lib as L
+        out16 = torch.full((nb, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, b, out16, n=cout, k=cin, conv=(nb, h, w), filt=filt, b_row_stride=cout, bias=bias)
+        assert _rel(out16, ref) < 6e-3
+        ops.gemm(a, b, out16, n=cout, k=cin, conv=(nb, h, w), filt=filt, b_row_stride=cout, act=L.ACT_RELU)
+        assert _rel(out16, (ref - bias).clamp_min(0)) < 6e-3
 
 
 def test_convtranspose_scatter(ops):

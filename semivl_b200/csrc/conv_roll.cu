@@ -18,6 +18,10 @@
 //   with the strip loads, the epilogue (idle 3/4 of the time), the TMEM read-modify-write of always-accumulating MMAs and the pixel-shifted
 //   descriptors all ruled out by knock-out runs.  Templating on (cin / 16, cout), hoisting the B descriptors out of the strip loop and making
 //   the non-wrapping case straight-line code halved the launch time.
+//   * maps at most 64 pixels wide (the first Up block: 64 x 64 at the 512^2 crop) use the DUAL form: a tile is one row of TWO maps
+//     (lanes 0..63 | 64..127), which cannot be one shifted window of a haloed strip (the second map would start 66, not 64, lines in), so
+//     each dx tap gets its own box {64 channels, 64 pixels, 1 row, 2 maps} loaded at pixel offset dx - 1 and a pipeline stage of its own;
+//   * more than 64 input channels = two 64-channel K chunks per stage;
 //   * warp 0 = TMA producer (weights once, strips through a shared-memory ring), warp 1 = MMA issuer, warps 2..17 = four epilogue
 //     quartets (tcgen05.ld -> bias / ReLU -> bf16 NHWC store -> tcgen05.st zeros -> block free); the blocks go to the quartets in turn: one
 //     quartet's chain of TMEM load, store and re-zero latencies is ~4x the tensor time of a strip (measured: 4 warps alone left the
@@ -38,10 +42,10 @@ constexpr int kRollMaxStages = 8;
 constexpr int kRollMaxBlocks = 16;
 
 struct RollParams {
-  int nb, h, w, tiles_x, roll_rows, chunks, units;
+  int nb, h, w, tiles_x, roll_rows, chunks, units;   // tiles_x: 128-pixel columns of a map (single form) / 1 (dual form: a unit column is a pair of maps)
   int cin, cout, nblk;               // nblk = 512 / cout accumulator blocks in the ring
   int a_koff, stages;
-  uint32_t strip_bytes, strip_stride, wgroup_bytes;      // wgroup = the three filter rows of one dx tap: 3 * cout rows of 128 bytes
+  uint32_t stage_tx, chunk_stride, stage_stride, wgroup_bytes;   // wgroup = the three filter rows of one (dx tap, K chunk): 3 * cout rows of 128 bytes
   int wrow[3][3], wcol[3][3];        // weight-tensor coordinates (row, column) of filter position (dy + 1, dx + 1)
   __nv_bfloat16* out; int64_t ldc;
   const float* bias; int relu;
@@ -55,14 +59,15 @@ __device__ __forceinline__ void tmem_zero_32(uint32_t taddr) {
   ptx::tmem_st_32x32(taddr, z);
 }
 
-template <int KS, int COUT>
+template <int KS, int COUT, bool DUAL>
 __global__ void __launch_bounds__(kRollThreads, 1)
 conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ RollParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_w = (raw + 1023u) & ~1023u;
-  const uint32_t smem_a = smem_w + 3u * p.wgroup_bytes;
-  const uint32_t bar_base = smem_a + (uint32_t)p.stages * p.strip_stride;
+  constexpr int KC = (KS + 3) / 4;                 // 64-channel K chunks
+  const uint32_t smem_a = smem_w + 3u * KC * p.wgroup_bytes;
+  const uint32_t bar_base = smem_a + (uint32_t)p.stages * p.stage_stride;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kRollMaxStages + s); };
   auto bfull_bar = [&](int b) { return bar_base + 8u * (2 * kRollMaxStages + b); };
@@ -98,26 +103,32 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(wbar, 3u * p.wgroup_bytes);
+      ptx::mbar_arrive_expect_tx(wbar, 3u * KC * p.wgroup_bytes);
       for (int dxi = 0; dxi < 3; ++dxi)
-        for (int k = 0; k < 3; ++k)              // block order inside a dx group: output rows r-1, r, r+1 <- filter rows +1, 0, -1
-          ptx::tma_load_2d(smem_w + (uint32_t)dxi * p.wgroup_bytes + (uint32_t)(k * p.cout) * 128u, &tmW, wbar, p.wcol[2 - k][dxi], p.wrow[2 - k][dxi]);
+        for (int kc = 0; kc < KC; ++kc)
+          for (int k = 0; k < 3; ++k)            // block order inside a group: output rows r-1, r, r+1 <- filter rows +1, 0, -1
+            ptx::tma_load_2d(smem_w + (uint32_t)(dxi * KC + kc) * p.wgroup_bytes + (uint32_t)(k * COUT) * 128u, &tmW, wbar,
+                             p.wcol[2 - k][dxi] + kc * 64, p.wrow[2 - k][dxi]);
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int c = u % p.chunks, tx = (u / p.chunks) % p.tiles_x, cn = u / (p.chunks * p.tiles_x);
         const int y0 = c * p.roll_rows, y1 = min(y0 + p.roll_rows, p.h);
         for (int rr = y0 - 1; rr <= y1; ++rr) {
+          for (int dxi = 0; dxi < (DUAL ? 3 : 1); ++dxi) {
 #ifdef SVL_GEMM_DIAG
-          const long long tp = clock64();
+            const long long tp = clock64();
 #endif
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
 #ifdef SVL_GEMM_DIAG
-          if (p.trace && blockIdx.x == 0) p.trace[4] += clock64() - tp;
+            if (p.trace && blockIdx.x == 0) p.trace[4] += clock64() - tp;
 #endif
-          ptx::mbar_arrive_expect_tx(full_bar(stage), p.strip_bytes);
-          ptx::tma_load_4d(smem_a + (uint32_t)stage * p.strip_stride, &tmA, full_bar(stage), p.a_koff, tx * 128 - 1, rr, cn);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            ptx::mbar_arrive_expect_tx(full_bar(stage), p.stage_tx);
+            for (int kc = 0; kc < KC; ++kc)
+              ptx::tma_load_4d(smem_a + (uint32_t)stage * p.stage_stride + (uint32_t)kc * p.chunk_stride, &tmA, full_bar(stage), p.a_koff + kc * 64,
+                               DUAL ? dxi - 1 : tx * 128 - 1, rr, DUAL ? 2 * cn : cn);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -137,8 +148,9 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int dxi = 0; dxi < 3; ++dxi)
 #pragma unroll
-      for (int kk = 0; kk < KS; ++kk) bdesc[dxi][kk] = tmpl + (uint64_t)((smem_w >> 4) + (uint32_t)(dxi * 3 * COUT * 8 + kk * 2));
-    const uint32_t a_base = smem_a >> 4, a_step = p.strip_stride >> 4;
+      for (int kk = 0; kk < KS; ++kk)
+        bdesc[dxi][kk] = tmpl + (uint64_t)((smem_w >> 4) + (uint32_t)((dxi * KC + (kk >> 2)) * 3 * COUT * 8 + (kk & 3) * 2));
+    const uint32_t a_base = smem_a >> 4, a_step = p.stage_stride >> 4, a_chunk = p.chunk_stride >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int blk = 0;                               // ring block of the current strip's first output row
@@ -169,41 +181,44 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef SVL_GEMM_DIAG
         const long long t1 = clock64();
 #endif
-        ptx::mbar_wait(full_bar(stage), phase);
-        ptx::tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(blk * COUT);
+        const bool last = s == nstrips - 1;
+        const int first = NBLK - blk;              // blocks before the ring wraps (>= 3: no wrap inside this strip)
+#pragma unroll
+        for (int dxi = 0; dxi < 3; ++dxi) {
+          if (DUAL || dxi == 0) {                  // single form: one stage holds the strip of all three taps; dual form: a stage per tap
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+          }
+          const uint32_t a_lo = a_base + (uint32_t)stage * a_step + (DUAL ? 0u : (uint32_t)(dxi * 8));
+          if (first >= 3) {
+            if (leader) {
+#pragma unroll
+              for (int kk = 0; kk < KS; ++kk)
+                ptx::umma_bf16(dcol, tmpl + (uint64_t)(a_lo + (uint32_t)((kk >> 2) * a_chunk + (kk & 3) * 2)), bdesc[dxi][kk], idesc3, 1u);
+            }
+          } else if (leader) {                     // the ring wraps inside the strip's three blocks: two MMAs per step
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+              const uint64_t adesc = tmpl + (uint64_t)(a_lo + (uint32_t)((kk >> 2) * a_chunk + (kk & 3) * 2));
+              ptx::umma_bf16(dcol, adesc, bdesc[dxi][kk], first == 2 ? idesc2 : idesc1, 1u);
+              ptx::umma_bf16(tmem_base, adesc, bdesc[dxi][kk] + (uint64_t)(first * COUT * 8), first == 1 ? idesc2 : idesc1, 1u);
+            }
+          }
+          if (DUAL || dxi == 2) {
+            if (leader) ptx::umma_commit(empty_bar(stage));
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
 #ifdef SVL_GEMM_DIAG
         if (p.trace && blockIdx.x == 0 && lane == 0) { p.trace[1] += t1 - t0; p.trace[2] += clock64() - t1; p.trace[3] += 1; }
 #endif
-        const uint32_t a_lo = a_base + (uint32_t)stage * a_step;
-        const uint32_t dcol = tmem_base + (uint32_t)(blk * COUT);
-        const bool last = s == nstrips - 1;
-        if (blk <= NBLK - 3) {
-          if (leader) {
-#pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi)
-#pragma unroll
-              for (int kk = 0; kk < KS; ++kk) ptx::umma_bf16(dcol, tmpl + (uint64_t)(a_lo + (uint32_t)(dxi * 8 + kk * 2)), bdesc[dxi][kk], idesc3, 1u);
-          }
-        } else {                               // the ring wraps inside the strip's three blocks: two MMAs per step
-          const int first = NBLK - blk;
-          if (leader) {
-#pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi)
-#pragma unroll
-              for (int kk = 0; kk < KS; ++kk) {
-                const uint64_t adesc = tmpl + (uint64_t)(a_lo + (uint32_t)(dxi * 8 + kk * 2));
-                ptx::umma_bf16(dcol, adesc, bdesc[dxi][kk], first == 2 ? idesc2 : idesc1, 1u);
-                ptx::umma_bf16(tmem_base, adesc, bdesc[dxi][kk] + (uint64_t)(first * COUT * 8), first == 1 ? idesc2 : idesc1, 1u);
-              }
-          }
-        }
         if (leader) {
-          ptx::umma_commit(empty_bar(stage));
           complete(0);
           if (last) { complete(1); complete(2); }
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         blk += last ? 3 : 1;
         if (blk >= NBLK) { blk -= NBLK; bphase ^= 1u; }
       }
@@ -229,7 +244,10 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       const int c = u % p.chunks, tx = (u / p.chunks) % p.tiles_x, cn = u / (p.chunks * p.tiles_x);
       const int y0 = c * p.roll_rows, nrows = min(y0 + p.roll_rows, p.h) - y0;
-      const int x = tx * 128 + q * 32 + lane;
+      // single form: lane = pixel of the 128-pixel column tx; dual form: lanes 0..63 | 64..127 = pixels of the maps 2 cn | 2 cn + 1
+      const int x = DUAL ? (q & 1) * 32 + lane : tx * 128 + q * 32 + lane;
+      const int img = DUAL ? 2 * cn + (q >> 1) : cn;
+      const bool valid = x < p.w && img < p.nb;
       for (int j = 0; j < nrows + 4; ++j) {
         if (turn != quartet) {                 // another quartet's block
           if (++turn == kRollQuartets) turn = 0;
@@ -244,14 +262,14 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef SVL_GEMM_DIAG
         if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) { p.trace[5] += clock64() - te; p.trace[6] += 1; }
 #endif
-        const uint32_t taddr = lane_base + (uint32_t)(blk * p.cout);
+        const uint32_t taddr = lane_base + (uint32_t)(blk * COUT);
         if (j >= 2 && j < nrows + 2) {         // a row of this unit: y0 + j - 2
-          __nv_bfloat16* dst = p.out + (((int64_t)cn * p.h + (y0 + j - 2)) * p.w + x) * p.ldc;
-          for (int c0 = 0; c0 < p.cout; c0 += 32) {
+          __nv_bfloat16* dst = p.out + (((int64_t)img * p.h + (y0 + j - 2)) * p.w + x) * p.ldc;
+          for (int c0 = 0; c0 < COUT; c0 += 32) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
-            if (x < p.w) {
+            if (valid) {
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
                 float f[16];
@@ -273,7 +291,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        for (int c0 = 0; c0 < p.cout; c0 += 32) tmem_zero_32(taddr + (uint32_t)c0);
+        for (int c0 = 0; c0 < COUT; c0 += 32) tmem_zero_32(taddr + (uint32_t)c0);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -298,8 +316,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream) {
   static int roll_rows = -1;
   if (roll_rows < 0) { const char* e = getenv("SVL_CONV_ROLL"); roll_rows = e ? atoi(e) : 16; }
-  if (roll_rows < 1 || !d->a_conv || d->num_taps != 9 || d->a_map_w != 0 || d->w < 96) return 0;
-  if ((d->n != 32 && d->n != 64) || (d->k_per_tap != 32 && d->k_per_tap != 64)) return 0;
+  if (roll_rows < 1 || !d->a_conv || d->num_taps != 9 || d->a_map_w != 0 || d->w < 33) return 0;
+  if ((d->n != 32 && d->n != 64) || (d->k_per_tap != 32 && d->k_per_tap != 64 && d->k_per_tap != 128)) return 0;
   if (d->out_dtype != SVL_BF16 || d->out_mode != SVL_OUT_LINEAR || d->preact_out || d->dact_src || d->residual || d->row_bias || d->accumulate) return 0;
   if (d->act != SVL_ACT_NONE && d->act != SVL_ACT_RELU) return 0;
   if (d->alpha != 0.f && d->alpha != 1.f) return 0;
@@ -314,19 +332,26 @@ int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream) {
     p.wcol[fy + 1][fx + 1] = d->tap_b_col[t];
   }
   for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) if (p.wrow[a][b] < 0) return 0;
+  const bool dual = d->w <= 64;                   // two maps side by side in the 128 accumulator lanes
+  if (!dual && d->w < 96) return 0;               // 65..95-pixel rows would leave a third of a 128-pixel tile empty: generic engine
   p.nb = d->nb; p.h = d->h; p.w = d->w;
   p.cin = d->k_per_tap; p.cout = d->n; p.nblk = 512 / p.cout;
-  p.tiles_x = (d->w + 127) / 128;
+  const int kc = (p.cin + 63) / 64;
+  p.tiles_x = dual ? 1 : (d->w + 127) / 128;
   p.roll_rows = roll_rows < d->h ? roll_rows : d->h;
   p.chunks = (d->h + p.roll_rows - 1) / p.roll_rows;
-  p.units = d->nb * p.tiles_x * p.chunks;
+  p.units = (dual ? (d->nb + 1) / 2 : d->nb) * p.tiles_x * p.chunks;
   p.a_koff = d->tap_a_koff[0];
-  p.strip_bytes = 130u * 128u;
-  p.strip_stride = (p.strip_bytes + 1023u) & ~1023u;
+  const uint32_t box_bytes = (dual ? 128u : 130u) * 128u;
+  p.chunk_stride = (box_bytes + 1023u) & ~1023u;
+  p.stage_stride = (uint32_t)kc * p.chunk_stride;
+  p.stage_tx = (uint32_t)kc * box_bytes;
   p.wgroup_bytes = (uint32_t)(3 * p.cout) * 128u;
-  p.stages = (int)((200u * 1024u - 3u * p.wgroup_bytes) / p.strip_stride);
+  const size_t wbytes = 3 * (size_t)kc * p.wgroup_bytes;
+  const size_t fixed = 1024 + wbytes + 8 * (2 * kRollMaxStages + 2 * kRollMaxBlocks + 2) + 16;
+  if (fixed + 2 * (size_t)p.stage_stride > 227 * 1024) return 0;
+  p.stages = (int)((227 * 1024 - fixed) / p.stage_stride);
   if (p.stages > kRollMaxStages) p.stages = kRollMaxStages;
-  if (p.stages < 3) return 0;
   p.out = (__nv_bfloat16*)d->out; p.ldc = d->ldc; p.bias = d->bias; p.relu = d->act == SVL_ACT_RELU;
 #ifdef SVL_GEMM_DIAG
   { const char* e = getenv("SVL_ROLL_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 10) : nullptr; }
@@ -336,29 +361,38 @@ int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream) {
     const int64_t a_cols = d->a_cols > 0 ? d->a_cols : d->lda;
     uint64_t dims[4] = {(uint64_t)a_cols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
     uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->w, (uint64_t)d->lda * 2 * d->w * d->h};
-    uint32_t box[4] = {64u, 130u, 1u, 1u};
+    uint32_t box[4] = {64u, dual ? 64u : 130u, 1u, dual ? 2u : 1u};
     if (int rc = tma_encode_bf16(&tmA, d->a, 4, dims, strides, box)) return rc;
     uint64_t dimsw[2] = {(uint64_t)d->ldb, (uint64_t)d->b_rows};
     uint64_t stridesw[1] = {(uint64_t)d->ldb * 2};
     uint32_t boxw[2] = {64u, (uint32_t)p.cout};
     if (int rc = tma_encode_bf16(&tmW, d->b, 2, dimsw, stridesw, boxw)) return rc;
   }
-  const size_t smem = 1024 + 3 * (size_t)p.wgroup_bytes + (size_t)p.stages * p.strip_stride + 8 * (2 * kRollMaxStages + 2 * kRollMaxBlocks + 2) + 16;
+  const size_t smem = fixed + (size_t)p.stages * p.stage_stride;
   const int grid = p.units < num_sms() ? p.units : num_sms();
-#define SVL_LAUNCH_ROLL(KS, COUT)                                                                                          \
-  do {                                                                                                                     \
-    static bool attr_set = false;                                                                                          \
-    if (!attr_set) {                                                                                                       \
-      SVL_CUDA(cudaFuncSetAttribute(conv_roll_kernel<KS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr_set = true;                                                                                                     \
-    }                                                                                                                      \
-    conv_roll_kernel<KS, COUT><<<grid, kRollThreads, smem, stream>>>(tmA, tmW, p);                                         \
+#define SVL_LAUNCH_ROLL_AS(KS, COUT, DUALV)                                                                                       \
+  do {                                                                                                                            \
+    static bool attr_set = false;                                                                                                 \
+    if (!attr_set) {                                                                                                              \
+      SVL_CUDA(cudaFuncSetAttribute(conv_roll_kernel<KS, COUT, DUALV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                                            \
+    }                                                                                                                             \
+    conv_roll_kernel<KS, COUT, DUALV><<<grid, kRollThreads, smem, stream>>>(tmA, tmW, p);                                         \
   } while (0)
-  if (p.cin == 32 && p.cout == 32) SVL_LAUNCH_ROLL(2, 32);
-  else if (p.cin == 64 && p.cout == 32) SVL_LAUNCH_ROLL(4, 32);
-  else if (p.cin == 32 && p.cout == 64) SVL_LAUNCH_ROLL(2, 64);
-  else SVL_LAUNCH_ROLL(4, 64);
+#define SVL_LAUNCH_ROLL(KS, COUT)                        \
+  do {                                                   \
+    if (dual) SVL_LAUNCH_ROLL_AS(KS, COUT, true);        \
+    else SVL_LAUNCH_ROLL_AS(KS, COUT, false);            \
+  } while (0)
+  const int ks = p.cin / 16;
+  if (ks == 2 && p.cout == 32) SVL_LAUNCH_ROLL(2, 32);
+  else if (ks == 4 && p.cout == 32) SVL_LAUNCH_ROLL(4, 32);
+  else if (ks == 8 && p.cout == 32) SVL_LAUNCH_ROLL(8, 32);
+  else if (ks == 2 && p.cout == 64) SVL_LAUNCH_ROLL(2, 64);
+  else if (ks == 4 && p.cout == 64) SVL_LAUNCH_ROLL(4, 64);
+  else SVL_LAUNCH_ROLL(8, 64);
 #undef SVL_LAUNCH_ROLL
+#undef SVL_LAUNCH_ROLL_AS
   SVL_LAUNCH_CHECK();
   return 1;
 }

@@ -131,7 +131,8 @@ def test_ffn_epilogues_bf16(ops, m, n, k):
                                                      (2, 128, 128, 32, 32, 3, 1), (2, 5, 5, 128, 128, 3, 1), (3, 51, 51, 64, 16, 3, 1),
                                                      (2, 128, 128, 32, 1, 3, 1), (4, 8, 8, 256, 64, 1, 1), (3, 37, 128, 64, 32, 3, 1),
                                                      (2, 21, 164, 32, 64, 3, 1), (5, 1, 130, 32, 32, 3, 1), (150, 16, 128, 32, 32, 3, 1),
-                                                     (2, 40, 204, 64, 64, 3, 1)])
+                                                     (2, 40, 204, 64, 64, 3, 1), (5, 64, 64, 64, 64, 3, 1), (3, 40, 48, 32, 32, 3, 1),
+                                                     (2, 20, 130, 128, 32, 3, 1), (7, 33, 64, 128, 32, 3, 1)])
 @pytest.mark.parametrize("precise", [False, True])
 def test_implicit_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
     g = torch.Generator(device="cuda").manual_seed(nb * h + cin + cout)

@@ -261,6 +261,9 @@ class Trainer:
         if self._graph is None or self._graph_key != key:
             self._g_img, self._g_mask = img.clone(), mask.clone()
             self._hyper = torch.zeros(5, device=img.device)
+            self._hyper_host = [torch.zeros(5, dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._hyper_done = [torch.cuda.Event() for _ in range(8)]
+            self._hyper_i = 0
             self.supervised_step(self._g_img, self._g_mask, update=False)        # eager pass: frozen-weight operand cache, lazy attributes
             self._bump_caches()                                                   # trainable-weight casts must be part of the graph
             self._refresh_operands()                                              # batched mode: job tables built (host -> device copies) before capture
@@ -276,7 +279,14 @@ class Trainer:
             L.launches = l0
         self._g_img.copy_(img, non_blocking=True)
         self._g_mask.copy_(mask, non_blocking=True)
-        self._hyper.copy_(torch.tensor(self._step_scalars(self.iters + 1), dtype=torch.float32))
+        # the step's scalars travel through a ring of PINNED host slots: a copy from pageable memory would block the host until everything
+        # queued before it (the previous step) has run, i.e. one graph launch latency of GPU idle time per step
+        slot = self._hyper_i % len(self._hyper_host)
+        self._hyper_i += 1
+        self._hyper_done[slot].synchronize()                       # the copy that last read this slot has run (long ago)
+        self._hyper_host[slot].copy_(torch.tensor(self._step_scalars(self.iters + 1), dtype=torch.float32))
+        self._hyper.copy_(self._hyper_host[slot], non_blocking=True)
+        self._hyper_done[slot].record()
         self._graph.replay()
         L.launches += self._graph_launches
         self.iters += 1

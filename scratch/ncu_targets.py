@@ -51,6 +51,13 @@ import ctypes as Cc
 lab = torch.randint(0, 21, (16, 512, 512), device=dev); coef = torch.full((1,), 1e-6, device=dev); lossb = torch.zeros(3, device=dev); dl2 = torch.zeros_like(low)
 arr = lambda t: (Cc.c_void_p * 3)(t.data_ptr() if t is not None else None, None, None)
 targets["upsample_ce"] = lambda: L.call("svl_upsample_ce", low, dl2, 16, 21, 128, 128, 512, 512, 1, arr(lab), arr(None), arr(coef), lossb, 1.0, 255)
+f3 = [(i - 1, j - 1) for i in range(3) for j in range(3)]
+xc32 = bf(336 * 128 * 128, 32); wc32 = bf(9 * 32, 32); oc32 = torch.empty(336 * 128 * 128, 32, device=dev, dtype=torch.bfloat16)
+targets["conv_roll_128x128_c32_c32"] = lambda: ops.gemm(xc32, wc32, oc32, n=32, k=32, conv=(336, 128, 128), filt=f3, b_row_stride=32)
+xc64 = bf(336 * 64 * 64, 64); wc64 = bf(9 * 64, 64); oc64 = torch.empty(336 * 64 * 64, 64, device=dev, dtype=torch.bfloat16)
+targets["conv_roll_dual_64x64_c64_c64"] = lambda: ops.gemm(xc64, wc64, oc64, n=64, k=64, conv=(336, 64, 64), filt=f3, b_row_stride=64)
+dwc = torch.zeros(9, 32, 32, device=dev)
+targets["wgrad_rowstack_c32_c32"] = lambda: ops.wgrad(oc32, xc32, dwc, m=32, n=32, conv=(336, 128, 128), filt=f3)
 sel = sys.argv[1:] or list(targets)
 for name in sel:
     fn = targets[name]

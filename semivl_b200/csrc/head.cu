@@ -345,7 +345,8 @@ gn_apply_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const flo
   }
 }
 
-// backward statistics: thread = (pixel slot, 8-channel vector), two pixels (x, dy: four 16-byte loads) in flight; the 18 per-thread
+// backward statistics: thread = (pixel slot, 8-channel vector), four pixels (x, dy: eight 16-byte loads) in flight (two left the kernel at
+// 3.2 TB/s: latency-bound); the 18 per-thread
 // partials (dgamma[8], dbeta[8], s1, s2) are reduced through a padded shared-memory table instead of same-address atomics.
 __global__ void __launch_bounds__(kGnThreads, 3)
 gn_bwd_stats_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x, int64_t ldx,
@@ -367,17 +368,23 @@ gn_bwd_stats_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, con
   float s1 = 0.f, s2 = 0.f, dg[8], db[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
-  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += 2 * ppi) {
-    const bool ok1 = pix + ppi < p1;
-    const int q1 = ok1 ? pix + ppi : pix;
-    const uint4 a0 = ld_stream16(xb + (int64_t)pix * ldx), b0 = ld_stream16(yb + (int64_t)pix * lddy);
-    const uint4 a1 = ld_stream16(xb + (int64_t)q1 * ldx), b1 = ld_stream16(yb + (int64_t)q1 * lddy);
+  constexpr int U = 4;                                   // pixels (x, dy: two 16-byte loads each) in flight per thread: 128 bytes
+  for (int pix = p0 + threadIdx.x / vpp; pix < p1; pix += U * ppi) {
+    uint4 a[U], b[U];
+    bool ok[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 0 || ok1) {
+    for (int u = 0; u < U; ++u) {
+      ok[u] = pix + u * ppi < p1;
+      const int q = ok[u] ? pix + u * ppi : pix;
+      a[u] = ld_stream16(xb + (int64_t)q * ldx);
+      b[u] = ld_stream16(yb + (int64_t)q * lddy);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) {
         float xv[8], d[8];
-        bf16x8_to_f32(u == 0 ? a0 : a1, xv);
-        bf16x8_to_f32(u == 0 ? b0 : b1, d);
+        bf16x8_to_f32(a[u], xv);
+        bf16x8_to_f32(b[u], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xh = (xv[i] - mu) * rs;

@@ -373,8 +373,10 @@ wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   }
 }
 
-// Split-K factor: one CTA per SM is resident, so the kernel runs in ceil(tiles * s / SMs) rounds of (K / s) each.  Pick the s (at most
-// ~3 rounds, at least 8 K blocks per CTA) that minimises rounds / s: a grid of 2 * SMs + 1 CTAs costs three rounds, not two.
+// Split-K factor: one CTA per SM is resident, so the kernel runs in ceil(tiles * s / SMs) rounds; a round costs its K blocks plus the
+// partial tile's red.global.add epilogue.  Fitted on the ViT shapes (scratch/wgrad_splits.py: 54 tiles x 257 K blocks, t(s) = rounds *
+// (K / s * 0.46 us + 9 us) within 5 %): the epilogue is worth ~20 K blocks, and beyond 8 partial sums per tile the same-address reductions
+// of the splits that finish together start to serialise (9 tiles: s = 8 27 us, s = 16 38 us).
 int pick_splits(int64_t tiles, int64_t num_kblocks) {
   const int64_t sms = num_sms();
   int64_t cap = num_kblocks / 8 > 0 ? num_kblocks / 8 : 1;
@@ -385,7 +387,7 @@ int pick_splits(int64_t tiles, int64_t num_kblocks) {
   double best_cost = 1e30;
   for (int64_t s = 1; s <= smax; ++s) {
     const int64_t rounds = (tiles * s + sms - 1) / sms;
-    const double cost = (double)rounds / (double)s + 1e-4 * (double)s;      // tie-break towards fewer partial sums
+    const double cost = (double)rounds * ((double)num_kblocks / (double)s + 20.0 + 2.5 * (double)(s > 8 ? s - 8 : 0));
     if (cost < best_cost) { best_cost = cost; best = s; }
   }
   return (int)best;

@@ -406,3 +406,54 @@ def test_lr_warmup_and_scheduler_max_iters(built):
         else:
             lr = 2e-4 * (1 - i / 80) ** 0.9
     assert np.allclose([tr.lr_at(it) for it in range(1, 13)], seen, rtol=1e-12)
+
+
+def test_operand_index_maps_and_gradient_scatter_semantics(built):
+    """Host side of the one-launch parameter plumbing (engine/vit.py WeightCache, svl_param_jobs): every operand layout of the head / encoder
+    is a pure gather of the parameter, the index map derived by pushing an arange through the layout function reproduces it (-1 = zero
+    padding), and scattering a staged gradient through the same map equals the reference-layout update the engines used to do with
+    permute + add_ (vlg_head.py parameters keep the reference's [Co, Ci, kh, kw] / [Ci, Co, 2, 2] layouts)."""
+    import torch
+    from semivl_b200.engine.head import HeadEngine
+    from semivl_b200.engine.vit import WeightCache
+    g = torch.Generator().manual_seed(3)
+    shapes = {"lin": (24, 40), "lin_t": (24, 40), "conv": (32, 16, 3, 3), "conv_t": (32, 16, 3, 3), "convT": (16, 8, 2, 2), "convT_t": (16, 8, 2, 2),
+              "conv1": (8, 1, 5, 5), "conv1_t": (8, 1, 5, 5), "projA": (8, 40, 1, 1), "projA_t": (8, 40, 1, 1), "projB": (8, 40, 1, 1),
+              "projB_t": (8, 40, 1, 1), "out1": (1, 32, 3, 3)}
+    for kind, shape in shapes.items():
+        fn = HeadEngine._layout(kind)
+        prm = torch.randn(*shape, generator=g)
+        idx, lshape = WeightCache._index_map(prm, fn)
+        lay = fn(prm).contiguous()
+        assert tuple(lay.shape) == lshape
+        flat = prm.reshape(-1)
+        got = torch.where(idx >= 0, flat[idx.clamp_min(0).long()], torch.zeros(()))
+        assert torch.equal(got, lay.reshape(-1)), kind
+        real = idx[idx >= 0]
+        assert real.unique().numel() == real.numel(), kind          # injective: the scatter needs no atomics
+    # gradient scatter of a conv weight gradient staged as [(tap, co), ci] == grads.add_(dw.view(ks, ks, co, ci).permute(2, 3, 0, 1))
+    co, ci = 32, 16
+    dw = torch.randn(9, co, ci, generator=g)
+    grad = torch.randn(co, ci, 3, 3, generator=g)
+    want = grad + dw.view(3, 3, co, ci).permute(2, 3, 0, 1)
+    idx, _ = WeightCache._index_map(grad, HeadEngine._layout("conv"))
+    got = grad.clone().reshape(-1)
+    got.index_add_(0, idx.long(), dw.reshape(-1))
+    assert torch.allclose(got.view_as(grad), want)
+    # transposed conv: dwq [4, ci, cu] staged in the "convT_t" layout of a [ci, cu, 2, 2] parameter
+    ci, cu = 16, 8
+    dwq = torch.randn(4, ci, cu, generator=g)
+    grad = torch.zeros(ci, cu, 2, 2)
+    idx, _ = WeightCache._index_map(grad, HeadEngine._layout("convT_t"))
+    got = grad.clone().reshape(-1)
+    got.index_add_(0, idx.long(), dwq.reshape(-1))
+    assert torch.allclose(got.view_as(grad), dwq.view(2, 2, ci, cu).permute(2, 3, 0, 1))
+    # the padded conv1 layout drops its padding columns on the way back
+    C, ks = 8, 5
+    dw1 = torch.randn(C, 64, generator=g)
+    grad = torch.zeros(C, 1, ks, ks)
+    idx, _ = WeightCache._index_map(grad, HeadEngine._layout("conv1"))
+    keep = idx >= 0
+    got = grad.clone().reshape(-1)
+    got.index_add_(0, idx[keep].long(), dw1.reshape(-1)[keep])
+    assert torch.allclose(got.view_as(grad), dw1[:, : ks * ks].reshape(C, 1, ks, ks))

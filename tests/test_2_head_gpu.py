@@ -70,7 +70,7 @@ def test_head_forward_backward(text_dir, hw, b, n, precise):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("R,N,hl,H", [(2, 21, 16, 64), (1, 19, 20, 72), (1, 150, 32, 128)])
+@pytest.mark.parametrize("R,N,hl,H", [(2, 21, 16, 64), (1, 19, 20, 72), (1, 150, 32, 128), (1, 5, 41, 164), (2, 81, 9, 36)])
 def test_fused_upsample_ce(R, N, hl, H):
     from semivl_b200 import lib as L
     L.check_device()

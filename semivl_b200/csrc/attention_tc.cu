@@ -14,6 +14,13 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#ifdef SVL_GEMM_DIAG
+#define ATT_T0() const long long att_t0 = clock64()
+#define ATT_ADD(slot) do { if (p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[slot] += clock64() - att_t0; } while (0)
+#else
+#define ATT_T0() do {} while (0)
+#define ATT_ADD(slot) do {} while (0)
+#endif
 #include "tma.h"
 
 namespace svl {
@@ -30,6 +37,7 @@ struct FwdParams {
   int L, heads;
   float scale;
   int s_first;        // MMA issue order: 1 = S_{j+1} before P_j V_j (the softmax of tile j+1 does not wait behind the P V product)
+  long long* trace;   // -DSVL_GEMM_DIAG: cycle totals of CTA (1, 0, 0): who waits for whom (SVL_ATTN_TRACE)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -379,7 +387,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     ptx::tc_fence_after();
     auto issue_s = [&](int j) {              // S_j = Q K_j^T (A = Q in TMEM) into score buffer j & 1, then the K stage is free
       const int st = j % KST, sb = j & 1;
-      ptx::mbar_wait(k_full(st), (uint32_t)((j / KST) & 1));
+      { ATT_T0(); ptx::mbar_wait(k_full(st), (uint32_t)((j / KST) & 1)); ATT_ADD(1); }
       ptx::tc_fence_after();
       const uint64_t kd = tmpl + (uint64_t)((sK + st * kHalfTile) >> 4);
       if (leader) {
@@ -393,8 +401,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
     auto issue_pv = [&](int j) {             // O += P_j V_j (A = P_j in the score buffer, K dimension = the 64 keys; V read MN-major)
       const int st = j % KST, sb = j & 1;
-      ptx::mbar_wait(v_full(st), (uint32_t)((j / KST) & 1));
-      ptx::mbar_wait(p_full(sb), (uint32_t)((j >> 1) & 1));
+      { ATT_T0(); ptx::mbar_wait(v_full(st), (uint32_t)((j / KST) & 1)); ATT_ADD(2); }
+      { ATT_T0(); ptx::mbar_wait(p_full(sb), (uint32_t)((j >> 1) & 1)); ATT_ADD(3); }
       ptx::tc_fence_after();
       const uint64_t vb = tmpl + (uint64_t)((sV + st * kHalfTile) >> 4);
       if (leader) {
@@ -406,6 +414,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     };
+    ATT_T0();
     issue_s(0);
     if (nt > 1) issue_s(1);
     for (int j = 0; j < nt; ++j) {
@@ -413,10 +422,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (j + 2 < nt) {
         // S_{j+2} overwrites score buffer j & 1 and the P_j stored inside it.  Issue order is NOT enough: the tensor pipe does not track a
         // later D write against an earlier TMEM A-operand read (run-to-run differences at 16 x 12 x 1025 proved it), so wait for P_j V_j.
-        ptx::mbar_wait(o_done, (uint32_t)(j & 1));
+        { const long long w0 = clock64(); ptx::mbar_wait(o_done, (uint32_t)(j & 1));
+#ifdef SVL_GEMM_DIAG
+          if (p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[4] += clock64() - w0;
+#endif
+        }
         issue_s(j + 2);
       }
     }
+    ATT_ADD(0);
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -442,7 +456,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < nt; ++j) {
       const int sb = j & 1;
-      ptx::mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1));
+      { ATT_T0(); ptx::mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1)); if (warp == 0) ATT_ADD(5); }
       ptx::tc_fence_after();
       const int nvalid = p.L - j * TK2;                   // >= 64 except on the last tile
       if (warp_valid) {
@@ -557,6 +571,7 @@ struct BwdParams {
   int L, Lp, heads;
   float scale;
   int s_first;        // MMA issue order: 1 = the score products of tile j+1 are issued before the accumulate products of tile j
+  long long* trace;   // -DSVL_GEMM_DIAG (SVL_ATTN_TRACE): cycle totals of CTA (1, 0, 0) of the kv kernel, slots 8..
 };
 
 __global__ void attn_prep_tc_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int64_t ldo,
@@ -713,7 +728,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     ptx::mbar_wait(kv_full, 0);
     auto scores = [&](int j) {               // S^T_j = K Q_j^T and dP^T_j = V dO_j^T (issued after the accumulates of tile j-1, which read the same columns)
       const int st = j & 1, k = j >> 1;
-      ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));
+      { ATT_T0(); ptx::mbar_wait(q_full(st), (uint32_t)(k & 1)); ATT_ADD(9); }
       ptx::tc_fence_after();
       const uint64_t qd = tmpl + (uint64_t)((sQ + st * kHalf) >> 4), gd = tmpl + (uint64_t)((sG + st * kHalf) >> 4);
       if (leader) {
@@ -728,7 +743,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     auto accumulate = [&](int j) {           // dV += P^T_j dO_j, dK += dS^T_j Q_j, then the operand buffers and the Q / dO stage are free
       const int st = j & 1;
       const uint64_t qd = tmpl + (uint64_t)((sQ + st * kHalf) >> 4), gd = tmpl + (uint64_t)((sG + st * kHalf) >> 4);
-      ptx::mbar_wait(p_full, (uint32_t)(j & 1));
+      { ATT_T0(); ptx::mbar_wait(p_full, (uint32_t)(j & 1)); ATT_ADD(10); }
       ptx::tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -741,13 +756,17 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       }
       __syncwarp();
     };
+    const long long att_tm0 = clock64();
     for (int j = 0; j < nt; ++j) {
       // the score products overwrite P^T_{j-1} / dS^T_{j-1}: wait until the accumulate products that read them have completed
       // (their commit on q_empty; issue order alone does not protect a TMEM A operand against a later accumulator write)
-      if (j > 0) ptx::mbar_wait(q_empty((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+      if (j > 0) { ATT_T0(); ptx::mbar_wait(q_empty((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1)); ATT_ADD(11); }
       scores(j);
       accumulate(j);
     }
+#ifdef SVL_GEMM_DIAG
+    if (p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) p.trace[8] = clock64() - att_tm0;
+#endif
     if (leader) ptx::umma_commit(acc_full);
     __syncwarp();
   } else {
@@ -760,7 +779,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     for (int j = 0; j < nt; ++j) {
       const int st = j & 1, k = j >> 1;
       ptx::mbar_wait(q_full(st), (uint32_t)(k & 1));            // lse / delta slices of this query tile
-      ptx::mbar_wait(s_full, (uint32_t)(j & 1));
+      { ATT_T0(); ptx::mbar_wait(s_full, (uint32_t)(j & 1)); if (warp == 2) ATT_ADD(12); }
       ptx::tc_fence_after();
       if (warp_valid) {
         uint32_t sv[32], dv[32], pk[16], dk[16];
@@ -1048,6 +1067,10 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int b, int L, int h
   if (int rc = tma_encode_bf16(&tm, qkv, 3, dims, strides, box)) return rc;
   FwdParams p;
   p.out = (__nv_bfloat16*)out; p.ldo = E; p.lse = lse; p.L = L; p.heads = heads; p.scale = scale;
+  p.trace = nullptr;
+#ifdef SVL_GEMM_DIAG
+  { const char* e = getenv("SVL_ATTN_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 10) : nullptr; }
+#endif
   static int gen = -1;
   if (gen < 0) { const char* e = getenv("SVL_ATTN_FWD"); gen = e ? atoi(e) : 2; }      // 1: the first-generation kernel (kept for comparison)
   if (gen == 2) {
@@ -1112,6 +1135,10 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
   BwdParams p;
   p.lse_p = lse_p; p.delta_p = delta_p; p.dv_add = dv_add; p.dv_add_dtype = dv_add_dtype; p.ld_dv_add = ld_dv_add;
   p.dqkv = (__nv_bfloat16*)dqkv; p.ldg = 3 * E; p.L = L; p.Lp = Lp; p.heads = heads; p.scale = scale;
+  p.trace = nullptr;
+#ifdef SVL_GEMM_DIAG
+  { const char* e = getenv("SVL_ATTN_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 10) : nullptr; }
+#endif
   static int s_first_b = -1;
   if (s_first_b < 0) { const char* e = getenv("SVL_ATTN_S_FIRST"); s_first_b = e ? atoi(e) : 1; }   // measured: backward 415 -> 377 us per layer
   p.s_first = s_first_b;

@@ -59,10 +59,34 @@ class HeadEngine:
             "projB": lambda t: t.reshape(t.shape[0], -1)[:, 4 * t.shape[0]:],
             "projB_t": lambda t: t.reshape(t.shape[0], -1)[:, 4 * t.shape[0]:].t(),
             "out1": lambda t: t[0].permute(1, 2, 0).reshape(-1),                        # head [1,C,3,3] -> f32 [9*C]
+            "rep4": lambda t: t.repeat(4),                                              # ConvTranspose bias, once per 2 x 2 output quadrant
         }[kind]
 
     def _prep(self, p, name, kind):
-        return self.cache.get_layout((name, kind, self.precise), p[name], self._layout(kind), self.precise, raw_f32=kind == "out1")
+        return self.cache.get_layout((name, kind, self.precise), p[name], self._layout(kind), self.precise, raw_f32=kind in ("out1", "rep4"))
+
+    def _text_f32(self, text):
+        """(fp32 contiguous copy of the frozen text-embedding table, memo dict for operands derived from it): made once per table instead
+        of once per pass; a handful of tables can be live (pl_text / mcc_text variants of the SemiVL step)"""
+        key = (text.data_ptr(), text._version, tuple(text.shape), text.dtype)
+        cache = self.__dict__.setdefault("_text_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) >= 4:
+                cache.clear()
+            hit = (text.float().contiguous(), {})
+            cache[key] = hit
+        return hit
+
+    def _text_t_operand(self, memo, txt_n, Kp):
+        """B operand [in_dim, Kp] of d(image embedding) = d_sim @ text_n (classes zero-padded to the MMA K step): a function of the frozen
+        table only, kept in the table's memo"""
+        k = ("txt_t", Kp, self.precise)
+        if k not in memo:
+            txt_t = torch.zeros(txt_n.shape[1], Kp, device=txt_n.device, dtype=torch.float32)
+            txt_t[:, : txt_n.shape[0]] = txt_n.t()
+            memo[k] = ops.prep_weight(txt_t, self.precise)
+        return memo[k]
 
     def _wgrad_buf(self, grads, name, kind, shape):
         """(buffer the weight-gradient kernel accumulates into in operand layout `kind`, staged?): the persistent staging buffer of the
@@ -174,7 +198,7 @@ class HeadEngine:
         cout = p[name + "conv.0.weight"].shape[0]
         H2, W2 = 2 * h, 2 * w
         cat = ops.new_act(nb * H2 * W2, ccat, pr, dev)
-        ops.gemm(x_act, self._prep(p, name + "up.weight", "convT"), cat, n=4 * cup, k=cin, precise=pr, bias=p[name + "up.bias"].repeat(4),
+        ops.gemm(x_act, self._prep(p, name + "up.weight", "convT"), cat, n=4 * cup, k=cin, precise=pr, bias=self._prep(p, name + "up.bias", "rep4"),
                  out_mode=L.OUT_CONVT2X2, out_hw=(h, w), out_dtype=adt, m=nb * h * w)
         L.call("svl_skip_fill", skip, L.F32, cs, cat, adt, cat.shape[-1], cup, B, N, skip_hw[0], skip_hw[1], cs, H2, W2)
         a0 = ops.new_act(nb * H2 * W2, cout, pr, dev)
@@ -236,7 +260,7 @@ class HeadEngine:
         B, h, w, D = emb.shape
         dev = emb.device
         hw = h * w
-        text = text.float().contiguous()
+        text, txt_memo = self._text_f32(text)
         N = text.shape[0]
         nb = B * N
         C = c.C
@@ -308,7 +332,7 @@ class HeadEngine:
         low = torch.empty(B, N, 4 * h, 4 * w, **f32)
         L.call("svl_conv_out1_fwd", u2, adt, u2.shape[-1], self._prep(p, "head.weight", "out1"), p["head.bias"], low, nb, 4 * h, 4 * w, c.up[1])
         if need_grad:
-            ctx.update(img_n=img_n, inv_img=inv_img, txt_n=txt_n, txt_act=txt_act, col=col, x1=x1, cat=cat, Sb=Sb, gap_act=gap_act, graw=graw,
+            ctx.update(img_n=img_n, inv_img=inv_img, txt_n=txt_n, txt_memo=txt_memo, txt_act=txt_act, col=col, x1=x1, cat=cat, Sb=Sb, gap_act=gap_act, graw=graw,
                        gmean=gmean, grstd=grstd, pool_act=pool_act, praw=praw, pmean=pmean, prstd=prstd, t=t, Sl=Sl, x_final=xcur, sk=sk, fa=fa,
                        Su1=Su1, Su2=Su2, u2=u2, hp=hp, wp=wp, geo=geo, n_taps=n_taps)
         return low, ctx
@@ -365,7 +389,7 @@ class HeadEngine:
         # SemanticTransformer layers
         hp, wp = ctx["hp"], ctx["wp"]
         Ed = C + c.Ct
-        d_t = torch.zeros(N, c.Ct, **f32)
+        tsum = torch.zeros(N * Ed, **f32)                   # column sums of the layers' token gradients: svl_colsum accumulates
         d_cur, d_cur_dtype = d_x, gdt
         for l in reversed(range(c.layers)):
             d_tok1 = torch.empty(B * hp * wp * N, Ed, **f32)
@@ -377,10 +401,9 @@ class HeadEngine:
             else:
                 ops.cast(d_cur, d_cur_dtype, d_prev, L.F32, nb * hw, C)
                 L.call("svl_pool_tokens_bwd", d_tok0, Ed, d_prev, B, N, h, w, C, c.pool)
-            tsum = torch.zeros(N * Ed, **f32)
             ops.colsum(d_tok0, L.F32, B * hp * wp, N * Ed, tsum, ld=N * Ed)
-            d_t.add_(tsum.view(N, Ed)[:, C:])
             d_cur, d_cur_dtype = d_prev, L.F32
+        d_t = tsum.view(N, Ed)[:, C:]
         # text projection (weights only; the text embeddings are frozen inputs)
         d_t_pre = d_t * (ctx["t"] > 0)
         ops.wgrad(ops.to_act(d_t_pre.contiguous(), pr), ctx["txt_act"], grads["text_proj.0.weight"], m=c.Ct, n=c.in_dim, precise=pr)
@@ -426,10 +449,8 @@ class HeadEngine:
         d_sim = ops.new_act(B * hw, Kp, pr, dev)
         L.call("svl_sim_col2im", d_col, gdt, 64, d_sim, adt, d_sim.shape[-1], Kp, B, N, h, w, c.ks)
         # similarity: d(normalised image embedding) = d_sim @ text_n
-        txt_t = torch.zeros(c.in_dim, Kp, **f32)
-        txt_t[:, :N] = ctx["txt_n"].t()
         d_img_n = torch.empty(B * hw, c.in_dim, device=dev, dtype=gtorch)
-        ops.gemm(d_sim, ops.prep_weight(txt_t, pr), d_img_n, n=c.in_dim, k=Kp, precise=pr)
+        ops.gemm(d_sim, self._text_t_operand(ctx["txt_memo"], ctx["txt_n"], Kp), d_img_n, n=c.in_dim, k=Kp, precise=pr)
         d_emb = torch.empty(B, h, w, c.in_dim, **f32)
         ops.l2norm_bwd(d_img_n, gdt, ctx["img_n"], ctx["inv_img"], d_emb.view(B * hw, c.in_dim))
         return d_taps + [d_emb] + d_conv

@@ -270,6 +270,9 @@ int svl_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const void* x, 
  * [R, N, H, W] = bilinear(low, align_corners=False) (vlg_head.py:247-248; the second resize of builder.py:93-97 is the identity).
  * ---------------------------------------------------------------------------------------------- */
 int svl_upsample_bilinear(const float* low, float* out, int64_t planes, int hl, int wl, int H, int W, void* stream);
+/* out = bilinear resize with align_corners=True of `planes` maps [hs, ws] -> [H, W]  (mmseg.ops.resize of the stitched evaluation logits to the
+ * label size, third_party/unimatch/supervised.py:95-100) */
+int svl_resize_bilinear_ac(const float* src, float* out, int64_t planes, int hs, int ws, int H, int W, void* stream);
 int svl_upsample_bilinear_bwd(const float* dout, float* dlow, int64_t planes, int hl, int wl, int H, int W, void* stream);   /* dlow += */
 /* conf = max_n softmax(scale * logits), label = argmax; label = 255 where conf < thresh (thresh > 0)
  * (semivl.py:231-232,251-252; model/vlm.py:103-109 with scale 100) -- the full-resolution logits are never materialised */

@@ -31,3 +31,4 @@ case("qkv n2304 k768 bf16", 2304, 768, torch.bfloat16)
 case("ffn1 n3072 k768 gelu dsave", 3072, 768, torch.bfloat16, act=L.ACT_GELU_DSAVE, preact=True)
 case("ffn2 n768 k3072 f32+res", 768, 3072, torch.float32, residual=True)
 case("dgrad n768 k2304 bf16", 768, 2304, torch.bfloat16)
+case("dgrad n768 k768 bf16", 768, 768, torch.bfloat16)

@@ -39,6 +39,21 @@ __global__ void upsample_kernel(const float* __restrict__ low, float* __restrict
     out[idx] = (1.f - wy) * ((1.f - wx) * p[y0 * wl + x0] + wx * p[y0 * wl + x1]) + wy * ((1.f - wx) * p[y1 * wl + x0] + wx * p[y1 * wl + x1]);
   }
 }
+// align_corners=True resize (mmseg.ops.resize of the stitched logits to the label size, supervised.py:95-100): source = o * (in - 1) / (out - 1)
+__global__ void resize_ac_kernel(const float* __restrict__ src, float* __restrict__ out, int64_t planes, int hs, int ws, int H, int W) {
+  const float sy = H > 1 ? (float)(hs - 1) / (H - 1) : 0.f, sx = W > 1 ? (float)(ws - 1) / (W - 1) : 0.f;
+  const int64_t total = planes * H * W;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % W), Y = (int)((idx / W) % H);
+    const int64_t pl = idx / ((int64_t)W * H);
+    const float fy = Y * sy, fx = X * sx;
+    const int y0 = min((int)fy, hs - 1), x0 = min((int)fx, ws - 1);
+    const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const float* p = src + pl * hs * ws;
+    out[idx] = (1.f - wy) * ((1.f - wx) * p[y0 * ws + x0] + wx * p[y0 * ws + x1]) + wy * ((1.f - wx) * p[y1 * ws + x0] + wx * p[y1 * ws + x1]);
+  }
+}
 // d_low += upsample^T(d_out)   (gather form; used when a caller backpropagates through the materialised logits)
 __global__ void upsample_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dlow, int64_t planes, int hl, int wl, int H, int W) {
   const float sy = (float)hl / H, sx = (float)wl / W;
@@ -361,6 +376,12 @@ using namespace svl;
 extern "C" int svl_upsample_bilinear(const float* low, float* out, int64_t planes, int hl, int wl, int H, int W, void* stream) {
   SVL_CHECK_ARG(low && out, "svl_upsample_bilinear: null pointer");
   upsample_kernel<<<ew_grid(planes * H * W), 256, 0, ST>>>(low, out, planes, hl, wl, H, W);
+  SVL_LAUNCH_CHECK();
+  return SVL_OK;
+}
+extern "C" int svl_resize_bilinear_ac(const float* src, float* out, int64_t planes, int hs, int ws, int H, int W, void* stream) {
+  SVL_CHECK_ARG(src && out && hs > 0 && ws > 0 && H > 0 && W > 0, "svl_resize_bilinear_ac: bad arguments");
+  resize_ac_kernel<<<ew_grid(planes * H * W), 256, 0, ST>>>(src, out, planes, hs, ws, H, W);
   SVL_LAUNCH_CHECK();
   return SVL_OK;
 }

@@ -64,9 +64,11 @@ def predict(model, img, mask, mode, cfg, return_logits=False):
         assert int((count == 0).sum()) == 0
         L.call("svl_divide_count", final, count, b, n, h * w)
         if tuple(mask.shape[-2:]) != (h, w):
-            # supervised.py:95-100 resizes the averaged logits to the label size (align_corners=True); the reference's loaders always give
-            # image and label the same size, so this branch has no kernel here and fails loudly instead of falling back to ATen
-            raise NotImplementedError(f"zegclip_sliding_window with a label size {tuple(mask.shape[-2:])} != image size {(h, w)}")
+            # supervised.py:95-100: the averaged logits are resized to the label size with align_corners=True
+            H2, W2 = int(mask.shape[-2]), int(mask.shape[-1])
+            resized = torch.empty(b, n, H2, W2, device=img.device)
+            L.call("svl_resize_bilinear_ac", final, resized, b * n, h, w, H2, W2)
+            final = resized
     elif mode == 'sliding_window':                            # supervised.py:105-117: clipped windows, stride 2/3 grid, softmax summed
         grid = cfg['crop_size']
         final = torch.zeros(b, n, h, w, device=img.device)

@@ -114,6 +114,7 @@ _PROTOS = {
     "svl_conv_out1_bwd": [_P, _P, _I, _L, _P, _P, _I, _L, _P, _P, _L, _I, _I, _I, _P],
     "svl_upsample_bilinear": [_P, _P, _L, _I, _I, _I, _I, _P],
     "svl_upsample_bilinear_bwd": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "svl_resize_bilinear_ac": [_P, _P, _L, _I, _I, _I, _I, _P],
     "svl_softmax_max": [_P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _F, _P],
     "svl_group_max": [_P, _L, _P, _P, _L, _I, _I, _P],
     "svl_upsample_ce": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P],

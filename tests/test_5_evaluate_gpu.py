@@ -109,3 +109,31 @@ def test_predict_and_iou_match_reference_golden(golden_dir):
         counts = E.intersection_union_counts(ref_pred.cuda(), target.cuda(), nclass, 255).cpu().numpy()
         want = g[f"iou{i}"]
         assert np.array_equal(counts[0], want[0]) and np.array_equal(counts[1] + counts[2] - counts[0], want[1]) and np.array_equal(counts[2], want[2])
+
+
+def test_zegclip_sliding_window_resizes_to_the_label_size():
+    """supervised.py:95-100: when the label is not the image's size the averaged window logits are resized with align_corners=True before the
+    arg-max (svl_resize_bilinear_ac); against the oracle's restatement of `predict` and against ATen for the resize itself."""
+    from oracle import semivl_oracle as O
+    from semivl_b200 import evaluate as E
+    from semivl_b200 import lib as L
+    nclass = 5
+    cfg = dict(nclass=nclass, crop_size=24, stride=16)
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(2, 3, 40, 44, generator=g)
+    mask = torch.randint(0, nclass, (2, 61, 53), generator=g)
+    stub = _Stub(nclass)
+    want, logits = O.predict_reference(stub, img, mask, "zegclip_sliding_window", cfg)
+    pred, final = E.predict(stub.cuda(), img.cuda(), mask, "zegclip_sliding_window", cfg, return_logits=True)
+    assert tuple(final.shape[-2:]) == (61, 53)
+    assert (final.cpu() - logits).abs().max() < 1e-4 * logits.abs().max()
+    top2 = logits.topk(2, dim=1).values
+    decidable = (top2[:, 0] - top2[:, 1]) > 1e-3 * logits.abs().max()
+    assert bool((pred.cpu()[decidable] == want[decidable]).all())
+    # the kernel alone, up- and down-scaling, degenerate sizes
+    for (hs, ws, H, W) in ((7, 9, 20, 31), (20, 31, 7, 9), (5, 1, 9, 4), (1, 6, 1, 11)):
+        src = torch.randn(3, hs, ws, generator=g).cuda()
+        out = torch.empty(3, H, W, device="cuda")
+        L.call("svl_resize_bilinear_ac", src, out, 3, hs, ws, H, W)
+        ref = F.interpolate(src[None], size=(H, W), mode="bilinear", align_corners=True)[0]
+        assert (out - ref).abs().max() < 1e-5

@@ -98,9 +98,16 @@ typedef struct {
   int accumulate;       /* 1: out += result (F32 out only) */
   /* ---- tuning ---- */
   int block_n;          /* 0 = auto */
+  /* ---- GroupNorm statistics of the output, fused into the epilogue of the 3 x 3 convolutions that svl_conv_gn_splits() accepts ----
+   * gn_part != NULL: per (map, slot, group) partial sums (sum, sum of squares) of the STORED (bf16-rounded) output, 16 channels per group, are
+   * written to gn_part[((map * splits + slot) * (n / 16) + group) * 2 + {0, 1}] with splits = svl_conv_gn_splits(d): every slot is written
+   * exactly once, in an order that depends on the map geometry only; svl_gn_relu_fwd(..., stats_splits = splits) consumes them. */
+  float* gn_part;
 } svl_gemm_desc;
 
 int svl_gemm(const svl_gemm_desc* d, void* stream);
+/* partial sums per map that svl_gemm(d) writes to d->gn_part, or 0 when this problem does not take the fused-statistics path */
+int svl_conv_gn_splits(const svl_gemm_desc* d);
 
 /* Weight gradient on the same tensor cores, operands read MN-major straight from their forward layouts:
  *   dw[slot*slot_stride + i*ld_dw + j] += alpha * sum_{taps t of slot} sum_rows DY[row, dy_koff_t + i] * X[shift_t(row), x_koff_t + j]
@@ -187,11 +194,13 @@ int svl_attention_bwd(const void* qkv, const void* out, const void* dout, int sp
  * ---------------------------------------------------------------------------------------------- */
 /* out = relu(GroupNorm(x)) (+ res); statistics per (map, group) saved to mean/rstd [maps, G]   (vlg_head.py:99-111,132-135).
  * The statistics are reduced in two fixed-order stages (per-CTA partials in `ws`, then one thread per (map, group)): no
- * floating-point atomics, so the result is bit-reproducible from run to run.  `ws`: svl_gn_workspace(maps, hw, C, G) floats. */
+ * floating-point atomics, so the result is bit-reproducible from run to run.  `ws`: svl_gn_workspace(maps, hw, C, G) floats.
+ * stats_splits > 0: the first stage already happened -- `ws` holds [maps, stats_splits, G, 2] partial sums written by the producing convolution
+ * (svl_gemm_desc.gn_part) -- and only the second stage and the apply pass run. */
 size_t svl_gn_workspace(int64_t maps, int hw, int C, int G);
 int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
                     int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, float* ws, int64_t maps,
-                    int hw, int C, int G, float eps, void* stream);
+                    int hw, int C, int G, float eps, int stats_splits, void* stream);
 /* dx = GN'(dy * [y > 0]) (data gradient reduced in fixed order like the forward); dgamma/dbeta += (atomics, may be NULL) */
 int svl_gn_relu_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx, const float* gamma,
                     const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int64_t lddx, float* dgamma,

@@ -49,6 +49,7 @@ struct RollParams {
   int wrow[3][3], wcol[3][3];        // weight-tensor coordinates (row, column) of filter position (dy + 1, dx + 1)
   __nv_bfloat16* out; int64_t ldc;
   const float* bias; int relu;
+  float* gn_part; int gn_splits;     // fused GroupNorm statistics of the stored output (16 channels per group), see svl_gemm_desc.gn_part
   long long* trace;                  // -DSVL_GEMM_DIAG: cycle totals of CTA 0
 };
 
@@ -241,6 +242,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     int blk = 0, turn = 0;                     // ring block and whose turn it is
     uint32_t bphase = 0;
+    constexpr int G = COUT / 16;               // GroupNorm groups of 16 channels
+    float gs1[G], gs2[G];                      // this warp's sums over the unit's rows it drains (fixed order: rows ascending)
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
       const int c = u % p.chunks, tx = (u / p.chunks) % p.tiles_x, cn = u / (p.chunks * p.tiles_x);
       const int y0 = c * p.roll_rows, nrows = min(y0 + p.roll_rows, p.h) - y0;
@@ -248,6 +251,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int x = DUAL ? (q & 1) * 32 + lane : tx * 128 + q * 32 + lane;
       const int img = DUAL ? 2 * cn + (q >> 1) : cn;
       const bool valid = x < p.w && img < p.nb;
+#pragma unroll
+      for (int g = 0; g < G; ++g) gs1[g] = gs2[g] = 0.f;
       for (int j = 0; j < nrows + 4; ++j) {
         if (turn != quartet) {                 // another quartet's block
           if (++turn == kRollQuartets) turn = 0;
@@ -265,6 +270,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t taddr = lane_base + (uint32_t)(blk * COUT);
         if (j >= 2 && j < nrows + 2) {         // a row of this unit: y0 + j - 2
           __nv_bfloat16* dst = p.out + (((int64_t)img * p.h + (y0 + j - 2)) * p.w + x) * p.ldc;
+#pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 32) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + (uint32_t)c0, v);
@@ -287,6 +293,17 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
                 }
                 st16(dst, SVL_BF16, c0 + g * 16, 0, 16, f);
+                if (p.gn_part) {                 // statistics of what was stored: the values rounded to bf16
+                  float a = 0.f, b = 0.f;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const float r = __bfloat162float(__float2bfloat16(f[i]));
+                    a += r;
+                    b += r * r;
+                  }
+                  gs1[c0 / 16 + g] += a;
+                  gs2[c0 / 16 + g] += b;
+                }
               }
             }
           }
@@ -298,6 +315,15 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(bempty_bar(blk));
         if (++turn == kRollQuartets) turn = 0;
         if (++blk == p.nblk) { blk = 0; bphase ^= 1u; }
+      }
+      if (p.gn_part) {
+        // one partial per (map, unit, warp): slot order depends on the map geometry only, every slot is written exactly once
+        const int slot = DUAL ? c * 8 + quartet * 2 + (q & 1) : (c * p.tiles_x + tx) * 16 + quartet * 4 + q;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float a = warp_sum(gs1[g]), b = warp_sum(gs2[g]);
+          if (lane == 0 && img < p.nb) *(float2*)(p.gn_part + (((int64_t)img * p.gn_splits + slot) * G + g) * 2) = make_float2(a, b);
+        }
       }
     }
   }
@@ -312,28 +338,28 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 }  // namespace
 
-// Returns 1 when the rolling kernel was launched, 0 when the problem does not qualify, < 0 on error.
-int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream) {
+namespace {
+// Fills the launch plan; false when the problem does not qualify for the rolling kernel.
+bool roll_plan(const svl_gemm_desc* d, RollParams& p, bool& dual) {
   static int roll_rows = -1;
   if (roll_rows < 0) { const char* e = getenv("SVL_CONV_ROLL"); roll_rows = e ? atoi(e) : 16; }
-  if (roll_rows < 1 || !d->a_conv || d->num_taps != 9 || d->a_map_w != 0 || d->w < 33) return 0;
-  if ((d->n != 32 && d->n != 64) || (d->k_per_tap != 32 && d->k_per_tap != 64 && d->k_per_tap != 128)) return 0;
-  if (d->out_dtype != SVL_BF16 || d->out_mode != SVL_OUT_LINEAR || d->preact_out || d->dact_src || d->residual || d->row_bias || d->accumulate) return 0;
-  if (d->act != SVL_ACT_NONE && d->act != SVL_ACT_RELU) return 0;
-  if (d->alpha != 0.f && d->alpha != 1.f) return 0;
-  if (d->ldc % 16 != 0 || ((uintptr_t)d->out & 31) != 0 || (d->bias && ((uintptr_t)d->bias & 15) != 0)) return 0;
-  RollParams p;
+  if (roll_rows < 1 || !d->a_conv || d->num_taps != 9 || d->a_map_w != 0 || d->w < 33) return false;
+  if ((d->n != 32 && d->n != 64) || (d->k_per_tap != 32 && d->k_per_tap != 64 && d->k_per_tap != 128)) return false;
+  if (d->out_dtype != SVL_BF16 || d->out_mode != SVL_OUT_LINEAR || d->preact_out || d->dact_src || d->residual || d->row_bias || d->accumulate) return false;
+  if (d->act != SVL_ACT_NONE && d->act != SVL_ACT_RELU) return false;
+  if (d->alpha != 0.f && d->alpha != 1.f) return false;
+  if (d->ldc % 16 != 0 || ((uintptr_t)d->out & 31) != 0 || (d->bias && ((uintptr_t)d->bias & 15) != 0)) return false;
   memset(&p, 0, sizeof(p));
   for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) p.wrow[a][b] = -1;
   for (int t = 0; t < 9; ++t) {
     const int fy = d->tap_dy[t], fx = d->tap_dx[t];
-    if (fy < -1 || fy > 1 || fx < -1 || fx > 1 || d->tap_a_koff[t] != d->tap_a_koff[0]) return 0;
+    if (fy < -1 || fy > 1 || fx < -1 || fx > 1 || d->tap_a_koff[t] != d->tap_a_koff[0]) return false;
     p.wrow[fy + 1][fx + 1] = d->tap_b_row[t];
     p.wcol[fy + 1][fx + 1] = d->tap_b_col[t];
   }
-  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) if (p.wrow[a][b] < 0) return 0;
-  const bool dual = d->w <= 64;                   // two maps side by side in the 128 accumulator lanes
-  if (!dual && d->w < 96) return 0;               // 65..95-pixel rows would leave a third of a 128-pixel tile empty: generic engine
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) if (p.wrow[a][b] < 0) return false;
+  dual = d->w <= 64;                              // two maps side by side in the 128 accumulator lanes
+  if (!dual && d->w < 96) return false;           // 65..95-pixel rows would leave a third of a 128-pixel tile empty: generic engine
   p.nb = d->nb; p.h = d->h; p.w = d->w;
   p.cin = d->k_per_tap; p.cout = d->n; p.nblk = 512 / p.cout;
   const int kc = (p.cin + 63) / 64;
@@ -349,10 +375,29 @@ int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream) {
   p.wgroup_bytes = (uint32_t)(3 * p.cout) * 128u;
   const size_t wbytes = 3 * (size_t)kc * p.wgroup_bytes;
   const size_t fixed = 1024 + wbytes + 8 * (2 * kRollMaxStages + 2 * kRollMaxBlocks + 2) + 16;
-  if (fixed + 2 * (size_t)p.stage_stride > 227 * 1024) return 0;
+  if (fixed + 2 * (size_t)p.stage_stride > 227 * 1024) return false;
   p.stages = (int)((227 * 1024 - fixed) / p.stage_stride);
   if (p.stages > kRollMaxStages) p.stages = kRollMaxStages;
   p.out = (__nv_bfloat16*)d->out; p.ldc = d->ldc; p.bias = d->bias; p.relu = d->act == SVL_ACT_RELU;
+  p.gn_splits = dual ? p.chunks * 8 : p.chunks * p.tiles_x * 16;
+  p.gn_part = d->gn_part;
+  return true;
+}
+}  // namespace
+
+int conv_roll_gn_splits(const svl_gemm_desc* d) {
+  RollParams p;
+  bool dual;
+  return roll_plan(d, p, dual) ? p.gn_splits : 0;
+}
+
+// Returns 1 when the rolling kernel was launched, 0 when the problem does not qualify, < 0 on error.
+int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream) {
+  RollParams p;
+  bool dual;
+  if (!roll_plan(d, p, dual)) return 0;
+  const int kc = (p.cin + 63) / 64;
+  const size_t fixed = 1024 + 3 * (size_t)kc * p.wgroup_bytes + 8 * (2 * kRollMaxStages + 2 * kRollMaxBlocks + 2) + 16;
 #ifdef SVL_GEMM_DIAG
   { const char* e = getenv("SVL_ROLL_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 10) : nullptr; }
 #endif

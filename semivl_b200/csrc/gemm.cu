@@ -791,9 +791,12 @@ int auto_block_n(int n) {
 
 namespace svl {
 int try_launch_conv_roll(const svl_gemm_desc* d, cudaStream_t stream);      // conv_roll.cu: 3 x 3 convolutions with 32 / 64 output channels
+int conv_roll_gn_splits(const svl_gemm_desc* d);
 }
 
 using namespace svl;
+
+extern "C" int svl_conv_gn_splits(const svl_gemm_desc* d) { return d ? conv_roll_gn_splits(d) : 0; }
 
 extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   SVL_CHECK_ARG(d && d->a && d->b && d->out, "svl_gemm: null operand");
@@ -814,6 +817,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
     const int rc = try_launch_conv_roll(d, (cudaStream_t)stream);
     if (rc != 0) return rc < 0 ? rc : SVL_OK;
   }
+  SVL_CHECK_ARG(!d->gn_part, "svl_gemm: gn_part is only served by the problems svl_conv_gn_splits() accepts");
 
   GemmParams p;
   p.cluster = 0;

@@ -1355,19 +1355,21 @@ extern "C" size_t svl_gn_workspace(int64_t maps, int hw, int C, int G) {
 
 extern "C" int svl_gn_relu_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
                                int64_t ldo, const void* res, int res_dtype, int64_t ldres, float* mean, float* rstd, float* ws, int64_t maps,
-                               int hw, int C, int G, float eps, void* stream) {
+                               int hw, int C, int G, float eps, int stats_splits, void* stream) {
   SVL_CHECK_ARG(x && gamma && beta && out && mean && rstd && ws, "svl_gn_relu_fwd: null pointer");
   SVL_CHECK_ARG(C % 8 == 0 && C <= 256 && G <= kMaxGroups && C % G == 0 && (C / G) % 8 == 0 && kGnThreads % (C / 8) == 0,
                 "svl_gn_relu_fwd: unsupported C=%d G=%d", C, G);
   if (maps == 0) return SVL_OK;
-  const int splits = gn_splits(maps, hw, C);
+  const int splits = stats_splits > 0 ? stats_splits : gn_splits(maps, hw, C);
   SVL_CHECK_ARG(maps * splits < (1ll << 31), "svl_gn_relu_fwd: grid too large");
   // all-bf16 fast path (every large GroupNorm of the throughput mode); anything else takes the generic kernels
   const int vshift = log2_exact(C / 8);
   const bool fast = x_dtype == SVL_BF16 && out_dtype == SVL_BF16 && (!res || res_dtype == SVL_BF16) && al16(x) && al16(out) && al16(res) &&
                     ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldres % 8 == 0) && vshift >= 0 && maps <= 65535 && C / G == 16 &&
                     (int64_t)hw * (C / 8) < (1ll << 30);
-  if (fast)
+  if (stats_splits > 0) {
+    // first stage done by the producing convolution's epilogue (conv_roll.cu)
+  } else if (fast)
     gn_stats_bf16_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>((const __nv_bfloat16*)x, ldx, ws, hw, C, G, splits);
   else
     gn_stats_kernel<<<(unsigned)(maps * splits), kGnThreads, 0, ST>>>(x, x_dtype, ldx, ws, hw, C, G, splits);

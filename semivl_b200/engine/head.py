@@ -104,9 +104,10 @@ class HeadEngine:
         cout, ks = wt.shape[0], wt.shape[2]
         raw = torch.empty(nb * h * w, cout, device=x_act.device, dtype=torch.float32 if pr else torch.bfloat16)
         filt = _f3(dil) if ks == 3 else [(0, 0)]
-        ops.gemm(x_act, self._prep(p, wname, "conv"), raw, n=cout, k=cin, precise=pr, conv=(nb, h, w), filt=filt, b_row_stride=cout)
+        gs = dict(maps=nb, G=G)                 # the GroupNorm statistics come out of the convolution's epilogue where the library can (conv_roll)
+        ops.gemm(x_act, self._prep(p, wname, "conv"), raw, n=cout, k=cin, precise=pr, conv=(nb, h, w), filt=filt, b_row_stride=cout, gn_stats=gs)
         mean, rstd = ops.gn_relu_fwd(raw, L.dtype_of(raw), p[gname + ".weight"], p[gname + ".bias"], out_act, ops.act_dtype(pr), nb, h * w, cout, G,
-                                     out_col0=out_col0, res=res, res_dtype=ops.act_dtype(pr), save_stats=need_grad)
+                                     out_col0=out_col0, res=res, res_dtype=ops.act_dtype(pr), save_stats=need_grad, stats=gs)
         return dict(raw=raw, mean=mean, rstd=rstd) if need_grad else None
 
     def _conv_gn_bwd(self, S, dy, dy_dtype, dy_col0, x_act, nb, h, w, cin, wname, gname, G, p, grads, dil, dx_out, dx_dtype, accumulate=False):

@@ -42,7 +42,7 @@ class GemmDesc(C.Structure):
         ("act", C.c_int), ("preact_out", C.c_void_p), ("preact_dtype", C.c_int), ("ld_preact", C.c_int64),
         ("dact_src", C.c_void_p), ("dact_dtype", C.c_int), ("dact_kind", C.c_int), ("ld_dact", C.c_int64),
         ("residual", C.c_void_p), ("res_dtype", C.c_int), ("ldres", C.c_int64),
-        ("accumulate", C.c_int), ("block_n", C.c_int),
+        ("accumulate", C.c_int), ("block_n", C.c_int), ("gn_part", C.c_void_p),
     ]
 
 
@@ -63,6 +63,8 @@ _lib.svl_version.restype = C.c_int
 _lib.svl_check_device.restype = C.c_int
 _lib.svl_gemm.restype = C.c_int
 _lib.svl_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+_lib.svl_conv_gn_splits.restype = C.c_int
+_lib.svl_conv_gn_splits.argtypes = [C.POINTER(GemmDesc)]
 
 _lib.svl_attention_bwd_workspace.restype = C.c_size_t
 _lib.svl_attention_bwd_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -88,7 +90,7 @@ _PROTOS = {
     "svl_colsum": [_P, _I, _L, _L, _I, _P, _P],
     "svl_batch_sum": [_P, _P, _I, _L, _I, _P],
     "svl_axpy": [_P, _P, _F, _L, _P],
-    "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _F, _P],
+    "svl_gn_relu_fwd": [_P, _I, _L, _P, _P, _P, _I, _L, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     "svl_gn_relu_bwd": [_P, _I, _L, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _P],
     "svl_stem_im2col": [_P, _P, _I, _L, _I, _I, _I, _I, _I, _P],
     "svl_maxpool3s2_fwd": [_P, _I, _L, _P, _I, _L, _P, _I, _I, _I, _I, _I, _I, _P],

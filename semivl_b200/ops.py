@@ -5,6 +5,8 @@ Storage conventions (see svl_dtype):
   * precise mode : GEMM operands are split bf16 pairs [rows, 2C] (hi | lo) -> three tensor-core taps per contraction
 A `Mat` is just (tensor, split flag); weights are prepared once per step by `prep_weight`.
 """
+import ctypes as C
+
 import torch
 
 from . import lib as L
@@ -47,13 +49,15 @@ def _set_taps(d, taps):
 def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0, a_koff=0, out_dtype=None, ldc=None,
          bias=None, act=L.ACT_NONE, alpha=1.0, residual=None, preact_out=None, dact_src=None, dact_kind=L.ACT_NONE,
          dact_split=False, row_bias=None, row_bias_div=1, accumulate=False, out_mode=L.OUT_LINEAR, out_hw=None,
-         block_n=0, m=None, lda=None, a_cols=None, b_col0=0, a_map_w=0, taps=None, a_lo=None):
+         block_n=0, m=None, lda=None, a_cols=None, b_col0=0, a_map_w=0, taps=None, a_lo=None, gn_stats=None):
     """out = epilogue(sum_taps A_t @ B_t^T).
 
     a     : bf16 tensor; 2-D [M, lda] or (conv=(nb,h,w)) NHWC [nb,h,w,lda]; split (hi|lo) when precise
     b     : bf16 weights [b_rows, K] (or [b_rows, 2K] when precise)
     filt  : list of (dy, dx) pixel offsets for conv taps; tap t uses weight rows [t*b_row_stride, ...)
     k     : logical contraction length per tap;   a_koff: logical column offset into A
+    gn_stats: optional dict {'maps': .., 'G': ..}: when the library can produce the GroupNorm statistics of the output in this launch's epilogue
+            (svl_conv_gn_splits > 0) the dict receives 'ws' (partial sums) and 'splits' for gn_relu_fwd(stats=...)
     """
     d = L.GemmDesc()
     d.a = a.data_ptr()
@@ -101,6 +105,12 @@ def gemm(a, b, out, *, n, k, precise=False, conv=None, filt=None, b_row_stride=0
         d.residual, d.res_dtype, d.ldres = residual.data_ptr(), L.dtype_of(residual), residual.shape[-1]
     d.accumulate = 1 if accumulate else 0
     d.block_n = block_n
+    if gn_stats is not None and not precise and n == 16 * gn_stats["G"]:
+        splits = L.lib().svl_conv_gn_splits(C.byref(d))
+        if splits > 0:
+            gn_stats["ws"] = torch.empty(gn_stats["maps"] * splits * gn_stats["G"] * 2, device=out.device, dtype=torch.float32)
+            gn_stats["splits"] = splits
+            d.gn_part = gn_stats["ws"].data_ptr()
     _profiled(lambda: L.raw_gemm(d), 2.0 * d.m * n * k * len(taps), f"gemm m{d.m} n{n} k{k} taps{len(taps)} conv{d.a_conv} out{d.out_dtype} mode{d.out_mode}")
     return out
 
@@ -264,15 +274,17 @@ def attention_bwd(qkv, out, dout, lse, b, seq, heads, precise, dv_add=None, dv_a
 
 # ---------------------------------------------------------------------------------------------- head kernels
 def gn_relu_fwd(x, x_dtype, gamma, beta, out, out_dtype, maps, hw, C, G, *, ldx=None, ldo=None, out_col0=0, res=None, res_dtype=L.BF16,
-                ldres=None, save_stats=True, eps=1e-5):
+                ldres=None, save_stats=True, eps=1e-5, stats=None):
+    """stats: the dict a producing ops.gemm(gn_stats=...) filled ('ws', 'splits'): the statistics pass is skipped."""
     dev = x.device
     mean = torch.empty(maps, G, device=dev, dtype=torch.float32)
     rstd = torch.empty(maps, G, device=dev, dtype=torch.float32)
-    ws = torch.empty(L.lib().svl_gn_workspace(maps, hw, C, G), device=dev, dtype=torch.float32)     # fixed-order partial sums
+    fused = stats is not None and "ws" in stats
+    ws = stats["ws"] if fused else torch.empty(L.lib().svl_gn_workspace(maps, hw, C, G), device=dev, dtype=torch.float32)     # fixed-order partial sums
     L.call("svl_gn_relu_fwd", x, x_dtype, ldx if ldx is not None else x.shape[-1], gamma, beta,
            out.data_ptr() + out_col0 * out.element_size(), out_dtype, ldo if ldo is not None else out.shape[-1],
            res, res_dtype, (ldres if ldres is not None else (res.shape[-1] if res is not None else 0)), mean, rstd, ws, maps, hw, C, G, eps,
-           n_launch=3)
+           stats["splits"] if fused else 0, n_launch=2 if fused else 3)
     return mean, rstd
 
 

@@ -158,6 +158,20 @@ def test_implicit_conv(ops, nb, h, w, cin, cout, ks, dil, precise):
         assert _rel(out16, ref) < 6e-3
         ops.gemm(a, b, out16, n=cout, k=cin, conv=(nb, h, w), filt=filt, b_row_stride=cout, act=L.ACT_RELU)
         assert _rel(out16, (ref - bias).clamp_min(0)) < 6e-3
+        if cout in (32, 64, 128):
+            # GroupNorm statistics fused into the epilogue (conv_roll only: `ws` appears in the dict when the library takes that path):
+            # same mean / rstd / normalised output as the stand-alone statistics pass over the stored bf16 tensor
+            G = cout // 16
+            gs = dict(maps=nb, G=G)
+            ops.gemm(a, b, out16, n=cout, k=cin, conv=(nb, h, w), filt=filt, b_row_stride=cout, bias=bias, gn_stats=gs)
+            gamma, beta = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+            raw = out16.view(-1, cout)
+            y0, y1 = torch.empty_like(raw), torch.empty_like(raw)
+            m0, r0 = ops.gn_relu_fwd(raw, L.BF16, gamma, beta, y0, L.BF16, nb, h * w, cout, G)
+            m1, r1 = ops.gn_relu_fwd(raw, L.BF16, gamma, beta, y1, L.BF16, nb, h * w, cout, G, stats=gs)
+            assert ("ws" in gs) == (ks == 3 and dil == 1 and cout in (32, 64) and cin in (32, 64, 128) and (w <= 64 and w >= 33 or w >= 96))
+            assert (m0 - m1).abs().max() < 1e-5 * (1 + m0.abs().max()) and ((r0 - r1).abs() / r0).max() < 1e-4
+            assert (y0.float() - y1.float()).abs().max() <= 2e-2 * y0.float().abs().max()
 
 
 def test_convtranspose_scatter(ops):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(built):
     from semivl_b200 import lib as L
     assert L.version() == 100
     bound = set(L._PROTOS) | {"svl_gemm", "svl_wgrad", "svl_last_error", "svl_version", "svl_check_device", "svl_attention_bwd_workspace", "svl_gn_workspace",
-                                 "svl_bn_workspace"}
+                                 "svl_bn_workspace", "svl_conv_gn_splits"}
     assert names == bound, (names - bound, bound - names)
 
 

@@ -129,6 +129,13 @@ __device__ __forceinline__ void transpose_cells_8x4(float* o, int lane) {
   }
 }
 
+// CONVT2X2: element offset (relative to output pixel (2y, 2x), channel 0) of column `col`: quadrant q = col / cq goes to pixel
+// (2y + q / 2, 2x + q % 2), channel col % cq
+__device__ __forceinline__ int64_t convt_quadrant_offset(const GemmParams& p, int col, int cq) {
+  const int qq = col / cq, cc = col - qq * cq;
+  return ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
+}
+
 // Epilogue specialisations: the fully generic epilogue is ~8k instructions and starves the instruction cache (ncu: stall_no_inst
 // dominated, profiles/r01_gemm_epilogue.md), so the hot combinations are compiled with everything else pruned.
 //   OUT  : svl_dtype of the output            ACT : svl_act applied after bias
@@ -362,6 +369,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int r = q * 32 + lane;            // tile row of this thread
     const float alpha = p.alpha == 0.f ? 1.f : p.alpha;
     const int cq = p.out_mode == SVL_OUT_CONVT2X2 ? p.n / 4 : 0;
+    // one column block (the Up blocks' transposed convolutions): the quadrant offsets of this thread's four 16-column groups do not depend
+    // on the tile -- the two divisions per group were 40 % of the epilogue's instructions, and with one k-block per tile the epilogue IS the kernel
+    int64_t ct_qoff[2][2] = {{0, 0}, {0, 0}};
+    if (EXT == 1 && cq && p.num_n_tiles == 1) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = (((warp - 2) >> 2) + j * kEpiGroups) * 32 + g * 16;
+          if (col < p.n) ct_qoff[j][g] = convt_quadrant_offset(p, col, cq);
+        }
+    }
     int as = 0;
     uint32_t aphase = 0;
     const RowInBox rib = row_in_box(p, r);
@@ -756,8 +775,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int64_t off = (SVL_DBG(8) ? (grow & 1023) : grow) * p.ldc + col;
             if (SVL_DBG(32)) off = ((((int64_t)tile * 2 + j) * 2 + g) * 16 + (warp - 2)) * 512 + lane * 16;      // diag: every store instruction covers 1 KB contiguous
             if (EXT == 1) {                                  // cq % 16 == 0 is checked by the launcher for this variant
-              const int qq = col / cq, cc = col % cq;
-              off = ct_base + ((int64_t)(qq >> 1) * (2 * p.out_w) + (qq & 1)) * p.ldc + cc;
+              off = ct_base + (p.num_n_tiles == 1 ? ct_qoff[j][g] : convt_quadrant_offset(p, col, cq));
             }
             if (EXT == 3) {
               float sv[16];

@@ -124,8 +124,18 @@ class HeadEngine:
         if not staged:
             grads[wname].add_(dw.view(ks, ks, cout, cin).permute(2, 3, 0, 1))
         if dx_out is not None:
-            ops.gemm(d_raw, self._prep(p, wname, "conv_t"), dx_out, n=cin, k=cout, precise=pr, conv=(nb, h, w), filt=[(-a, -b) for a, b in filt],
-                     b_row_stride=cin, out_dtype=dx_dtype, accumulate=accumulate)
+            mirrored = [(-a, -b) for a, b in filt]
+            if (not pr and cin == 128 and cout in (32, 64) and ks == 3 and dil == 1 and not accumulate and dx_dtype == L.BF16 and
+                    dx_out.shape[-1] == cin and (33 <= w <= 64 or w >= 96)):
+                # 128 data-gradient channels = 3 x 128 accumulator columns per strip, more than one MMA holds: two 64-channel halves on the rolling
+                # convolution kernel (conv_roll.cu) instead of one launch of the generic engine (281 -> 2 x 97 us at config-2 size)
+                wt_t = self._prep(p, wname, "conv_t")                  # [(tap, ci), co]
+                for half in range(2):
+                    taps = [(fy, fx, 0, t * cin + half * 64, 0) for t, (fy, fx) in enumerate(mirrored)]
+                    ops.gemm(d_raw, wt_t, dx_out[:, half * 64:], n=64, k=cout, conv=(nb, h, w), taps=taps, out_dtype=dx_dtype, ldc=cin)
+            else:
+                ops.gemm(d_raw, self._prep(p, wname, "conv_t"), dx_out, n=cin, k=cout, precise=pr, conv=(nb, h, w), filt=mirrored,
+                         b_row_stride=cin, out_dtype=dx_dtype, accumulate=accumulate)
         return d_raw
 
     # ------------------------------------------------------------------ class-attention encoder layer (SemanticTransformer.transformer)

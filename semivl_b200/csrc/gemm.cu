@@ -106,29 +106,6 @@ __device__ __forceinline__ int64_t tile_row_to_global(const GemmParams& p, int m
   return ((int64_t)img * p.h + y) * p.w + x;
 }
 
-// Warp-local transpose of a 32-row x 32-word accumulator chunk (row per lane, 8 cells of 4 words) into the layout a coalesced
-// 128-bit access wants: afterwards lane l holds in cell j the words [4 (l >> 2), +4) of row 4 j + (l & 3), so instruction j of the warp
-// covers 4 rows x 128 contiguous bytes (4 L1 wavefronts) instead of 32 rows x 16 bytes (32 wavefronts).  Three butterfly stages, each
-// swapping lane bit 2 + s with cell bit s: 48 SHFL per chunk.
-__device__ __forceinline__ void transpose_cells_8x4(float* o, int lane) {
-#pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const bool hi = (lane >> (2 + s)) & 1;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      if (c & (1 << s)) continue;
-      const int c1 = c | (1 << s);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float send = hi ? o[c * 4 + k] : o[c1 * 4 + k];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 1 << (2 + s));
-        o[c * 4 + k] = hi ? recv : o[c * 4 + k];
-        o[c1 * 4 + k] = hi ? o[c1 * 4 + k] : recv;
-      }
-    }
-  }
-}
-
 // CONVT2X2: element offset (relative to output pixel (2y, 2x), channel 0) of column `col`: quadrant q = col / cq goes to pixel
 // (2y + q / 2, 2x + q % 2), channel col % cq
 __device__ __forceinline__ int64_t convt_quadrant_offset(const GemmParams& p, int col, int cq) {
@@ -142,7 +119,7 @@ __device__ __forceinline__ int64_t convt_quadrant_offset(const GemmParams& p, in
 //   PRE  : dtype of the saved pre-activation or -1         DACT: 0 none, 1 GELU' from a bf16 pre-activation
 //   RES  : dtype of the residual or -1        GEN : runtime-generic epilogue (all features, everything a runtime branch)
 //   EXT  : 0 linear output; 1 ConvT 2x2 scatter; 2 per-row-block bias (row_bias); 3 accumulate into an F32 output;
-//          4 F32 output + F32 residual through the warp-transposed (coalesced) path
+//          5 / 6 staged epilogues (per-quartet shared-memory buffers, TMA side-tile load and TMA store): F32 + F32 residual / BF16
 template <int OUT, int ACT, int PRE, int DACT, int RES, int EXT, bool GEN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
@@ -665,40 +642,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (c0 >= p.block_n || n0 + c0 >= p.n) break;
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c0), v);
-          if (EXT == 4) {
-            // out = acc * alpha + bias + residual, fp32 in / fp32 out (attention out-proj and FFN2 of the encoder): a row per lane would
-            // touch 32 lines per 128-bit access; transpose the chunk inside the warp, then every access is 4 rows x 128 contiguous bytes.
-            const int colT = n0 + c0 + (lane >> 2) * 4;
-            int64_t growT[8];
-            float4 resT[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              growT[jj] = __shfl_sync(0xffffffffu, grow, jj * 4 + (lane & 3));
-              resT[jj] = growT[jj] >= 0 && !SVL_DBG(4) ? *(const float4*)((const float*)p.residual + growT[jj] * p.ldres + colT) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            ptx::tmem_ld_wait();
-            if (j == 0 && warp == 2 && lane == 0) SVL_TRACE(tseq, 3);
-            float o[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]) * alpha;
-            if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 bb = __ldg((const float4*)(p.bias + n0 + c0) + i);
-                o[4 * i] += bb.x; o[4 * i + 1] += bb.y; o[4 * i + 2] += bb.z; o[4 * i + 3] += bb.w;
-              }
-            }
-            transpose_cells_8x4(o, lane);
-            if (j == 0 && warp == 2 && lane == 0) SVL_TRACE(tseq, 7);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              if (growT[jj] >= 0 && !SVL_DBG(1))
-                *(float4*)((float*)p.out + growT[jj] * p.ldc + colT) =
-                    make_float4(o[4 * jj] + resT[jj].x, o[4 * jj + 1] + resT[jj].y, o[4 * jj + 2] + resT[jj].z, o[4 * jj + 3] + resT[jj].w);
-            }
-            if (warp == 2 && lane == 0) SVL_TRACE(tseq, j == 0 ? 11 : 15);
-            continue;
-          }
           float side[2][16];
           if (RES >= 0 && grow >= 0 && !SVL_DBG(4)) {
 #pragma unroll
@@ -1077,13 +1020,7 @@ extern "C" int svl_gemm(const svl_gemm_desc* d, void* stream) {
   } else if (plain && no_extra && p.out_dtype == SVL_F32) {
     SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, -1, 0, false);
   } else if (plain && p.out_dtype == SVL_F32 && p.residual && p.res_dtype == SVL_F32 && !p.preact_out && !p.dact_src && p.act == SVL_ACT_NONE) {
-    static int transposed = -1;
-    if (transposed < 0) { const char* e = getenv("SVL_GEMM_TRANSPOSED_EPILOGUE"); transposed = e ? atoi(e) : 1; }     // =0: row-per-lane path (measured equal: these launches are DRAM / wave bound)
-    if (transposed && p.n % 32 == 0 && p.ldc % 4 == 0 && p.ldres % 4 == 0 && ((uintptr_t)p.out & 15) == 0 && ((uintptr_t)p.residual & 15) == 0 &&
-        (!p.bias || ((uintptr_t)p.bias & 15) == 0))
-      SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, SVL_F32, 4, false);
-    else
-      SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, SVL_F32, 0, false);
+    SVL_LAUNCH_GEMM(SVL_F32, SVL_ACT_NONE, -1, 0, SVL_F32, 0, false);      // register epilogue (SVL_GEMM_STAGED bit 0 off, or an unaligned problem)
   } else if (plain && p.out_dtype == SVL_BF16 && p.act == SVL_ACT_GELU && !p.dact_src && !p.residual &&
              (!p.preact_out || p.preact_dtype == SVL_BF16)) {
     if (p.preact_out) SVL_LAUNCH_GEMM(SVL_BF16, SVL_ACT_GELU, SVL_BF16, 0, -1, 0, false);

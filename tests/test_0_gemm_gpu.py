@@ -282,3 +282,43 @@ def test_optin_launch_modes_subprocess(env):
                         "plain_gemm or epilogue or ffn_epilogues or wgrad_linear"], env=dict(os.environ, **env), cwd=root, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout", [(1, 1, 33, 32, 32), (3, 2, 47, 64, 32), (2, 17, 64, 128, 64), (1, 33, 96, 32, 64), (3, 5, 127, 64, 64),
+                                             (1, 18, 129, 32, 32), (2, 3, 200, 128, 32), (1, 16, 257, 64, 32), (5, 31, 40, 32, 32),
+                                             (4, 16, 64, 64, 64)])
+def test_conv_roll_geometry_sweep(ops, nb, h, w, cin, cout):
+    """The rolling-accumulator convolution kernel (conv_roll.cu) on awkward geometries: single rows, odd map counts in the dual-map form, rows
+    that end inside a 128-pixel tile, units shorter than the ring, every channel combination -- output and fused GroupNorm statistics against
+    fp32 PyTorch on the bf16-rounded operands."""
+    from semivl_b200 import lib as L
+    g = torch.Generator(device="cuda").manual_seed(nb * 1000 + h * 10 + w + cin + cout)
+    x = _bf(torch.randn(nb, cin, h, w, device="cuda", generator=g)).float()
+    wt = _bf(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5).float()
+    ref = F.conv2d(x, wt, None, padding=1).permute(0, 2, 3, 1)
+    a = _bf(x.permute(0, 2, 3, 1).contiguous())
+    b = _bf(wt.permute(2, 3, 0, 1).reshape(9 * cout, cin))
+    filt = [(i - 1, j - 1) for i in range(3) for j in range(3)]
+    G = cout // 16
+    gs = dict(maps=nb, G=G)
+    out = torch.full((nb, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, n=cout, k=cin, conv=(nb, h, w), filt=filt, b_row_stride=cout, gn_stats=gs)
+    assert "ws" in gs, "this geometry should take the rolling kernel"
+    assert _rel(out, ref) < 6e-3
+    # the mirrored taps of the data gradient (weights [tap, ci, co]) through the same kernel
+    dy = _bf(torch.randn(nb, cout, h, w, device="cuda", generator=g)).float()
+    refd = F.conv_transpose2d(dy, wt, None, padding=1).permute(0, 2, 3, 1)
+    bt = _bf(wt.permute(2, 3, 1, 0).reshape(9 * cin, cout))
+    if cin in (32, 64):
+        dx = torch.full((nb, h, w, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(_bf(dy.permute(0, 2, 3, 1).contiguous()), bt, dx, n=cin, k=cout, conv=(nb, h, w), filt=[(-fy, -fx) for fy, fx in filt], b_row_stride=cin)
+        assert _rel(dx, refd) < 6e-3
+    # fused statistics == statistics of the stored tensor
+    stored = out.float().view(nb, h * w, G, 16)
+    mean_ref = stored.mean(dim=(1, 3))
+    var_ref = stored.var(dim=(1, 3), unbiased=False)
+    gamma, beta = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+    y = torch.empty(nb * h * w, cout, device="cuda", dtype=torch.bfloat16)
+    m1, r1 = ops.gn_relu_fwd(out.view(-1, cout), L.BF16, gamma, beta, y, L.BF16, nb, h * w, cout, G, stats=gs)
+    assert (m1 - mean_ref).abs().max() < 1e-5 * (1 + mean_ref.abs().max())
+    assert ((r1 - (var_ref + 1e-5).rsqrt()).abs() / r1).max() < 1e-3

@@ -457,3 +457,38 @@ def test_operand_index_maps_and_gradient_scatter_semantics(built):
     got = grad.clone().reshape(-1)
     got.index_add_(0, idx[keep].long(), dw1.reshape(-1)[keep])
     assert torch.allclose(got.view_as(grad), dw1[:, : ks * ks].reshape(C, 1, ks, ks))
+
+
+def test_conv_gn_splits_plan_through_the_c_abi(built):
+    """svl_conv_gn_splits() is pure host arithmetic on the descriptor (no CUDA call): the number of GroupNorm partial sums per map the rolling
+    convolution kernel writes depends on the map geometry only -- 16-row units x 128-pixel columns x 16 epilogue warps, or x 8 warps per map in
+    the dual-map form (maps up to 64 pixels wide) -- and is 0 for every problem the kernel does not take."""
+    from semivl_b200 import lib as L
+
+    def desc(nb, h, w, cin, cout, taps=9, dil=1, out_dtype=L.BF16, ldc=None):
+        d = L.GemmDesc()
+        d.a_conv, d.nb, d.h, d.w, d.m = 1, nb, h, w, nb * h * w
+        d.lda, d.ldb, d.b_rows = cin, cin, taps * cout
+        d.n, d.k_per_tap, d.num_taps = cout, cin, taps
+        k = 0
+        for i in range(3):
+            for j in range(3):
+                if k < taps:
+                    d.tap_dy[k], d.tap_dx[k], d.tap_b_row[k] = (i - 1) * dil, (j - 1) * dil, k * cout
+                    k += 1
+        d.out, d.out_dtype, d.ldc = 4096, out_dtype, ldc if ldc is not None else cout      # a fake, aligned pointer: nothing is dereferenced
+        return d
+
+    f = L.lib().svl_conv_gn_splits
+    assert f(ctypes.byref(desc(336, 128, 128, 32, 32))) == 8 * 1 * 16          # 8 units of 16 rows, one 128-pixel column
+    assert f(ctypes.byref(desc(5, 40, 204, 64, 64))) == 3 * 2 * 16             # 40 rows -> 3 units, 204 pixels -> 2 columns
+    assert f(ctypes.byref(desc(336, 64, 64, 128, 64))) == 4 * 8                # dual-map form: 4 units x 8 warps per map
+    assert f(ctypes.byref(desc(2, 7, 33, 32, 32))) == 1 * 8
+    assert f(ctypes.byref(desc(2, 64, 80, 32, 32))) == 0                       # 65..95-pixel rows stay on the generic engine
+    assert f(ctypes.byref(desc(2, 64, 32, 32, 32))) == 0                       # too narrow
+    assert f(ctypes.byref(desc(2, 64, 128, 32, 128))) == 0                     # 3 x 128 accumulator columns do not fit one MMA
+    assert f(ctypes.byref(desc(2, 64, 128, 32, 32, dil=2))) == 0               # dilated taps
+    assert f(ctypes.byref(desc(2, 64, 128, 32, 32, taps=4))) == 0
+    assert f(ctypes.byref(desc(2, 64, 128, 32, 32, out_dtype=L.F32))) == 0     # bf16 outputs only
+    # batch independence: the plan does not depend on the number of maps
+    assert f(ctypes.byref(desc(1, 128, 128, 64, 32))) == f(ctypes.byref(desc(300, 128, 128, 64, 32)))

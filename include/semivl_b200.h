@@ -166,8 +166,9 @@ int svl_cast(const void* src, int src_dtype, int64_t ld_src, int64_t src_batch_s
 /* Batched parameter jobs, one launch.  mode 0: refresh the GEMM-operand copies of the trainable weights after the optimizer step
  * (dst[i] = cast(src[idx[i]]), idx < 0 = zero padding; replaces the per-tensor reshape / permute / cast launches the reference's optimizer.step
  * + autocast would do, semivl.py:326-328).  mode 1: scatter staged weight gradients into the parameter layout (dst[idx[i]] += src[i]; src[i] = 0).
- * jobs: device int64 [njobs][5] = {src, dst, idx (int32*), n, flags (bit 0: f32 dst)}; block_start: device int32 [njobs + 1], first
- * 1024-element block of each job. */
+ * jobs: device int64 [njobs][5] = {src, dst, idx (int32*), n, flags}; flags bit 0: f32 dst; bit 1 (mode 0): the layout is the plain transpose of
+ * the parameter viewed as [R, n / R] with R = flags >> 8 (32 x 32 tiles, idx unused); block_start: device int32 [njobs + 1], first block of
+ * each job (a block = 1024 elements, or one 32 x 32 tile of a transpose job). */
 int svl_param_jobs(const void* jobs, const void* block_start, int njobs, int total_blocks, int mode, void* stream);
 /* out[col] += sum_rows x[row, col]  (bias gradients) */
 int svl_colsum(const void* x, int x_dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);

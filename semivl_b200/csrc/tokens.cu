@@ -650,7 +650,8 @@ extern "C" int svl_l2norm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
 // Batched parameter jobs: ONE launch refreshes every GEMM-operand copy of the trainable weights after the optimizer step (dst[i] =
 // cast(src[idx[i]]), idx < 0 = zero padding: any operand layout is a gather of the parameter) or scatters every staged weight gradient
 // back into the parameter layout (dst[idx[i]] += src[i]; src[i] = 0: the index maps are injective, no atomics).  A job row is
-// {src, dst, idx, n, flags} (flags bit 0: dst is f32 instead of bf16); block_start[j] = first 1024-element block of job j.
+// {src, dst, idx, n, flags} (flags bit 0: dst is f32 instead of bf16; bit 1: the layout is the 2-D transpose of the parameter viewed as
+// [flags >> 8, n / (flags >> 8)], handled in 32 x 32 tiles); block_start[j] = first block of job j (1024 elements or one tile each).
 __global__ void __launch_bounds__(256) param_jobs_kernel(const long long* __restrict__ jobs, const int* __restrict__ block_start, int njobs, int mode) {
   int lo = 0, hi = njobs;                                   // last job whose first block is <= blockIdx.x
   while (hi - lo > 1) {
@@ -661,6 +662,32 @@ __global__ void __launch_bounds__(256) param_jobs_kernel(const long long* __rest
   const long long n = J[3];
   const int* __restrict__ idx = (const int*)J[2];
   const long long base = (long long)((int)blockIdx.x - block_start[lo]) * 1024;
+  if (mode == 0 && (J[4] & 2)) {
+    // the operand is the plain 2-D transpose of the parameter viewed as [R, C] (data-gradient copies of the linear layers: half of all
+    // refreshed bytes): 32 x 32 tiles through shared memory, both sides coalesced, instead of a gather with a stride of C elements
+    __shared__ float tile[32][33];
+    const int R = (int)(J[4] >> 8), C = (int)(n / R);
+    const int tiles_c = (C + 31) / 32;
+    const int b = (int)blockIdx.x - block_start[lo], tr = b / tiles_c, tc = b - tr * tiles_c;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* __restrict__ src = (const float*)J[0];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = tr * 32 + ty + 8 * k, c = tc * 32 + tx;
+      tile[ty + 8 * k][tx] = (r < R && c < C) ? src[(long long)r * C + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = tc * 32 + ty + 8 * k, r = tr * 32 + tx;      // dst is [C, R]
+      if (c < C && r < R) {
+        const float v = tile[tx][ty + 8 * k];
+        if (J[4] & 1) ((float*)J[1])[(long long)c * R + r] = v;
+        else ((__nv_bfloat16*)J[1])[(long long)c * R + r] = __float2bfloat16(v);
+      }
+    }
+    return;
+  }
   if (mode == 0) {
     const float* __restrict__ src = (const float*)J[0];
     const bool f32 = J[4] & 1;

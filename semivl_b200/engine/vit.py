@@ -60,7 +60,14 @@ class WeightCache:
                 with torch.no_grad():
                     lay = layout_fn(param.detach().float()).contiguous()
                     dst = lay if raw_f32 else lay.to(torch.bfloat16)
-                    job = (param.data_ptr(), self._index_map(param, layout_fn)[0], dst, 1 if raw_f32 else 0, ver)
+                    idx = self._index_map(param, layout_fn)[0]
+                    flags = 1 if raw_f32 else 0
+                    if lay.dim() == 2:                       # the plain transpose of the parameter as [R, C]?  -> tiled path of the kernel
+                        C_, R_ = lay.shape
+                        k = torch.arange(idx.numel(), device=idx.device)
+                        if R_ > 1 and C_ > 1 and bool((idx.long() == (k % R_) * C_ + k // R_).all()):
+                            flags |= 2 | (R_ << 8)
+                    job = (param.data_ptr(), idx, dst, flags, ver)
                 self._jobs[key] = job
                 self._table = None
             return job[2]
@@ -91,7 +98,11 @@ class WeightCache:
             src, dst = (t.data_ptr(), ptr) if scatter else (ptr, t.data_ptr())
             rows.append([src, dst, idx.data_ptr(), idx.numel(), flags])
             starts.append(nb)
-            nb += (idx.numel() + 1023) // 1024
+            if not scatter and flags & 2:                   # one block per 32 x 32 tile
+                R_ = flags >> 8
+                nb += ((R_ + 31) // 32) * ((idx.numel() // R_ + 31) // 32)
+            else:
+                nb += (idx.numel() + 1023) // 1024
         dev = next(iter(jobs.values()))[1].device
         return (torch.tensor(rows, dtype=torch.int64).to(dev), torch.tensor(starts + [nb], dtype=torch.int32).to(dev), len(rows), nb)
 

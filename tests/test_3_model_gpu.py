@@ -498,3 +498,41 @@ def test_trainer_checkpoint_resume_and_weight_reload(text_dir):
     m3 = m3.cuda()
     l_want = Trainer(m3, OptimCfg()).supervised_step(imgs[0], masks[0], update=False).item()
     assert abs(l_new - l_want) < 1e-5 * abs(l_want) and abs(l_new - l_old) > 1e-6
+
+
+def test_operand_refresh_and_gradient_scatter_jobs():
+    """svl_param_jobs through WeightCache: after the parameter changes, ONE launch rewrites every registered operand copy (gather path, the
+    tiled-transpose path for non-multiple-of-32 shapes, fp32 and zero-padded layouts), and the staged-gradient scatter adds into the
+    parameter layout and re-zeroes the staging buffer."""
+    from semivl_b200 import lib as L
+    from semivl_b200.engine.head import HeadEngine
+    from semivl_b200.engine.vit import WeightCache
+    L.check_device()
+    g = torch.Generator().manual_seed(5)
+    cache = WeightCache()
+    cache.batched = True
+    params = {"a": torch.randn(70, 45, generator=g).cuda(), "b": torch.randn(64, 32, 3, 3, generator=g).cuda(), "c": torch.randn(8, 1, 5, 5, generator=g).cuda(),
+              "d": torch.randn(1, 32, 3, 3, generator=g).cuda()}
+    cache.volatile = set(params)
+    lays = {("a", "lin_t"): HeadEngine._layout("lin_t"), ("a", "lin"): HeadEngine._layout("lin"), ("b", "conv"): HeadEngine._layout("conv"),
+            ("b", "conv_t"): HeadEngine._layout("conv_t"), ("c", "conv1"): HeadEngine._layout("conv1"), ("d", "out1"): HeadEngine._layout("out1")}
+    ops_ = {k: cache.get_layout(k, params[k[0]], fn, False, raw_f32=k[1] == "out1") for k, fn in lays.items()}
+    assert cache._jobs[("a", "lin_t")][3] & 2 and not cache._jobs[("a", "lin")][3] & 2          # the transpose is recognised, the plain copy is not
+    for p in params.values():
+        p.data.mul_(-1.7).add_(0.3)                                # "optimizer step" behind the cache's back: `.data` edits keep the version counter
+    cache.refresh()
+    torch.cuda.synchronize()
+    for k, fn in lays.items():
+        want = fn(params[k[0]].float()).contiguous()
+        want = want if k[1] == "out1" else want.to(torch.bfloat16)
+        assert ops_[k].data_ptr() == cache.get_layout(k, params[k[0]], fn, False, raw_f32=k[1] == "out1").data_ptr()      # persistent tensors
+        assert torch.equal(ops_[k], want), k
+    # gradient scatter
+    grad = torch.randn(64, 32, 3, 3, generator=g).cuda()
+    g0 = grad.clone()
+    st = cache.grad_staging(("b", "conv"), grad, HeadEngine._layout("conv"))
+    dw = torch.randn(st.shape, generator=g).cuda()
+    st.copy_(dw)
+    cache.scatter_grads()
+    torch.cuda.synchronize()
+    assert torch.allclose(grad, g0 + dw.view(3, 3, 64, 32).permute(2, 3, 0, 1)) and float(st.abs().max()) == 0.0

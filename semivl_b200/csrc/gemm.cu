@@ -2,8 +2,14 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
-//   warps 2..9  : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global); warp w owns TMEM lane
-//                 quarter w % 4 and every other 32-column chunk
+//   warps 2..17 : epilogue (tcgen05.ld 32 lanes x 32 columns -> fused bias/act/act'/residual -> global); warp w owns TMEM lane
+//                 quarter w % 4 and the 32-column chunks (w - 2) / 4 and (w - 2) / 4 + 4: a QUARTET = the four warps of one chunk.
+//                 Staged variants (EXT 5 / 6): a quartet owns one shared-memory buffer; the side tile (residual, saved gelu') arrives by
+//                 TMA, is combined in place and leaves by TMA store (profiles/r02_gemm_epilogue.md)
+//
+// Measured anatomy of a K = 768 tile (profiles/r02_gemm_epilogue.md): the main loop alone needs 7.0k cycles (1500 TFLOP/s), bf16 output
+// stores add ~1.4k cycles to the MAIN LOOP whatever their pattern (library parity), the epilogues that move a second tile were latency
+// chains of 12-19k cycles before the staged variants.
 //
 // Tile order: M fastest (all concurrent CTAs share one B tile) unless the A operand is too large to stay in L2 between column
 // blocks; then N fastest: the concurrent CTAs cover (#SMs / n_tiles) row blocks x all column blocks, so each A row block comes from
@@ -147,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kblocks_per_tap = (p.k_per_tap + BK - 1) / BK;
   // Cluster mode (plain GEMMs): the two CTAs of a cluster take the row blocks 2s and 2s + 1 of the same column block in lockstep; each
   // loads its own A tile and HALF of the B tile, multicast into both CTAs, so a CTA pulls 32 KB instead of 48 KB per k-block through
-  // L2 -> SMEM (the wide GEMMs run at the ~6300 B/clk L2 ceiling otherwise, profiles/README.md).  A stage is free when BOTH CTAs have
+  // L2 -> SMEM.  A stage is free when BOTH CTAs have
   // consumed it (the peer's multicast writes into this CTA's copy), hence the 2-arrival empty barriers and the multicast commits.
   const int crank = p.cluster ? (int)ptx::cluster_ctarank() : 0;
   constexpr bool pair = PAIR;                  // cta_group::2 code only exists in the PAIR instantiations (they must be launched as clusters)
